@@ -1,0 +1,174 @@
+/* phyloacc_b200.h -- C ABI of the B200-native PhyloAcc-ST engine (libphyloacc_b200.so).
+ *
+ * The reference has no in-process plugin / FFI: its seam is the OpenMP element loop of
+ * src/PhyloAcc-ST/main.cpp:452-500, which owns one BPP_C per element, reads the shared
+ * immutable batch model `BPP` and writes per-element slots of it.  This header is the C
+ * surface a maintainer would bind at that seam; every entry point
+ * names the reference code it replaces (paths relative to src/PhyloAcc-ST/).
+ *
+ * Conventions: plain pointers and sizes, caller-allocated outputs, no exceptions across
+ * the boundary; every function returns PA_OK (0) or a negative error code and leaves a
+ * message retrievable with pa_last_error() (thread-local).  A handle is bound to one CUDA
+ * device; calls on one handle must be serialised by the caller, different handles are
+ * independent.  There is NO CPU fallback: entry points that compute fail with
+ * PA_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PHYLOACC_B200_H
+#define PHYLOACC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_OK 0
+#define PA_ERR_ARG (-1)      /* bad argument / malformed input (reference: exit(1) paths, main.cpp:112,129,162) */
+#define PA_ERR_CUDA (-2)     /* CUDA runtime error or no usable device */
+#define PA_ERR_STATE (-3)    /* call order violated (e.g. run before load) */
+#define PA_ERR_IO (-4)       /* file could not be read / written */
+#define PA_ERR_LIMIT (-5)    /* problem exceeds a compiled-in limit (tree too large for shared memory, ...) */
+
+/* model indices follow the reference's resZ (main.cpp:466-494): the ORDER of slots in every
+ * per-model array of this header is M0, M1, M2 = resZ 0, 2, 1. */
+#define PA_M0 0  /* null:  resZ = 0 */
+#define PA_M1 1  /* accelerated only in non-conserved, non-outgroup clades: resZ = 2 */
+#define PA_M2 2  /* full:  resZ = 1 */
+
+typedef struct pa_engine pa_engine;
+
+/* Tree in the reference's numbering (newick.cpp:382-400, bpp.cpp:84-117): leaves 0..S-1,
+ * internal nodes S..N-1 in post-order, root = N-1, N = 2S-1; children ordered by node id. */
+typedef struct pa_tree {
+  int32_t S, N;
+  const int32_t* parent;    /* [N], -1 for the root */
+  const int32_t* children;  /* [N][2], -1 for leaves */
+  const double* distances;  /* [N] branch length above each node, already passed through float (newick.cpp:185) */
+} pa_tree;
+
+/* PhyloTree.pi / PhyloTree.subs_rate (newick.h); Q rows are "from", columns "to" */
+typedef struct pa_subst {
+  double pi[4];
+  double Q[16];
+} pa_subst;
+
+/* Numeric engine parameters, defaults = main.cpp:49-90 (use pa_params_default). */
+typedef struct pa_params {
+  int32_t seed;                                   /* SEED */
+  double init_conserve_rate, init_acce_rate;      /* INIT_CONSERVE_RATE, INIT_ACCE_RATE (ratio0, ratio1) */
+  double conserve_prior_a, conserve_prior_b;      /* CONSERVE_PRIOR_A/B */
+  double acce_prior_a, acce_prior_b;              /* ACCE_PRIOR_A/B */
+  int32_t ropt;                                   /* ROPT */
+  double cub, nlb;                                /* CUB, NLB */
+  int32_t burnin, mcmc, adapt_freq;               /* BURNIN, MCMC, ADAPT_FREQ */
+  double init_lrate, init_lrate2, init_grate;     /* INIT_LRATE, INIT_LRATE2, INIT_GRATE */
+  double hyper_lrate_a, hyper_lrate_b;            /* HYPER_LRATE_A/B */
+  double hyper_grate_a, hyper_grate_b;            /* HYPER_GRATE_A/B */
+  double hyper_lrate2_a, hyper_lrate2_b;          /* HYPER_LRATE2_A/B (A == 0: Dollo, main.cpp:286) */
+  double conserve_prop, gap_prop, constomis;      /* CONSERVE_PROP, GAP_PROP, CONSTOMIS */
+  char gapchar;                                   /* GAPCHAR */
+  int32_t prune_tree;                             /* PRUNE_TREE */
+  double trim_gap_percent;                        /* TRIM_GAP_PERCENT */
+  int32_t min_len;                                /* MIN_LEN */
+  int32_t n_outgroup;  const int32_t* outgroup;   /* OUTGROUP species as leaf ids (bpp.hpp:303-309); id S = "name not found" */
+  int32_t n_conserve;  const int32_t* conserve;   /* CONSERVE species as leaf ids (bpp.hpp:237-242) */
+  int32_t num_thread;                             /* NUM_THREAD: host threads for the integer front-end and Eval2 */
+} pa_params;
+
+void pa_params_default(pa_params* p);
+
+/* Per-element summaries = what the reference stores in bpp.log_liks_* / Max_Z (Gibbs bpp_c.cpp:470-471,
+ * Eval2 bpp_c2.cpp:332-349) and prints in Output_init (bpp_c2.cpp:739-785).  All arrays are caller-allocated,
+ * indexed [i] over the ids passed to pa_engine_run; model slot order M0, M1, M2. */
+typedef struct pa_results {
+  int32_t n;                /* capacity (>= number of ids) */
+  int32_t N;                /* nodes per tree (row length of the Z arrays) */
+  uint8_t* filtered;        /* [n] 1 if the element was filtered by the front-end (bpp_c.hpp:158,288,369) */
+  double* loglik;           /* [n][3] marginal log-likelihood estimates (log_liks_null / resZ / sgl) */
+  double* loglik_max;       /* [n][3] MaxLoglik (log_liks_Z) */
+  int8_t* max_Z;            /* [n][3][N] Max_Z, -1 for pruned nodes */
+  double* median_rates;     /* [n][3][5] posterior medians n, c, g, l, l2 over the FULL trace (bpp_c2.cpp:742-755) */
+  double* post_Z;           /* [n][3][N][4] frequencies of Z = -1,0,1,2 over post-burn-in samples (bpp_c2.cpp:757-781) */
+} pa_results;
+
+/* Raw MCMC traces of one chain (Output_sampling, bpp_c2.cpp:706-736); T = burnin + mcmc rows. */
+typedef struct pa_trace {
+  int32_t T, N;
+  double* loglik; double* n_rate; double* c_rate; double* g_rate; double* l_rate; double* l2_rate;  /* [T] each */
+  int8_t* Z;                /* [T][N] */
+} pa_trace;
+
+/* Integer front-end of one element (BPP_C::BPP_C, bpp_c.hpp:143-476) for parity tests. Caller-allocated:
+ * missing/children2/parent2/distances2/nodes sized N (children2 2N); codes sized S*GG_max, weights/site_pattern GG_max. */
+typedef struct pa_element_info {
+  int32_t filtered, GG, P, root, n_nodes;
+  uint8_t* missing; int32_t* nodes; int32_t* children2; int32_t* parent2; double* distances2;
+  uint8_t* pattern_codes;   /* [P][S] nibble masks of the unique columns, sorted lexicographically */
+  int32_t* pattern_weights; /* [P] */
+  int32_t* site_pattern;    /* [GG] pattern index of every kept column, original column order */
+  uint8_t* fixZ;            /* [3][N]: 1 where fixZ == 1 for M0, M1, M2 (initMCMC bpp_c.cpp:155-161,240-289) */
+} pa_element_info;
+
+const char* pa_last_error(void);
+const char* pa_version(void);
+
+/* BPP::BPP + BPP::InitMCMC (bpp.hpp:173-404, bpp.cpp:186-224): tree arrays, eigensystem of Q, upper sets.
+ * device < 0: do not touch CUDA (front-end only; compute entry points will fail with PA_ERR_CUDA). */
+int pa_engine_create(const pa_tree* tree, const pa_subst* subst, const pa_params* params, int device, pa_engine** out);
+void pa_engine_destroy(pa_engine* e);
+
+/* Launch stream for all device work of this handle (a cudaStream_t; NULL = default stream). */
+int pa_engine_set_stream(pa_engine* e, void* cuda_stream);
+
+/* PhyloProf.X + element_start/size (profile.cpp:17-126, bpp.hpp:257-274) followed by the integer part of
+ * BPP_C::BPP_C for every element: tip encoding, column trimming, missing species, filters, pruned tree
+ * (bpp_c.hpp:143-476), then site-pattern compression (new stage) and upload of the packed batch to HBM.
+ * X is [S][G] row-major lower-case characters in TREE leaf order (rows already matched, bpp.cpp:133-184). */
+int pa_engine_load_alignment(pa_engine* e, const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len);
+
+int pa_engine_num_elements(const pa_engine* e);
+int pa_engine_element_info(const pa_engine* e, int32_t elem, pa_element_info* out);
+
+/* Replayed log-likelihoods: for each state i, log P(X_elem | Z, n_rate, c_rate) exactly as the reference
+ * evaluates it after initMCMC (bpp_c.cpp:131-236) + Update_Tg(.,.,false) (bpp_c.cpp:647-671) +
+ * sum_g log_exp_sum(lambda[g][root]).  Z is [n_states][N] in original node numbering (-1 for pruned nodes). */
+int pa_engine_loglik_replay(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate,
+                            const double* c_rate, double* loglik_out);
+
+/* The element loop of main.cpp:452-500: for every id, M0 -> M1 -> M2 chains (initMCMC, Gibbs, Eval2,
+ * Output_init).  pa_engine_sample launches the on-device chains asynchronously on the handle's stream
+ * (traces stay in HBM); pa_engine_collect synchronises, runs Eval2 / summaries and fills `out`.
+ * pa_engine_run = sample + collect. */
+int pa_engine_sample(pa_engine* e, const int32_t* ids, int32_t n_ids);
+int pa_engine_collect(pa_engine* e, pa_results* out);
+int pa_engine_run(pa_engine* e, const int32_t* ids, int32_t n_ids, pa_results* out);
+
+/* Trace of one chain of the last pa_engine_sample (i = position in ids, model = PA_M0..PA_M2). */
+int pa_engine_get_trace(pa_engine* e, int32_t i, int32_t model, pa_trace* out);
+
+/* Work counters of the last pa_engine_sample, for the roofline: node-pattern updates,
+ * root evaluations, P(t) builds, history draws, kernel launches. */
+typedef struct pa_counters {
+  uint64_t node_pattern_updates, root_evals, pt_builds, history_draws, chain_iterations, kernel_launches;
+} pa_counters;
+int pa_engine_counters(pa_engine* e, pa_counters* out);
+
+/* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
+ * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
+int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);
+/* Borrowed views of what the parsers produced (valid until the handle is destroyed). */
+int pa_engine_get_tree(const pa_engine* e, pa_tree* tree_out, pa_subst* subst_out);
+const char* pa_engine_node_name(const pa_engine* e, int32_t node);
+const char* pa_engine_element_name(const pa_engine* e, int32_t elem);
+int pa_engine_get_ids(const pa_engine* e, const int32_t** ids_out, int32_t* n_out);
+int pa_engine_get_params(const pa_engine* e, pa_params* out);
+
+/* Whole-program entry = main() of the reference (main.cpp:324-528): parameter file in, result files out
+ * (<prefix>_elem_lik.txt, _rate_postZ_M{0,1,2}.txt, _M{0,1,2}_elem_Z.txt, _hyper.txt, _species_names.txt,
+ * optional _mcmc_trace_M*_*.txt) and the "time used:" log line. */
+int pa_run_from_config(const char* cfg_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

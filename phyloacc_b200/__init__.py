@@ -1,0 +1,332 @@
+"""phyloacc_b200 -- B200-native engine for PhyloAcc's per-element MCMC hot path (PhyloAcc-ST).
+
+This package is a thin ctypes binding of the C ABI in ``include/phyloacc_b200.h`` (libphyloacc_b200.so, built
+in-tree by ``phyloacc_b200.build``).  All arithmetic of the hot path runs in hand-written sm_100a CUDA kernels;
+there is no CPU fallback and importing this module never touches ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = _build.LIB
+BIN_PATH = _build.BIN
+
+PA_OK = 0
+M0, M1, M2 = 0, 1, 2
+MODEL_RESZ = {M0: 0, M1: 2, M2: 1}  # model slot -> reference's resZ (main.cpp:466-494)
+
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+_i8p = C.POINTER(C.c_int8)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class PaTree(C.Structure):
+    _fields_ = [("S", C.c_int32), ("N", C.c_int32), ("parent", _i32p), ("children", _i32p), ("distances", _f64p)]
+
+
+class PaSubst(C.Structure):
+    _fields_ = [("pi", C.c_double * 4), ("Q", C.c_double * 16)]
+
+
+class PaParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_int32), ("init_conserve_rate", C.c_double), ("init_acce_rate", C.c_double),
+        ("conserve_prior_a", C.c_double), ("conserve_prior_b", C.c_double), ("acce_prior_a", C.c_double), ("acce_prior_b", C.c_double),
+        ("ropt", C.c_int32), ("cub", C.c_double), ("nlb", C.c_double),
+        ("burnin", C.c_int32), ("mcmc", C.c_int32), ("adapt_freq", C.c_int32),
+        ("init_lrate", C.c_double), ("init_lrate2", C.c_double), ("init_grate", C.c_double),
+        ("hyper_lrate_a", C.c_double), ("hyper_lrate_b", C.c_double), ("hyper_grate_a", C.c_double), ("hyper_grate_b", C.c_double),
+        ("hyper_lrate2_a", C.c_double), ("hyper_lrate2_b", C.c_double),
+        ("conserve_prop", C.c_double), ("gap_prop", C.c_double), ("constomis", C.c_double),
+        ("gapchar", C.c_char), ("prune_tree", C.c_int32), ("trim_gap_percent", C.c_double), ("min_len", C.c_int32),
+        ("n_outgroup", C.c_int32), ("outgroup", _i32p), ("n_conserve", C.c_int32), ("conserve", _i32p),
+        ("num_thread", C.c_int32),
+    ]
+
+
+class PaResults(C.Structure):
+    _fields_ = [("n", C.c_int32), ("N", C.c_int32), ("filtered", _u8p), ("loglik", _f64p), ("loglik_max", _f64p),
+                ("max_Z", _i8p), ("median_rates", _f64p), ("post_Z", _f64p)]
+
+
+class PaTrace(C.Structure):
+    _fields_ = [("T", C.c_int32), ("N", C.c_int32), ("loglik", _f64p), ("n_rate", _f64p), ("c_rate", _f64p),
+                ("g_rate", _f64p), ("l_rate", _f64p), ("l2_rate", _f64p), ("Z", _i8p)]
+
+
+class PaElementInfo(C.Structure):
+    _fields_ = [("filtered", C.c_int32), ("GG", C.c_int32), ("P", C.c_int32), ("root", C.c_int32), ("n_nodes", C.c_int32),
+                ("missing", _u8p), ("nodes", _i32p), ("children2", _i32p), ("parent2", _i32p), ("distances2", _f64p),
+                ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p)]
+
+
+class PaCounters(C.Structure):
+    _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
+                ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
+
+
+EXPORTS = [
+    "pa_last_error", "pa_version", "pa_params_default", "pa_engine_create", "pa_engine_destroy", "pa_engine_set_stream",
+    "pa_engine_load_alignment", "pa_engine_num_elements", "pa_engine_element_info", "pa_engine_loglik_replay",
+    "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters",
+    "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
+    "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config",
+]
+
+_lib = None
+
+
+class PhyloAccError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"phyloacc_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen the native library; fails loudly (no fallback) when it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m phyloacc_b200.build` (there is no CPU fallback)")
+        _build.build_native()
+    lib = C.CDLL(LIB_PATH)
+    lib.pa_last_error.restype = C.c_char_p
+    lib.pa_version.restype = C.c_char_p
+    lib.pa_params_default.argtypes = [C.POINTER(PaParams)]
+    lib.pa_params_default.restype = None
+    lib.pa_engine_create.argtypes = [C.POINTER(PaTree), C.POINTER(PaSubst), C.POINTER(PaParams), C.c_int, C.POINTER(C.c_void_p)]
+    lib.pa_engine_destroy.argtypes = [C.c_void_p]
+    lib.pa_engine_destroy.restype = None
+    lib.pa_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.pa_engine_load_alignment.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, _i64p, _i32p]
+    lib.pa_engine_num_elements.argtypes = [C.c_void_p]
+    lib.pa_engine_element_info.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PaElementInfo)]
+    lib.pa_engine_loglik_replay.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _f64p, _f64p, _f64p]
+    lib.pa_engine_sample.argtypes = [C.c_void_p, _i32p, C.c_int32]
+    lib.pa_engine_collect.argtypes = [C.c_void_p, C.POINTER(PaResults)]
+    lib.pa_engine_run.argtypes = [C.c_void_p, _i32p, C.c_int32, C.POINTER(PaResults)]
+    lib.pa_engine_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PaTrace)]
+    lib.pa_engine_counters.argtypes = [C.c_void_p, C.POINTER(PaCounters)]
+    lib.pa_engine_create_from_config.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.pa_engine_get_tree.argtypes = [C.c_void_p, C.POINTER(PaTree), C.POINTER(PaSubst)]
+    lib.pa_engine_node_name.argtypes = [C.c_void_p, C.c_int32]
+    lib.pa_engine_node_name.restype = C.c_char_p
+    lib.pa_engine_element_name.argtypes = [C.c_void_p, C.c_int32]
+    lib.pa_engine_element_name.restype = C.c_char_p
+    lib.pa_engine_get_ids.argtypes = [C.c_void_p, C.POINTER(_i32p), _i32p]
+    lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
+    lib.pa_run_from_config.argtypes = [C.c_char_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != PA_OK:
+        raise PhyloAccError(rc, load_library().pa_last_error().decode(errors="replace"))
+
+
+def default_params() -> PaParams:
+    p = PaParams()
+    load_library().pa_params_default(C.byref(p))
+    return p
+
+
+class Results:
+    """numpy view of pa_results for n elements on an N-node tree."""
+
+    def __init__(self, n: int, N: int):
+        self.n, self.N = n, N
+        self.filtered = np.zeros(n, dtype=np.uint8)
+        self.loglik = np.zeros((n, 3))
+        self.loglik_max = np.zeros((n, 3))
+        self.max_Z = np.zeros((n, 3, N), dtype=np.int8)
+        self.median_rates = np.zeros((n, 3, 5))
+        self.post_Z = np.zeros((n, 3, N, 4))
+        s = PaResults()
+        s.n, s.N = n, N
+        s.filtered = self.filtered.ctypes.data_as(_u8p)
+        s.loglik = self.loglik.ctypes.data_as(_f64p)
+        s.loglik_max = self.loglik_max.ctypes.data_as(_f64p)
+        s.max_Z = self.max_Z.ctypes.data_as(_i8p)
+        s.median_rates = self.median_rates.ctypes.data_as(_f64p)
+        s.post_Z = self.post_Z.ctypes.data_as(_f64p)
+        self.struct = s
+
+    @property
+    def logBF1(self):  # bpp.cpp:579
+        return self.loglik[:, M1] - self.loglik[:, M0]
+
+    @property
+    def logBF2(self):
+        return self.loglik[:, M1] - self.loglik[:, M2]
+
+
+class Engine:
+    """One pa_engine handle.  Mirrors the reference's BPP (batch model) + the element loop of main.cpp:452-500."""
+
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        self._lib = load_library()
+        t, s = PaTree(), PaSubst()
+        _check(self._lib.pa_engine_get_tree(self._h, C.byref(t), C.byref(s)))
+        self.S, self.N = t.S, t.N
+        self.parent = np.ctypeslib.as_array(t.parent, shape=(self.N,)).copy()
+        self.children = np.ctypeslib.as_array(t.children, shape=(self.N, 2)).copy()
+        self.distances = np.ctypeslib.as_array(t.distances, shape=(self.N,)).copy()
+        self.pi = np.array(list(s.pi))
+        self.Q = np.array(list(s.Q)).reshape(4, 4)
+
+    # ---- construction
+    @classmethod
+    def create(cls, parent, children, distances, pi, Q, params: Optional[PaParams] = None, outgroup: Sequence[int] = (),
+               conserve: Sequence[int] = (), device: int = 0) -> "Engine":
+        lib = load_library()
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        children = np.ascontiguousarray(children, dtype=np.int32)
+        distances = np.ascontiguousarray(distances, dtype=np.float64)
+        N = parent.shape[0]
+        t = PaTree((N + 1) // 2, N, parent.ctypes.data_as(_i32p), children.ctypes.data_as(_i32p), distances.ctypes.data_as(_f64p))
+        s = PaSubst()
+        s.pi[:] = list(map(float, pi))
+        s.Q[:] = list(map(float, np.asarray(Q).reshape(-1)))
+        p = params if params is not None else default_params()
+        og = np.ascontiguousarray(outgroup, dtype=np.int32)
+        cg = np.ascontiguousarray(conserve, dtype=np.int32)
+        p.n_outgroup, p.outgroup = len(og), og.ctypes.data_as(_i32p)
+        p.n_conserve, p.conserve = len(cg), cg.ctypes.data_as(_i32p)
+        h = C.c_void_p()
+        _check(lib.pa_engine_create(C.byref(t), C.byref(s), C.byref(p), device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_config(cls, cfg_path: str, device: int = 0) -> "Engine":
+        lib = load_library()
+        h = C.c_void_p()
+        _check(lib.pa_engine_create_from_config(cfg_path.encode(), device, C.byref(h)))
+        return cls(h.value)
+
+    def close(self):
+        if self._h:
+            self._lib.pa_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- data
+    def set_stream(self, cuda_stream: int):
+        _check(self._lib.pa_engine_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def load_alignment(self, X: np.ndarray, elem_start, elem_len):
+        """X: uint8 [S, G] lower-case characters in tree-leaf order."""
+        X = np.ascontiguousarray(X, dtype=np.uint8)
+        es = np.ascontiguousarray(elem_start, dtype=np.int64)
+        el = np.ascontiguousarray(elem_len, dtype=np.int32)
+        assert X.shape[0] == self.S
+        _check(self._lib.pa_engine_load_alignment(self._h, X.ctypes.data_as(C.c_void_p), X.shape[1], len(el),
+                                                  es.ctypes.data_as(_i64p), el.ctypes.data_as(_i32p)))
+
+    @property
+    def num_elements(self) -> int:
+        return self._lib.pa_engine_num_elements(self._h)
+
+    def node_names(self) -> List[str]:
+        return [self._lib.pa_engine_node_name(self._h, i).decode() for i in range(self.N)]
+
+    def element_name(self, c: int) -> str:
+        return self._lib.pa_engine_element_name(self._h, c).decode()
+
+    def ids(self) -> np.ndarray:
+        p, n = _i32p(), C.c_int32()
+        _check(self._lib.pa_engine_get_ids(self._h, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, dtype=np.int32)
+
+    def params(self) -> PaParams:
+        p = PaParams()
+        _check(self._lib.pa_engine_get_params(self._h, C.byref(p)))
+        return p
+
+    def element_info(self, c: int, gg_max: int = 4096):
+        N, S = self.N, self.S
+        bufs = dict(missing=np.zeros(N, np.uint8), nodes=np.zeros(N, np.int32), children2=np.zeros((N, 2), np.int32),
+                    parent2=np.zeros(N, np.int32), distances2=np.zeros(N), pattern_codes=np.zeros((gg_max, S), np.uint8),
+                    pattern_weights=np.zeros(gg_max, np.int32), site_pattern=np.zeros(gg_max, np.int32), fixZ=np.zeros((3, N), np.uint8))
+        info = PaElementInfo()
+        info.missing = bufs["missing"].ctypes.data_as(_u8p)
+        info.nodes = bufs["nodes"].ctypes.data_as(_i32p)
+        info.children2 = bufs["children2"].ctypes.data_as(_i32p)
+        info.parent2 = bufs["parent2"].ctypes.data_as(_i32p)
+        info.distances2 = bufs["distances2"].ctypes.data_as(_f64p)
+        info.pattern_codes = bufs["pattern_codes"].ctypes.data_as(_u8p)
+        info.pattern_weights = bufs["pattern_weights"].ctypes.data_as(_i32p)
+        info.site_pattern = bufs["site_pattern"].ctypes.data_as(_i32p)
+        info.fixZ = bufs["fixZ"].ctypes.data_as(_u8p)
+        _check(self._lib.pa_engine_element_info(self._h, c, C.byref(info)))
+        out = dict(filtered=bool(info.filtered), GG=info.GG, P=info.P, root=info.root, n_nodes=info.n_nodes)
+        if not out["filtered"]:
+            out.update(missing=bufs["missing"].astype(bool), nodes=bufs["nodes"][:info.n_nodes].tolist(), children2=bufs["children2"],
+                       parent2=bufs["parent2"], distances2=bufs["distances2"], pattern_codes=bufs["pattern_codes"][:info.P],
+                       pattern_weights=bufs["pattern_weights"][:info.P], site_pattern=bufs["site_pattern"][:info.GG], fixZ=bufs["fixZ"])
+        return out
+
+    # ---- compute (CUDA only)
+    def loglik_replay(self, elem, Z, n_rate, c_rate) -> np.ndarray:
+        elem = np.ascontiguousarray(elem, dtype=np.int32)
+        Z = np.ascontiguousarray(Z, dtype=np.int8).reshape(len(elem), self.N)
+        nr = np.ascontiguousarray(n_rate, dtype=np.float64)
+        cr = np.ascontiguousarray(c_rate, dtype=np.float64)
+        out = np.zeros(len(elem))
+        _check(self._lib.pa_engine_loglik_replay(self._h, len(elem), elem.ctypes.data_as(_i32p), Z.ctypes.data_as(_i8p),
+                                                 nr.ctypes.data_as(_f64p), cr.ctypes.data_as(_f64p), out.ctypes.data_as(_f64p)))
+        return out
+
+    def sample(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._last_ids = ids
+        _check(self._lib.pa_engine_sample(self._h, ids.ctypes.data_as(_i32p), len(ids)))
+
+    def collect(self) -> Results:
+        res = Results(len(self._last_ids), self.N)
+        _check(self._lib.pa_engine_collect(self._h, C.byref(res.struct)))
+        return res
+
+    def run(self, ids) -> Results:
+        self.sample(ids)
+        return self.collect()
+
+    def trace(self, i: int, model: int):
+        p = self.params()
+        T, N = p.burnin + p.mcmc, self.N
+        b = dict(loglik=np.zeros(T), n_rate=np.zeros(T), c_rate=np.zeros(T), g_rate=np.zeros(T), l_rate=np.zeros(T),
+                 l2_rate=np.zeros(T), Z=np.zeros((T, N), np.int8))
+        t = PaTrace()
+        t.T, t.N = T, N
+        for k in ("loglik", "n_rate", "c_rate", "g_rate", "l_rate", "l2_rate"):
+            setattr(t, k, b[k].ctypes.data_as(_f64p))
+        t.Z = b["Z"].ctypes.data_as(_i8p)
+        _check(self._lib.pa_engine_get_trace(self._h, i, model, C.byref(t)))
+        return b
+
+    def counters(self) -> dict:
+        c = PaCounters()
+        _check(self._lib.pa_engine_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in PaCounters._fields_}
+
+
+def run_from_config(cfg_path: str) -> int:
+    """main() of the reference (main.cpp:324-528)."""
+    return load_library().pa_run_from_config(cfg_path.encode())

@@ -1,0 +1,20 @@
+// pa_chain.cuh -- on-device Gibbs/MH chain kernel (declared here, defined in pa_chain.cu).
+#ifndef PA_CHAIN_CUH
+#define PA_CHAIN_CUH
+#include "pa_internal.h"
+namespace pa {
+struct ChainLaunch {
+  const uint8_t* blobs; const int64_t* blob_off;
+  const int32_t* chain_list;  // [n_chains][2]
+  int n_chains;
+  SubstDev sd; ChainParams cp;
+  int n_max, slots_max, P_max, T, ZW;
+  double* trace_d; uint32_t* trace_z;
+  uint8_t* arena; size_t arena_stride;
+  unsigned long long* counters; int* queue;
+};
+size_t chain_smem_bytes(int n_max, int slots_max, int BD);
+size_t chain_arena_bytes(int n_max, int P_max);
+int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
+}  // namespace pa
+#endif

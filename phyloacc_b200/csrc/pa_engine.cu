@@ -1,0 +1,233 @@
+// pa_engine.cu -- the engine object behind the C ABI: batch upload, replay kernel, chain kernel launch,
+// trace collection.  Kernels are written for sm_100a (B200): fp64 pruning over compressed site patterns,
+// P(t) from the shared eigensystem, one CTA per chain with partials resident in L2.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "pa_chain.cuh"
+#include "pa_device.cuh"
+#include "pa_engine.h"
+#include "pa_internal.h"
+
+namespace pa {
+
+#define PA_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess) {                                                                    \
+      set_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #call);          \
+      return PA_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ replay kernel
+// One CTA per (element, Z, n_rate, c_rate) state: builds P(t) for every branch from its class, prunes every
+// pattern with the shared-memory temp stack only (no global partials) and reduces sum_p w_p log L_p.
+__global__ void __launch_bounds__(128) replay_kernel(const uint8_t* __restrict__ blobs, const int64_t* __restrict__ blob_off, SubstDev sd,
+                                                      int n_states, const int32_t* __restrict__ elem, const int8_t* __restrict__ Z,
+                                                      const double* __restrict__ n_rate, const double* __restrict__ c_rate, int N, int n_max,
+                                                      int slots_max, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int BD = blockDim.x, tid = threadIdx.x;
+  const int st = blockIdx.x;
+  if (st >= n_states) return;
+  const int64_t off = blob_off[elem[st]];
+  if (off < 0) {  // filtered element
+    if (tid == 0) out[st] = CUDART_NAN;
+    return;
+  }
+  const uint8_t* blob = blobs + off;
+  const ElemView ev = make_view(blob);
+  const ElemHeader* h = ev.h;
+  const int n = h->n, ni = h->ni;
+  // shared memory carve-up
+  double* Pm = reinterpret_cast<double*>(smem_raw);                     // [n_max][16]
+  double* stack = Pm + (size_t)n_max * 16;                              // [slots_max][4][BD]
+  double* red = stack + (size_t)slots_max * 4 * BD;                     // [33]
+  int* stack_sc = reinterpret_cast<int*>(red + 34);                     // [slots_max][BD]
+  int16_t* s_child = reinterpret_cast<int16_t*>(stack_sc + (size_t)slots_max * BD);  // [n_max][2]
+  int16_t* s_tiprow = s_child + 2 * n_max;
+  int16_t* s_su = s_tiprow + n_max;
+  int16_t* s_intidx = s_su + n_max;
+  uint8_t* s_flags = reinterpret_cast<uint8_t*>(s_intidx + n_max);
+  int8_t* s_slot = reinterpret_cast<int8_t*>(s_flags + n_max);
+  __shared__ double s_pi[4];
+  for (int i = tid; i < n; i += BD) {
+    s_child[2 * i] = ev.child[2 * i];
+    s_child[2 * i + 1] = ev.child[2 * i + 1];
+    s_tiprow[i] = ev.tiprow[i];
+    s_intidx[i] = ev.intidx[i];
+    s_flags[i] = ev.flags[i];
+    s_slot[i] = ev.slot[i];
+    // P(t) of the branch above node i for its class (initMCMC, bpp_c.cpp:187-228; Update_Tg bpp_c.cpp:661-663)
+    const int z = Z[(size_t)st * N + ev.orig[i]];
+    const double rate = (z == 2) ? n_rate[st] : (z == 0 ? 1.0 : c_rate[st]);
+    double P16[16];
+    build_P(sd, ev.dist[i], rate, true, P16);
+#pragma unroll
+    for (int k = 0; k < 16; k++) Pm[i * 16 + k] = P16[k];
+  }
+  for (int i = tid; i < ni; i += BD) s_su[i] = ev.su[i];
+  if (tid < 4) s_pi[tid] = sd.pi[tid];
+  __syncthreads();
+  TreeSmem ts{s_child, s_flags, s_tiprow, s_su, s_slot, s_intidx};
+  double acc = 0.0;
+  for (int p = tid; p < h->Ppad; p += BD) {
+    if (p < h->P) {
+      const double ll = prune_pattern<false, false>(h, ts, ev.codes, Pm, nullptr, stack, stack_sc, nullptr, nullptr, s_pi, p, BD, tid);
+      acc += (double)ev.weights[p] * ll;
+    }
+  }
+  const double tot = block_sum(acc, red, tid, BD);
+  if (tid == 0) out[st] = tot;
+}
+
+static size_t replay_smem_bytes(int n_max, int slots_max, int BD) {
+  size_t b = (size_t)n_max * 16 * 8 + (size_t)slots_max * 4 * BD * 8 + 34 * 8 + (size_t)slots_max * BD * 4;
+  b += (size_t)n_max * (2 + 1 + 1 + 1) * 2 + (size_t)n_max * 2;
+  return (b + 15) & ~size_t(15);
+}
+
+// ------------------------------------------------------------------------------------------ Engine
+Engine::~Engine() { release_device(); }
+
+void Engine::release_device() {
+  if (device < 0) return;
+  cudaSetDevice(device);
+  auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
+  fr((void*&)d_blobs); fr((void*&)d_blob_off);
+  fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
+}
+
+int Engine::init(const pa_tree* tree, const pa_subst* subst, const pa_params* params, int dev) {
+  Tree t;
+  t.S = tree->S;
+  t.N = tree->N;
+  if (t.N != 2 * t.S - 1 || t.S < 2) {
+    set_error("tree must be strictly binary with N = 2S-1");
+    return PA_ERR_ARG;
+  }
+  t.parent.assign(tree->parent, tree->parent + t.N);
+  t.children.assign(tree->children, tree->children + 2 * t.N);
+  t.dist.assign(tree->distances, tree->distances + t.N);
+  t.names.assign(t.N, "");
+  memcpy(t.pi, subst->pi, sizeof(t.pi));
+  memcpy(t.Q, subst->Q, sizeof(t.Q));
+  if (!build_model(t, *params, model)) return PA_ERR_ARG;
+  device = dev;
+  if (device >= 0) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count) {
+      set_error("no usable CUDA device " + std::to_string(device) + " (this engine has no CPU fallback)");
+      device = -1;
+      return PA_ERR_CUDA;
+    }
+    PA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PA_CUDA(cudaGetDeviceProperties(&prop, device));
+    num_sms = prop.multiProcessorCount;
+    smem_optin = (int)prop.sharedMemPerBlockOptin;
+  }
+  return PA_OK;
+}
+
+int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len) {
+  if (C < 0 || G < 0) {
+    set_error("bad alignment dimensions");
+    return PA_ERR_ARG;
+  }
+  for (int c = 0; c < C; c++)
+    if (elem_start[c] < 0 || elem_len[c] < 0 || elem_start[c] + elem_len[c] > G) {
+      set_error("element " + std::to_string(c) + " lies outside the alignment");
+      return PA_ERR_ARG;
+    }
+  plans.assign(C, ElemPlan());
+  const int nt = std::max(1, model.prm.num_thread);
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+  for (int c = 0; c < C; c++) plan_element(model, X, G, elem_start[c], elem_len[c], c, plans[c]);
+  blob_off.assign(C, -1);
+  size_t total = 0;
+  n_max = 0; slots_max = 1; P_max = 0; GG_max = 0;
+  for (int c = 0; c < C; c++) {
+    if (plans[c].filtered) continue;
+    blob_off[c] = (int64_t)total;
+    total += plans[c].blob.size();
+    const ElemHeader* h = reinterpret_cast<const ElemHeader*>(plans[c].blob.data());
+    n_max = std::max(n_max, h->n);
+    slots_max = std::max(slots_max, h->n_slots);
+    P_max = std::max(P_max, h->Ppad);
+    GG_max = std::max(GG_max, h->GG);
+  }
+  loaded = true;
+  if (device < 0) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  release_device();
+  std::vector<uint8_t> all(total);
+  for (int c = 0; c < C; c++)
+    if (!plans[c].filtered) {
+      memcpy(all.data() + blob_off[c], plans[c].blob.data(), plans[c].blob.size());
+      std::vector<uint8_t>().swap(plans[c].blob);  // the packed copy now lives in HBM
+    }
+  PA_CUDA(cudaMalloc(&d_blobs, std::max<size_t>(total, 16)));
+  PA_CUDA(cudaMalloc(&d_blob_off, sizeof(int64_t) * std::max(C, 1)));
+  PA_CUDA(cudaMemcpyAsync(d_blobs, all.data(), total, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_blob_off, blob_off.data(), sizeof(int64_t) * C, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaStreamSynchronize(stream));
+  h2d_bytes = total + sizeof(int64_t) * C;
+  return PA_OK;
+}
+
+int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out) {
+  if (!loaded) {
+    set_error("pa_engine_loglik_replay called before pa_engine_load_alignment");
+    return PA_ERR_STATE;
+  }
+  if (device < 0) {
+    set_error("no CUDA device bound to this engine (there is no CPU fallback)");
+    return PA_ERR_CUDA;
+  }
+  if (n_states <= 0) return PA_OK;
+  const int N = model.tree.N;
+  for (int i = 0; i < n_states; i++)
+    if (elem[i] < 0 || elem[i] >= (int)plans.size()) {
+      set_error("element id out of range");
+      return PA_ERR_ARG;
+    }
+  PA_CUDA(cudaSetDevice(device));
+  int32_t* d_elem = nullptr;
+  int8_t* d_Z = nullptr;
+  double *d_n = nullptr, *d_c = nullptr, *d_out = nullptr;
+  PA_CUDA(cudaMalloc(&d_elem, sizeof(int32_t) * n_states));
+  PA_CUDA(cudaMalloc(&d_Z, (size_t)n_states * N));
+  PA_CUDA(cudaMalloc(&d_n, sizeof(double) * n_states));
+  PA_CUDA(cudaMalloc(&d_c, sizeof(double) * n_states));
+  PA_CUDA(cudaMalloc(&d_out, sizeof(double) * n_states));
+  PA_CUDA(cudaMemcpyAsync(d_elem, elem, sizeof(int32_t) * n_states, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_Z, Z, (size_t)n_states * N, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_n, n_rate, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_c, c_rate, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
+  const int BD = 128;
+  const size_t smem = replay_smem_bytes(n_max, slots_max, BD);
+  if ((int)smem > smem_optin) {
+    set_error("tree too large for the replay kernel's shared memory");
+    return PA_ERR_LIMIT;
+  }
+  PA_CUDA(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  replay_kernel<<<n_states, BD, smem, stream>>>(d_blobs, d_blob_off, model.subst_dev, n_states, d_elem, d_Z, d_n, d_c, N, n_max, slots_max, d_out);
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_states, cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaStreamSynchronize(stream));
+  cudaFree(d_elem); cudaFree(d_Z); cudaFree(d_n); cudaFree(d_c); cudaFree(d_out);
+  return PA_OK;
+}
+
+}  // namespace pa

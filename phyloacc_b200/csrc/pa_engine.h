@@ -1,0 +1,83 @@
+// pa_engine.h -- the engine object behind the C ABI (one per pa_engine handle).
+#ifndef PA_ENGINE_H
+#define PA_ENGINE_H
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "pa_internal.h"
+
+namespace pa {
+
+const std::string& get_error();
+
+struct ChainTraceHost {  // host copy of one chain's trace (Output_sampling columns)
+  std::vector<double> loglik, n_rate, c_rate, g_rate, l_rate, l2_rate;
+  std::vector<int8_t> Z;  // [T][N] original node numbering, -1 for pruned nodes
+};
+
+struct Engine {
+  Model model;
+  int device = -1;
+  int num_sms = 0, smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  bool loaded = false;
+  std::vector<ElemPlan> plans;
+  std::vector<int64_t> blob_off;
+  int n_max = 0, slots_max = 1, P_max = 0, GG_max = 0;
+  size_t h2d_bytes = 0;
+
+  // device-resident batch
+  uint8_t* d_blobs = nullptr;
+  int64_t* d_blob_off = nullptr;
+
+  // last sampling run
+  std::vector<int32_t> run_ids;          // element ids passed to sample()
+  std::vector<int32_t> chain_elem_pos;   // per chain: position in run_ids
+  std::vector<int32_t> chain_model;      // per chain: PA_M0..PA_M2
+  std::vector<int32_t> chain_of;         // [n_ids][3] -> chain index or -1 (filtered)
+  int n_chains = 0, T = 0, ZW = 0;
+  int32_t* d_chain_list = nullptr;       // [n_chains][2] (element id, model) sorted by decreasing cost
+  double* d_trace_d = nullptr;           // [n_chains][6][T]
+  uint32_t* d_trace_z = nullptr;         // [n_chains][T][ZW] 2-bit packed Z by local node index
+  uint8_t* d_arena = nullptr;            // per-CTA scratch (partials, scale counts, log P tables)
+  unsigned long long* d_counters = nullptr;
+  int* d_queue = nullptr;
+  std::vector<double> h_trace_d;
+  std::vector<uint32_t> h_trace_z;
+  bool sampled = false, collected = false;
+  pa_counters counters{};
+
+  ~Engine();
+  void release_device();
+  int init(const pa_tree* tree, const pa_subst* subst, const pa_params* params, int dev);
+  int load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len);
+  int loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out);
+  int sample(const int32_t* ids, int32_t n_ids);
+  int fetch_traces();
+  int collect(pa_results* out);
+  int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);
+};
+
+// Eval2 + summaries (pa_eval.cpp)
+struct ChainSummary {
+  double logml = 0, loglik_max = 0;
+  std::vector<int8_t> max_Z;
+  double med[5] = {0, 0, 0, 0, 0};
+  std::vector<double> post_Z;  // [N][4]
+  int failure = 0;
+};
+int summarize_chain(Engine& eng, int elem, int mdl, const ChainTraceHost& tr, ChainSummary& out);
+
+}  // namespace pa
+
+// the opaque handle of the C ABI
+struct pa_engine {
+  pa::Engine eng;
+  pa::Params params;                       // set by pa_engine_create_from_config
+  std::vector<std::string> element_names;  // BED column 0 (profile.cpp:85)
+  std::vector<int32_t> ids;                // element ids selected by ID_FILE / BATCH (main.cpp:406-439)
+  bool from_config = false;
+};
+#endif
