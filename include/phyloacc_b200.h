@@ -153,6 +153,10 @@ typedef struct pa_counters {
 } pa_counters;
 int pa_engine_counters(pa_engine* e, pa_counters* out);
 
+/* Measurement helper for the roofline: sustained FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of `device`, from a
+ * register-resident DFMA micro-benchmark run for about `millis` ms. Not part of the reference's interface. */
+int pa_device_fp64_peak(int device, int millis, double* tflops_out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

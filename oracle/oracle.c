@@ -57,6 +57,7 @@ double pa_or_gamma(uint32_t seed, uint32_t chain_key, uint32_t idx, uint32_t sub
   const double c = (1.0 / 3.0) / sqrt(d);
   for (uint32_t attempt = 0;; attempt++) {
     if (attempt > 0) pa_or_philox(seed, chain_key, idx, sub0 + attempt, iter, stream, w);
+    if (attempt > 1000) return NAN; /* non-finite parameters: never spin */
     const double x = sqrt(-2.0 * log(u01(w[0]))) * cos(6.283185307179586 * u01(w[1]));
     double v = 1.0 + c * x;
     if (v <= 0) continue;

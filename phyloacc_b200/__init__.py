@@ -79,7 +79,7 @@ EXPORTS = [
     "pa_engine_load_alignment", "pa_engine_num_elements", "pa_engine_element_info", "pa_engine_loglik_replay",
     "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters",
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
-    "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config",
+    "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
 ]
 
 _lib = None
@@ -127,6 +127,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_ids.argtypes = [C.c_void_p, C.POINTER(_i32p), _i32p]
     lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
     lib.pa_run_from_config.argtypes = [C.c_char_p]
+    lib.pa_device_fp64_peak.argtypes = [C.c_int, C.c_int, _f64p]
     _lib = lib
     return lib
 
@@ -325,6 +326,13 @@ class Engine:
         c = PaCounters()
         _check(self._lib.pa_engine_counters(self._h, C.byref(c)))
         return {k: getattr(c, k) for k, _ in PaCounters._fields_}
+
+
+def fp64_peak_tflops(device: int = 0, millis: int = 300) -> float:
+    """Measured FP64 FMA throughput of the device (roofline denominator; MEASURED_PEAKS.json has no FP64 entry)."""
+    v = C.c_double(0.0)
+    _check(load_library().pa_device_fp64_peak(device, millis, C.byref(v)))
+    return v.value
 
 
 def run_from_config(cfg_path: str) -> int:

@@ -16,5 +16,6 @@ struct ChainLaunch {
 size_t chain_smem_bytes(int n_max, int slots_max, int BD);
 size_t chain_arena_bytes(int n_max, int P_max);
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
+int chain_block_dim();
 }  // namespace pa
 #endif

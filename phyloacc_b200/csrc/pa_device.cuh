@@ -66,6 +66,7 @@ __device__ inline double sched_gamma(uint32_t seed, uint32_t key, uint32_t idx, 
   const double c = (1.0 / 3.0) / sqrt(d);
   for (uint32_t attempt = 0;; attempt++) {
     if (attempt > 0) w = philox4(seed, key, idx, sub0 + attempt, iter, stream);
+    if (attempt > 1000) return CUDART_NAN;  // non-finite parameters: never spin
     const double x = sqrt(-2.0 * log(u01(w.x))) * cos(6.283185307179586 * u01(w.y));
     double v = 1.0 + c * x;
     if (v <= 0) continue;

@@ -230,4 +230,55 @@ int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z
   return PA_OK;
 }
 
+// ------------------------------------------------------------------------------------------ FP64 FMA peak
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+int fp64_peak(int device, int millis, double* tflops_out) {
+  PA_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PA_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  double* d = nullptr;
+  PA_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  PA_CUDA(cudaEventCreate(&e0));
+  PA_CUDA(cudaEventCreate(&e1));
+  int iters = 2000;
+  double best = 0;
+  float total_ms = 0;
+  for (int rep = 0; rep < 64 && total_ms < (float)millis; rep++) {
+    PA_CUDA(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(d, iters, 1.0);
+    PA_CUDA(cudaEventRecord(e1));
+    PA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    total_ms += ms;
+    const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    if (ms < 20.f) iters *= 2;
+  }
+  cudaFree(d);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops_out = best;
+  return PA_OK;
+}
+
 }  // namespace pa
+
+extern "C" int pa_device_fp64_peak(int device, int millis, double* tflops_out) {
+  if (!tflops_out) return PA_ERR_ARG;
+  return pa::fp64_peak(device, millis, tflops_out);
+}

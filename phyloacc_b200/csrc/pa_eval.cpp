@@ -1,8 +1,459 @@
+// pa_eval.cpp -- host side of a sampling run: chain scheduling, trace collection, and the per-chain summaries the
+// reference computes after Gibbs: MaxLoglik / Max_Z (MonitorChain, bpp_c.cpp:768-814), Eval2 (bpp_c2.cpp:14-353) and
+// Output_init's medians / posterior Z frequencies (bpp_c2.cpp:739-785).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "pa_chain.cuh"
 #include "pa_engine.h"
+
 namespace pa {
-int summarize_chain(Engine&, int, int, const ChainTraceHost&, ChainSummary&) { return PA_ERR_STATE; }
-int Engine::sample(const int32_t*, int32_t) { set_error("not built"); return PA_ERR_STATE; }
-int Engine::fetch_traces() { return PA_ERR_STATE; }
-int Engine::collect(pa_results*) { return PA_ERR_STATE; }
-int Engine::get_trace(int32_t, int32_t, ChainTraceHost&) { return PA_ERR_STATE; }
+
+int chain_block_dim();
+
+#define PA_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t err__ = (call);                                                               \
+    if (err__ != cudaSuccess) {                                                               \
+      set_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #call);     \
+      return PA_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+static double gamma_pdf(double x, double a, double b) {  // gsl_ran_gamma_pdf
+  if (x < 0) return 0;
+  if (x == 0) return (a == 1) ? 1 / b : 0;
+  if (a == 1) return std::exp(-x / b) / b;
+  return std::exp((a - 1) * std::log(x / b) - x / b - std::lgamma(a)) / b;
 }
+static double lnbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
+
+// ------------------------------------------------------------------------------------------ launch
+int Engine::sample(const int32_t* ids, int32_t n_ids) {
+  if (!loaded) {
+    set_error("pa_engine_sample called before pa_engine_load_alignment");
+    return PA_ERR_STATE;
+  }
+  if (device < 0) {
+    set_error("no CUDA device bound to this engine (there is no CPU fallback)");
+    return PA_ERR_CUDA;
+  }
+  const pa_params& P = model.prm;
+  T = P.burnin + P.mcmc;
+  if (T < 2 || P.adapt_freq < 1) {
+    set_error("BURNIN + MCMC must be >= 2 and ADAPT_FREQ >= 1");
+    return PA_ERR_ARG;
+  }
+  run_ids.assign(ids, ids + n_ids);
+  chain_of.assign((size_t)n_ids * 3, -1);
+  chain_elem_pos.clear();
+  chain_model.clear();
+  std::vector<double> cost;
+  for (int i = 0; i < n_ids; i++) {
+    const int c = ids[i];
+    if (c < 0 || c >= (int)plans.size()) {
+      set_error("element id out of range");
+      return PA_ERR_ARG;
+    }
+    if (plans[c].filtered) continue;
+    for (int mdl = 0; mdl < 3; mdl++) {
+      chain_of[(size_t)i * 3 + mdl] = (int)chain_elem_pos.size();
+      chain_elem_pos.push_back(i);
+      chain_model.push_back(mdl);
+      cost.push_back((double)plans[c].GG * plans[c].nodes.size() * (mdl == 0 ? 0.8 : 1.0));
+    }
+  }
+  n_chains = (int)chain_elem_pos.size();
+  sampled = true;
+  collected = false;
+  counters = pa_counters{};
+  if (n_chains == 0) return PA_OK;
+  ZW = (n_max + 15) / 16;
+  // longest chains first so that the tail of the persistent-CTA queue is short
+  std::vector<int> order(n_chains);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  // chain index on the device = position in `order`; keep the mapping
+  std::vector<int32_t> list((size_t)n_chains * 2);
+  std::vector<int> dev_index(n_chains);
+  for (int k = 0; k < n_chains; k++) {
+    const int ch = order[k];
+    list[2 * k] = run_ids[chain_elem_pos[ch]];
+    list[2 * k + 1] = chain_model[ch];
+    dev_index[ch] = k;
+  }
+  for (auto& v : chain_of)
+    if (v >= 0) v = dev_index[v];
+  {
+    std::vector<int32_t> pos2(n_chains), mdl2(n_chains);
+    for (int ch = 0; ch < n_chains; ch++) {
+      pos2[dev_index[ch]] = chain_elem_pos[ch];
+      mdl2[dev_index[ch]] = chain_model[ch];
+    }
+    chain_elem_pos.swap(pos2);
+    chain_model.swap(mdl2);
+  }
+
+  PA_CUDA(cudaSetDevice(device));
+  auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
+  fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
+  const int BD = chain_block_dim();
+  const size_t smem = chain_smem_bytes(n_max, slots_max, BD);
+  if ((int)smem > smem_optin) {
+    set_error("tree too large for the chain kernel's shared memory (" + std::to_string(smem) + " bytes needed)");
+    return PA_ERR_LIMIT;
+  }
+  int per_sm = std::max(1, std::min(2, (int)((size_t)smem_optin / smem)));
+  if (smem * 2 + 2048 > 233472) per_sm = 1;
+  const int grid = std::min(n_chains, num_sms * per_sm);
+  const size_t stride = chain_arena_bytes(n_max, P_max);
+  PA_CUDA(cudaMalloc(&d_chain_list, sizeof(int32_t) * 2 * n_chains));
+  PA_CUDA(cudaMalloc(&d_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
+  PA_CUDA(cudaMalloc(&d_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));
+  PA_CUDA(cudaMalloc(&d_arena, stride * grid));
+  PA_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * 8));
+  PA_CUDA(cudaMalloc(&d_queue, sizeof(int)));
+  PA_CUDA(cudaMemcpyAsync(d_chain_list, list.data(), sizeof(int32_t) * 2 * n_chains, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, stream));
+  PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int), stream));
+
+  ChainLaunch L;
+  L.blobs = d_blobs;
+  L.blob_off = d_blob_off;
+  L.chain_list = d_chain_list;
+  L.n_chains = n_chains;
+  L.sd = model.subst_dev;
+  ChainParams& cp = L.cp;
+  cp.cprior_a = P.conserve_prior_a; cp.cprior_b = P.conserve_prior_b; cp.nprior_a = P.acce_prior_a; cp.nprior_b = P.acce_prior_b;
+  cp.prior_l_a = P.hyper_lrate_a; cp.prior_l_b = P.hyper_lrate_b; cp.prior_l2_a = P.hyper_lrate2_a; cp.prior_l2_b = P.hyper_lrate2_b;
+  cp.prior_g_a = P.hyper_grate_a; cp.prior_g_b = P.hyper_grate_b;
+  cp.init_crate = P.init_conserve_rate; cp.init_nrate = P.init_acce_rate;
+  cp.init_lrate = P.init_lrate; cp.init_lrate2 = (P.hyper_lrate2_a == 0) ? 0.0 : P.init_lrate2; cp.init_grate = P.init_grate;
+  cp.cub = P.cub; cp.nlb = P.nlb; cp.log_constomis = std::log(P.constomis);
+  cp.ropt = P.ropt; cp.num_burn = P.burnin; cp.num_mcmc = P.mcmc; cp.adaptive_freq = P.adapt_freq;
+  cp.seed = (uint32_t)P.seed;
+  cp.pad_ = 0;
+  L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T; L.ZW = ZW;
+  L.trace_d = d_trace_d; L.trace_z = d_trace_z;
+  L.arena = d_arena; L.arena_stride = stride;
+  L.counters = d_counters; L.queue = d_queue;
+  const int rc = launch_chains(L, grid, BD, stream);
+  if (rc != PA_OK) return rc;
+  counters.kernel_launches = 1;
+  return PA_OK;
+}
+
+int Engine::fetch_traces() {
+  if (!sampled) {
+    set_error("nothing sampled yet");
+    return PA_ERR_STATE;
+  }
+  if (collected || n_chains == 0) {
+    collected = true;
+    return PA_OK;
+  }
+  PA_CUDA(cudaSetDevice(device));
+  h_trace_d.resize((size_t)6 * T * n_chains);
+  h_trace_z.resize((size_t)ZW * T * n_chains);
+  unsigned long long hc[8];
+  PA_CUDA(cudaMemcpyAsync(h_trace_d.data(), d_trace_d, sizeof(double) * h_trace_d.size(), cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaMemcpyAsync(h_trace_z.data(), d_trace_z, sizeof(uint32_t) * h_trace_z.size(), cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaMemcpyAsync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaStreamSynchronize(stream));
+  counters.node_pattern_updates = hc[0];
+  counters.root_evals = hc[1];
+  counters.pt_builds = hc[2];
+  counters.history_draws = hc[3];
+  counters.chain_iterations = hc[4];
+  collected = true;
+  return PA_OK;
+}
+
+int Engine::get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr) {
+  int rc = fetch_traces();
+  if (rc != PA_OK) return rc;
+  if (i < 0 || i >= (int)run_ids.size() || mdl < 0 || mdl > 2) {
+    set_error("bad chain index");
+    return PA_ERR_ARG;
+  }
+  const int ch = chain_of[(size_t)i * 3 + mdl];
+  if (ch < 0) {
+    set_error("element was filtered; it has no chain");
+    return PA_ERR_ARG;
+  }
+  const ElemPlan& pl = plans[run_ids[i]];
+  const int N = model.tree.N, n = (int)pl.nodes.size();
+  const double* d = &h_trace_d[(size_t)ch * 6 * T];
+  tr.loglik.assign(d, d + T);
+  tr.n_rate.assign(d + T, d + 2 * T);
+  tr.c_rate.assign(d + 2 * T, d + 3 * T);
+  tr.g_rate.assign(d + 3 * T, d + 4 * T);
+  tr.l_rate.assign(d + 4 * T, d + 5 * T);
+  tr.l2_rate.assign(d + 5 * T, d + 6 * T);
+  tr.Z.assign((size_t)T * N, -1);
+  const uint32_t* z = &h_trace_z[(size_t)ch * T * ZW];
+  for (int m = 0; m < T; m++)
+    for (int k = 0; k < n; k++) tr.Z[(size_t)m * N + pl.nodes[k]] = (int8_t)((z[(size_t)m * ZW + (k >> 4)] >> (2 * (k & 15))) & 3);
+  return PA_OK;
+}
+
+// ------------------------------------------------------------------------------------------ summaries
+namespace {
+
+struct Eval2Work {  // state carried to the (rare) fallback that needs pruning on the device (bpp_c2.cpp:199-316)
+  bool need_fallback = false;
+  std::vector<std::vector<int8_t>> configZ;
+  std::vector<double> priorZ;
+  double rn = 0, rc = 0, varc = 0, varn = 0, cov = 0, meann = 0, meanc = 0;
+};
+
+double prior_z_config(const Engine& eng, const ElemPlan& pl, int mdl, const int8_t* cfgZ) {  // bpp_c2.cpp:131-163
+  const pa_params& P = eng.model.prm;
+  const int N = eng.model.tree.N;
+  const uint8_t* fixZ = &pl.fixZ[(size_t)mdl * N];
+  double nZ[9] = {0}, nF[9] = {0};
+  const int n = (int)pl.nodes.size();
+  for (int i = 0; i < n - 1; i++) {
+    const int s = pl.nodes[i];
+    const int k = cfgZ[s] * 3 + cfgZ[pl.parent2[s]];
+    nZ[k] += 1;
+    if (!fixZ[s]) nF[k] += 1;
+  }
+  double pz = lnbeta(P.hyper_grate_a + nZ[3] + nZ[6], P.hyper_grate_b + nZ[0]) - lnbeta(P.hyper_grate_a, P.hyper_grate_b);
+  pz += lnbeta(P.hyper_lrate_a + nF[7], P.hyper_lrate_b + nF[4]) - lnbeta(P.hyper_lrate_a, P.hyper_lrate_b);
+  if (P.hyper_lrate2_a > 0) pz += lnbeta(P.hyper_lrate2_a + nF[5], P.hyper_lrate2_b + nF[8]) - lnbeta(P.hyper_lrate2_a, P.hyper_lrate2_b);
+  const double prior_z[3] = {std::log(0.5), std::log(0.5), -INFINITY};
+  pz += prior_z[cfgZ[pl.root]];
+  return pz;
+}
+
+// everything except the pruning fallback; returns VB (possibly to be replaced by the fallback)
+double eval2_main(const Engine& eng, const ElemPlan& pl, int mdl, const ChainTraceHost& tr, const std::vector<double>& full,
+                  const int8_t* Max_Z, Eval2Work& work) {
+  const pa_params& P = eng.model.prm;
+  const int N = eng.model.tree.N, num_burn = P.burnin, num_mcmc = P.mcmc, T = num_burn + num_mcmc;
+  const bool null_model = (mdl == PA_M0);  // resZ == 0
+  std::vector<int> uncertain;
+  for (int s = 0; s < N; s++) {
+    int cnt = 0;
+    for (int i = num_burn; i < T; i++) cnt += tr.Z[(size_t)i * N + s] == Max_Z[s];
+    if (cnt < num_mcmc) uncertain.push_back(s);
+  }
+  std::vector<const int8_t*> configZ{Max_Z};
+  std::vector<int> num{0};
+  std::vector<double> var_c{0}, mean_c{0}, var_n{0}, mean_n{0}, cov{0}, sum_full{0};
+  for (int i = T - 1; i >= num_burn; i--) {
+    const int8_t* zi = &tr.Z[(size_t)i * N];
+    size_t j = 0;
+    for (; j < configZ.size(); j++) {
+      size_t k = 0;
+      for (; k < uncertain.size(); k++)
+        if (zi[uncertain[k]] != configZ[j][uncertain[k]]) break;
+      if (k == uncertain.size()) break;
+    }
+    if (j == configZ.size()) {
+      configZ.push_back(zi);
+      num.push_back(0); var_c.push_back(0); mean_c.push_back(0); var_n.push_back(0); mean_n.push_back(0); cov.push_back(0); sum_full.push_back(0);
+    }
+    num[j]++;
+    var_c[j] += std::pow(tr.c_rate[i], 2);
+    mean_c[j] += tr.c_rate[i];
+    if (!null_model) {
+      var_n[j] += std::pow(tr.n_rate[i], 2);
+      mean_n[j] += tr.n_rate[i];
+      cov[j] += tr.c_rate[i] * tr.n_rate[i];
+    }
+    sum_full[j] += full[i] / num_mcmc;
+  }
+  double VB = 0, logdet;
+  int effective_sum = 0;
+  const int numConf = (int)configZ.size();
+  for (int i = 0; i < numConf; i++) {
+    const double w = (double)num[i] / num_mcmc;
+    if (w < 0.02) continue;
+    const double priorZ = prior_z_config(eng, pl, mdl, configZ[i]);
+    sum_full[i] += num[i] * priorZ / num_mcmc;
+    if (null_model) {
+      logdet = std::log(var_c[i] - std::pow(mean_c[i], 2) / num[i]) - std::log(num[i]);
+    } else {
+      const double vc = var_c[i] - std::pow(mean_c[i], 2) / num[i];
+      const double vn = var_n[i] - std::pow(mean_n[i], 2) / num[i];
+      const double cv = cov[i] - mean_n[i] * mean_c[i] / num[i];
+      logdet = std::log(vc * vn - cv * cv) - 2 * std::log(num[i]);
+    }
+    if (std::isnan(logdet)) continue;
+    effective_sum += num[i];
+    VB -= w * std::log(num[i]);
+    VB += sum_full[i];
+    VB += 0.5 * logdet * num[i] / num_mcmc;
+  }
+  if (effective_sum == 0) {
+    work.need_fallback = true;
+    for (int i = 0; i < numConf; i++) {
+      work.varc += var_c[i]; work.meanc += mean_c[i];
+      if (!null_model) { work.meann += mean_n[i]; work.varn += var_n[i]; work.cov += cov[i]; }
+      work.configZ.emplace_back(configZ[i], configZ[i] + N);
+      work.priorZ.push_back(prior_z_config(eng, pl, mdl, configZ[i]));
+    }
+    work.rn = work.meann / num_mcmc;
+    work.rc = work.meanc / num_mcmc;
+    return NAN;
+  }
+  if (!null_model) return VB * ((double)num_mcmc / effective_sum) + std::log(num_mcmc) + std::log(2 * M_PI) + 1;
+  return VB * ((double)num_mcmc / effective_sum) + std::log(num_mcmc) + 0.5 * (std::log(2 * M_PI) + 1);
+}
+
+double eval2_fallback_finish(const Engine& eng, int mdl, const Eval2Work& w, const double* logliks) {  // bpp_c2.cpp:289-314
+  const pa_params& P = eng.model.prm;
+  const int num_mcmc = P.mcmc;
+  const bool null_model = (mdl == PA_M0);
+  std::vector<double> s(w.configZ.size());
+  double mx = -INFINITY;
+  for (size_t i = 0; i < s.size(); i++) {
+    s[i] = logliks[i] + w.priorZ[i];
+    if (s[i] > mx) mx = s[i];
+  }
+  double VB;
+  if (mx == -INFINITY) VB = -INFINITY;
+  else {
+    double acc = 0;
+    for (double v : s) acc += std::exp(v - mx);
+    VB = std::log(acc) + mx;
+  }
+  VB += std::log(gamma_pdf(w.rc, P.conserve_prior_a, P.conserve_prior_b));
+  if (!null_model) VB += std::log(gamma_pdf(w.rn, P.acce_prior_a, P.acce_prior_b));
+  double varc = w.varc, varn = w.varn, cv = w.cov;
+  if (null_model) {
+    varc -= std::pow(w.meanc, 2) / num_mcmc;
+    const double logdet = std::log(varc) - std::log(num_mcmc);
+    VB += 0.5 * logdet + 0.5 * std::log(2 * M_PI);
+  } else {
+    varn -= std::pow(w.meann, 2) / num_mcmc;
+    varc -= std::pow(w.meanc, 2) / num_mcmc;
+    cv -= w.meann * w.meanc / num_mcmc;
+    const double logdet = std::log(varc * varn - cv * cv) - 2 * std::log(num_mcmc);
+    VB += 0.5 * logdet + std::log(2 * M_PI);
+  }
+  return VB;
+}
+
+}  // namespace
+
+int Engine::collect(pa_results* out) {
+  int rc = fetch_traces();
+  if (rc != PA_OK) return rc;
+  const int n_ids = (int)run_ids.size();
+  if (out->n < n_ids || out->N != model.tree.N) {
+    set_error("pa_results too small for this run");
+    return PA_ERR_ARG;
+  }
+  const pa_params& P = model.prm;
+  const int N = model.tree.N, num_burn = P.burnin, num_mcmc = P.mcmc;
+  for (int i = 0; i < n_ids; i++) {
+    const bool filt = plans[run_ids[i]].filtered;
+    if (out->filtered) out->filtered[i] = filt;
+    if (out->loglik) for (int k = 0; k < 3; k++) out->loglik[i * 3 + k] = 0;
+    if (out->loglik_max) for (int k = 0; k < 3; k++) out->loglik_max[i * 3 + k] = 0;
+    if (out->max_Z) memset(out->max_Z + (size_t)i * 3 * N, 0, (size_t)3 * N);
+    if (out->median_rates) for (int k = 0; k < 15; k++) out->median_rates[(size_t)i * 15 + k] = 0;
+    if (out->post_Z) for (size_t k = 0; k < (size_t)3 * N * 4; k++) out->post_Z[(size_t)i * 3 * N * 4 + k] = 0;
+  }
+  std::vector<Eval2Work> works(n_chains);
+  std::vector<double> logml(n_chains, 0.0);
+  int err = PA_OK;
+  const int nt = std::max(1, P.num_thread);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
+  for (int ch = 0; ch < n_chains; ch++) {
+    const int i = chain_elem_pos[ch], mdl = chain_model[ch];
+    const ElemPlan& pl = plans[run_ids[i]];
+    ChainTraceHost tr;
+    if (get_trace(i, mdl, tr) != PA_OK) {
+#pragma omp critical
+      err = PA_ERR_STATE;
+      continue;
+    }
+    // MonitorChain: full log-likelihood and its arg-max after burn-in (bpp_c.cpp:768-814)
+    std::vector<double> full(T);
+    double max_ll = -INFINITY;
+    int max_m = -1;
+    for (int m = 0; m < T; m++) {
+      full[m] = tr.loglik[m] + 0.0;
+      full[m] += std::log(gamma_pdf(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b));
+      if (mdl != PA_M0) full[m] += std::log(gamma_pdf(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b));
+      if (m >= num_burn && full[m] > max_ll) {
+        max_ll = full[m];
+        max_m = m;
+      }
+    }
+    std::vector<int8_t> Max_Z(N, 0);
+    if (max_m >= 0) Max_Z.assign(&tr.Z[(size_t)max_m * N], &tr.Z[(size_t)max_m * N] + N);
+    if (out->loglik_max) out->loglik_max[i * 3 + mdl] = max_ll;
+    if (out->max_Z) memcpy(out->max_Z + ((size_t)i * 3 + mdl) * N, Max_Z.data(), N);
+    if (max_m >= 0) logml[ch] = eval2_main(*this, pl, mdl, tr, full, Max_Z.data(), works[ch]);
+    else logml[ch] = NAN;
+    // Output_init: medians of the sorted FULL traces, Z frequencies after burn-in (bpp_c2.cpp:742-781)
+    if (out->median_rates) {
+      double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
+      std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
+      for (int k = 0; k < 5; k++) {
+        std::sort(cols[k]->begin(), cols[k]->end());
+        md[k] = (*cols[k])[cols[k]->size() / 2];
+      }
+    }
+    if (out->post_Z) {
+      double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
+      std::vector<int> cnt((size_t)N * 4, 0);
+      for (int m = num_burn; m < T; m++)
+        for (int s = 0; s < N; s++) cnt[s * 4 + tr.Z[(size_t)m * N + s] + 1]++;
+      for (int s = 0; s < N; s++) {
+        if (pl.missing[s]) cnt[s * 4] = num_mcmc;
+        for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
+      }
+    }
+  }
+  if (err != PA_OK) return err;
+  // Eval2 fallback (no configuration carries >= 2% weight with a finite log-det): exact log-likelihood of every
+  // configuration at the posterior-mean rates, by the replay kernel, in one batch
+  {
+    std::vector<int32_t> elem;
+    std::vector<int8_t> Z;
+    std::vector<double> nr, cr;
+    for (int ch = 0; ch < n_chains; ch++) {
+      const Eval2Work& w = works[ch];
+      if (!w.need_fallback) continue;
+      for (size_t k = 0; k < w.configZ.size(); k++) {
+        elem.push_back(run_ids[chain_elem_pos[ch]]);
+        Z.insert(Z.end(), w.configZ[k].begin(), w.configZ[k].end());
+        nr.push_back(chain_model[ch] == PA_M0 ? 1.0 : w.rn);
+        cr.push_back(w.rc);
+      }
+    }
+    if (!elem.empty()) {
+      std::vector<double> ll(elem.size());
+      rc = loglik_replay((int32_t)elem.size(), elem.data(), Z.data(), nr.data(), cr.data(), ll.data());
+      if (rc != PA_OK) return rc;
+      size_t off = 0;
+      for (int ch = 0; ch < n_chains; ch++) {
+        const Eval2Work& w = works[ch];
+        if (!w.need_fallback) continue;
+        logml[ch] = eval2_fallback_finish(*this, chain_model[ch], w, &ll[off]);
+        off += w.configZ.size();
+      }
+    }
+  }
+  if (out->loglik)
+    for (int ch = 0; ch < n_chains; ch++) out->loglik[chain_elem_pos[ch] * 3 + chain_model[ch]] = logml[ch];
+  return PA_OK;
+}
+
+int summarize_chain(Engine&, int, int, const ChainTraceHost&, ChainSummary&) { return PA_ERR_STATE; }
+
+}  // namespace pa
