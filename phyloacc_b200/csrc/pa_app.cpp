@@ -87,7 +87,6 @@ static int create_from_config(const char* cfg_path, int device, pa_engine** out)
 static int run_from_config(const char* cfg_path) {
   const time_t start = time(NULL);
   std::cout << std::fixed << std::setprecision(4);
-  std::cout << "Loading input data and running parameters......" << std::endl;
   // peek at RESULT_FOLDER first, as the reference checks it before loading data (main.cpp:334-338)
   {
     Params P0;
@@ -148,13 +147,46 @@ static int run_from_config(const char* cfg_path) {
   pa_results res{n, N, filtered.data(), loglik.data(), loglik_max.data(), maxZ.data(), med.data(), postZ.data()};
   for (int iter = 0; iter < P.num_chain; iter++) {
     std::cout << "Running MCMC chain " << iter + 1 << " ..." << std::endl;
-    rc = e->eng.sample(ids.data(), n);
-    if (rc == PA_OK) rc = e->eng.collect(&res);
-    if (rc != PA_OK) {
-      std::cerr << "(Error. " << get_error() << ")" << std::endl;
-      delete e;
-      return 1;
+    // elements go to the device in waves so that the traces of one wave fit comfortably in HBM and host memory
+    const int wave = 4096;
+    for (int w0 = 0; w0 < n; w0 += wave) {
+      const int wn = std::min(wave, n - w0);
+      pa_results wres{wn, N, filtered.data() + w0, loglik.data() + (size_t)w0 * 3, loglik_max.data() + (size_t)w0 * 3,
+                      maxZ.data() + (size_t)w0 * 3 * N, med.data() + (size_t)w0 * 15, postZ.data() + (size_t)w0 * 3 * N * 4};
+      rc = e->eng.sample(ids.data() + w0, wn);
+      if (rc == PA_OK) rc = e->eng.collect(&wres);
+      if (rc != PA_OK) {
+        std::cerr << "(Error. " << get_error() << ")" << std::endl;
+        delete e;
+        return 1;
+      }
+      // VERBOSE: per-chain traces (Output_sampling, bpp_c2.cpp:706-736); file index is the reference's third argument 0,1,2
+      if (P.verbose) {
+        for (int i = 0; i < wn; i++) {
+          if (filtered[w0 + i]) continue;
+          for (int m = 0; m < 3; m++) {
+            ChainTraceHost tr;
+            if (e->eng.get_trace(i, m, tr) != PA_OK) continue;
+            const std::string path = prefix + "_mcmc_trace_M" + std::to_string(m) + "_" + std::to_string(ids[w0 + i]) + ".txt";
+            std::ofstream ot;
+            ot.precision(8);
+            if (iter == 0) {
+              ot.open(path.c_str());
+              ot << "loglik\trate_n\trate_c\tgrate\tlrate\tlrate2\t";
+              for (int s = 0; s < N; s++) ot << tree.names[s] << "\t";
+              ot << std::endl;
+            } else ot.open(path.c_str(), std::ios::app);
+            const int T = (int)tr.loglik.size();
+            for (int t = 0; t < T; t++) {
+              ot << tr.loglik[t] << "\t" << tr.n_rate[t] << "\t" << tr.c_rate[t] << "\t" << tr.g_rate[t] << "\t" << tr.l_rate[t] << "\t" << tr.l2_rate[t] << "\t";
+              for (int s = 0; s < N; s++) ot << (int)tr.Z[(size_t)t * N + s] << "\t";
+              ot << std::endl;
+            }
+          }
+        }
+      }
     }
+    (void)res;
     // rows of _rate_postZ_Mk.txt (Output_init, bpp_c2.cpp:776-783; default ofstream precision = 6 significant digits)
     for (int i = 0; i < n; i++) {
       if (filtered[i]) continue;
@@ -165,31 +197,6 @@ static int run_from_config(const char* cfg_path) {
         for (int s = 0; s < N; s++)
           for (int k = 0; k < 4; k++) out_Z[m] << "\t" << pz[s * 4 + k];
         out_Z[m] << std::endl;
-      }
-    }
-    // VERBOSE: per-chain traces (Output_sampling, bpp_c2.cpp:706-736); file index is the reference's third argument 0,1,2
-    if (P.verbose) {
-      for (int i = 0; i < n; i++) {
-        if (filtered[i]) continue;
-        for (int m = 0; m < 3; m++) {
-          ChainTraceHost tr;
-          if (e->eng.get_trace(i, m, tr) != PA_OK) continue;
-          const std::string path = prefix + "_mcmc_trace_M" + std::to_string(m) + "_" + std::to_string(ids[i]) + ".txt";
-          std::ofstream ot;
-          ot.precision(8);
-          if (iter == 0) {
-            ot.open(path.c_str());
-            ot << "loglik\trate_n\trate_c\tgrate\tlrate\tlrate2\t";
-            for (int s = 0; s < N; s++) ot << tree.names[s] << "\t";
-            ot << std::endl;
-          } else ot.open(path.c_str(), std::ios::app);
-          const int T = (int)tr.loglik.size();
-          for (int t = 0; t < T; t++) {
-            ot << tr.loglik[t] << "\t" << tr.n_rate[t] << "\t" << tr.c_rate[t] << "\t" << tr.g_rate[t] << "\t" << tr.l_rate[t] << "\t" << tr.l2_rate[t] << "\t";
-            for (int s = 0; s < N; s++) ot << (int)tr.Z[(size_t)t * N + s] << "\t";
-            ot << std::endl;
-          }
-        }
       }
     }
     // _elem_lik.txt and _M{k}_elem_Z.txt (BPP::Output_init, bpp.cpp:568-619): one row per id, zeros for filtered ones
