@@ -152,6 +152,9 @@ typedef struct pa_counters {
   uint64_t node_pattern_updates, root_evals, pt_builds, history_draws, chain_iterations, kernel_launches;
 } pa_counters;
 int pa_engine_counters(pa_engine* e, pa_counters* out);
+/* SM cycles per phase of the chain kernel, summed over CTAs (thread 0 clock64 deltas): init, trace, history sampling,
+ * emission, Z update, Z-dirty pruning, n-rate step, c-rate step, commit, transitions. */
+int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10);
 
 /* Measurement helper for the roofline: sustained FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of `device`, from a
  * register-resident DFMA micro-benchmark run for about `millis` ms. Not part of the reference's interface. */

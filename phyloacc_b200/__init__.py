@@ -77,7 +77,7 @@ class PaCounters(C.Structure):
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_params_default", "pa_engine_create", "pa_engine_destroy", "pa_engine_set_stream",
     "pa_engine_load_alignment", "pa_engine_num_elements", "pa_engine_element_info", "pa_engine_loglik_replay",
-    "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters",
+    "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters", "pa_engine_phase_cycles",
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
 ]
@@ -118,6 +118,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_run.argtypes = [C.c_void_p, _i32p, C.c_int32, C.POINTER(PaResults)]
     lib.pa_engine_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PaTrace)]
     lib.pa_engine_counters.argtypes = [C.c_void_p, C.POINTER(PaCounters)]
+    lib.pa_engine_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     lib.pa_engine_create_from_config.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.pa_engine_get_tree.argtypes = [C.c_void_p, C.POINTER(PaTree), C.POINTER(PaSubst)]
     lib.pa_engine_node_name.argtypes = [C.c_void_p, C.c_int32]
@@ -321,6 +322,13 @@ class Engine:
         t.Z = b["Z"].ctypes.data_as(_i8p)
         _check(self._lib.pa_engine_get_trace(self._h, i, model, C.byref(t)))
         return b
+
+    PHASES = ["init", "trace", "history", "emission", "z_update", "z_dirty_prune", "n_rate", "c_rate", "commit", "transitions"]
+
+    def phase_cycles(self) -> dict:
+        buf = (C.c_uint64 * 10)()
+        _check(self._lib.pa_engine_phase_cycles(self._h, buf))
+        return dict(zip(self.PHASES, [int(v) for v in buf]))
 
     def counters(self) -> dict:
         c = PaCounters()

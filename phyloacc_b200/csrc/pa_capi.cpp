@@ -155,6 +155,12 @@ int pa_engine_get_trace(pa_engine* e, int32_t i, int32_t model, pa_trace* out) {
   });
 }
 
+int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
+  if (!e || !out10) return PA_ERR_ARG;
+  for (int k = 0; k < 10; k++) out10[k] = e->eng.phase_cycles[k];
+  return PA_OK;
+}
+
 int pa_engine_counters(pa_engine* e, pa_counters* out) {
   if (!e || !out) return PA_ERR_ARG;
   *out = e->eng.counters;

@@ -168,6 +168,14 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
   int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)L.n_max * L.P_max * 4);
 
   unsigned long long w_npu = 0, w_root = 0, w_pt = 0, w_hist = 0, w_iter = 0;  // work counters (thread 0)
+  long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, ph6 = 0, ph7 = 0, ph8 = 0, ph9 = 0;  // SM cycles per phase (thread 0)
+  long long t_last = clock64();
+#define PA_PHASE(var)                \
+  if (tid == 0) {                    \
+    const long long t_now = clock64(); \
+    var += t_now - t_last;           \
+    t_last = t_now;                  \
+  }
 
   for (;;) {
     __syncthreads();
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
     }
     __syncthreads();
 
+    PA_PHASE(ph0)
     double* tr_d = L.trace_d + (size_t)chain * 6 * T;
     uint32_t* tr_z = L.trace_z + (size_t)chain * T * L.ZW;
 
@@ -277,6 +286,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       if (m == T - 1) break;
       if (tid == 0) w_iter++;
+      PA_PHASE(ph1)
 
       // ---------------- sample ancestral histories site by site + count parent->child base pairs per branch
       for (int i = tid; i < n * 16; i += kBD) S.cnt[i] = 0;
@@ -387,6 +397,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       if (tid == 0) w_hist += (unsigned long long)GG * ni;
 
+      PA_PHASE(ph2)
       // ---------------- getEmission: e_s(k) = sum_bins count * log P_k (bpp_c2.cpp:355-390); missing nodes keep constants
       for (int task = tid; task < n * 3; task += kBD) {
         const int i = task / 3, k = task - 3 * i;
@@ -406,6 +417,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       __syncthreads();
 
+      PA_PHASE(ph3)
       // ---------------- Update_Z_subtree (bpp_c.cpp:1182-1293): scaled linear messages by tree level, one warp
       if (warp == 0) {
         if (lane == 0) S.ivars[IV_ZFALLBACK] = 0;
@@ -472,6 +484,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       __syncthreads();
 
+      PA_PHASE(ph4)
       // ---------------- changed Z: dirty ancestors, class switch of P(t), class presence
       for (int i = tid; i < n; i += kBD) {
         const int zo = S.Z[i];
@@ -508,6 +521,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       for (int i = tid; i < n; i += kBD) S.dirty[i] = 0;
       __syncthreads();
 
+      PA_PHASE(ph5)
       // ---------------- sample_rate: accelerated rate n (cls 2), then conserved rate c (cls 1)  (bpp_c.cpp:930-1176)
       for (int step = 0; step < 2; step++) {
         const bool neut = (step == 0);
@@ -646,6 +660,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
           }
         }
         __syncthreads();
+        if (neut) { PA_PHASE(ph6) } else { PA_PHASE(ph7) }
       }
 
       // ---------------- commit: bring the stored partials of stale nodes up to date with the accepted rates
@@ -661,6 +676,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         for (int i = tid; i < n; i += kBD) S.stale[i] = 0;
       }
 
+      PA_PHASE(ph8)
       // ---------------- sample_transition (bpp_c.cpp:522-613)
       if (tid < 18) S.nz[tid] = 0;
       __syncthreads();
@@ -687,6 +703,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         Tx[0] = 1 - g; Tx[3] = g;
       }
       __syncthreads();
+      PA_PHASE(ph9)
     }  // iterations
   }    // chains
 
@@ -696,6 +713,8 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
     atomicAdd(&L.counters[2], w_pt);
     atomicAdd(&L.counters[3], w_hist);
     atomicAdd(&L.counters[4], w_iter);
+    const long long phs[10] = {ph0, ph1, ph2, ph3, ph4, ph5, ph6, ph7, ph8, ph9};
+    for (int k = 0; k < 10; k++) atomicAdd(&L.counters[8 + k], (unsigned long long)phs[k]);
   }
 }
 

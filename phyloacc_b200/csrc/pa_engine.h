@@ -48,6 +48,7 @@ struct Engine {
   std::vector<uint32_t> h_trace_z;
   bool sampled = false, collected = false;
   pa_counters counters{};
+  unsigned long long phase_cycles[10] = {0};  // SM cycles spent per chain-kernel phase (thread 0 of every CTA, summed)
 
   ~Engine();
   void release_device();

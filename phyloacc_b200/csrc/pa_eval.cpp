@@ -119,10 +119,10 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
   PA_CUDA(cudaMalloc(&d_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
   PA_CUDA(cudaMalloc(&d_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));
   PA_CUDA(cudaMalloc(&d_arena, stride * grid));
-  PA_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * 8));
+  PA_CUDA(cudaMalloc(&d_counters, sizeof(unsigned long long) * 24));
   PA_CUDA(cudaMalloc(&d_queue, sizeof(int)));
   PA_CUDA(cudaMemcpyAsync(d_chain_list, list.data(), sizeof(int32_t) * 2 * n_chains, cudaMemcpyHostToDevice, stream));
-  PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 8, stream));
+  PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 24, stream));
   PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int), stream));
 
   ChainLaunch L;
@@ -163,7 +163,7 @@ int Engine::fetch_traces() {
   PA_CUDA(cudaSetDevice(device));
   h_trace_d.resize((size_t)6 * T * n_chains);
   h_trace_z.resize((size_t)ZW * T * n_chains);
-  unsigned long long hc[8];
+  unsigned long long hc[24];
   PA_CUDA(cudaMemcpyAsync(h_trace_d.data(), d_trace_d, sizeof(double) * h_trace_d.size(), cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaMemcpyAsync(h_trace_z.data(), d_trace_z, sizeof(uint32_t) * h_trace_z.size(), cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaMemcpyAsync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
@@ -173,6 +173,7 @@ int Engine::fetch_traces() {
   counters.pt_builds = hc[2];
   counters.history_draws = hc[3];
   counters.chain_iterations = hc[4];
+  for (int k = 0; k < 10; k++) phase_cycles[k] = hc[8 + k];
   collected = true;
   return PA_OK;
 }

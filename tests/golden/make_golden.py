@@ -40,6 +40,10 @@ CASES = {
                   params=dict(BURNIN=10, MCMC=40, CHAIN=1, ADAPT_FREQ=10, SEED=2, TRIM_GAP_PERCENT=0.6, PRUNE_TREE=1, HYPER_LRATE2_A=0,
                               MIN_LEN=20, GAP_PROP=0.5),
                   n_states=2, chains=[0, 1], refrun_seeds=[1, 2]),
+    # longer chains, several seeds of the reference binary: distributional targets (BF1/BF2, posterior Z, rate medians)
+    "post43": dict(S=43, tree_seed=43, C=6, length=100, seed=21, gap=0.01, missing=0.03, ambig=0.0,
+                   params=dict(BURNIN=200, MCMC=400, CHAIN=1, ADAPT_FREQ=100, SEED=1), n_states=1, chains=[],
+                   refrun_seeds=[1, 2, 3, 4, 5, 6], only=None),
 }
 
 
@@ -65,7 +69,10 @@ def load_case(outdir):
 
 def main():
     rng = np.random.default_rng(2026)
+    only = sys.argv[1:] or None
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         cdir = os.path.join(GOLD, name)
         if os.path.exists(cdir):
             shutil.rmtree(cdir)

@@ -29,3 +29,6 @@ res = eng.collect()
 dt = time.time() - t0
 c = eng.counters()
 print(f"elems={elems} iters={iters} wall={dt:.3f}s  el-iter/s={elems * 3 * iters / dt:.0f}  counters={c}")
+ph = eng.phase_cycles()
+tot = sum(ph.values())
+print("phase cycles per chain-iteration:", {k: round(v / max(c["chain_iterations"], 1)) for k, v in ph.items()}, "total", round(tot / max(c["chain_iterations"], 1)))
