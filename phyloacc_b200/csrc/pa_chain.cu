@@ -9,9 +9,11 @@
 //   sample_rate (n, then c): MH with the histories integrated out (log_f_Xz)                 bpp_c.cpp:860-1176
 //   sample_transition: Beta draws for g, l, l2                                               bpp_c.cpp:522-613
 //
-// Data layout: tip codes (4 bit), weights, gap masks and the pruning program of the element come from its blob in
-// HBM; per-pattern partials of every internal node live in this CTA's arena (HBM, L2-resident while the chain
-// runs); proposal evaluations keep their partials in a per-thread shared-memory stack and never touch the arena.
+// Data layout.  Tip codes (4 bit), weights, gap masks and the tree of the element come from its blob in HBM.  The
+// per-pattern partials of every internal node live in this CTA's arena in HBM (L2-resident while the chain runs) in
+// TWO copies; a per-node selector says which copy is current.  A pruning pass keeps the partials it recomputes in a
+// per-thread shared-memory stack (for its own parents) and streams them to the non-current copy; accepting a
+// proposal just flips the selectors of the recomputed nodes, rejecting leaves everything untouched.
 // Random numbers: Philox4x32-10 indexed by (chain, iteration, purpose, site/node), see oracle/oracle.h.
 #include <cuda_runtime.h>
 
@@ -27,17 +29,18 @@ namespace {
 constexpr int kBD = 256;
 constexpr int kNW = kBD / 32;
 
-// scalar slots in shared memory
-enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_LLNEW, SC_R, SC_COUNT = 16 };
-enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_STALE, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NDIRTY, IV_COUNT = 16 };
+enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R, SC_COUNT = 16 };
+enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_NTIPS, IV_COUNT = 16 };
 
 struct Smem {
   double *Pcur, *Pprop, *stack, *red, *emis, *back, *eamb, *dist, *uz, *scal, *T;  // T: [2][9] linear Z transition (free, fixed)
+  uint4* ops;        // [ni] pruning program (SU order), see build in init
+  uint2* tipl;       // [n] non-missing tips: {node | tiprow << 16, parent's internal index}
   int *stack_sc, *ivars, *nz;
-  uint32_t *cnt, *xs;
-  int16_t *parent, *child, *tiprow, *su, *intidx, *intlist, *up_nodes, *up_off, *down_nodes, *down_off;
-  uint8_t *flags, *fix, *dirty, *stale, *cnt8;
-  int8_t *slot, *Z, *Znew;
+  uint32_t *cnt, *hs;  // hs: [ni] history descriptors: node | parent's internal index << 16 (0xffff for the root)
+  int16_t *parent, *child, *intidx, *up_nodes, *up_off, *down_nodes, *down_off;
+  uint8_t *flags, *fix, *dirty, *sel, *cnt8, *xs8;
+  int8_t *Z, *Znew;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -45,7 +48,6 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(
 __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int n, int slots, int BD) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return base ? base + r : (unsigned char*)nullptr; };
-  const int XW = (n + 15) / 16 + 1;
   unsigned char* p;
   p = take(sizeof(double) * n * 16); if (s) s->Pcur = (double*)p;
   p = take(sizeof(double) * n * 16); if (s) s->Pprop = (double*)p;
@@ -58,17 +60,16 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int n, int
   p = take(sizeof(double) * n); if (s) s->uz = (double*)p;
   p = take(sizeof(double) * SC_COUNT); if (s) s->scal = (double*)p;
   p = take(sizeof(double) * 18); if (s) s->T = (double*)p;
+  p = take(sizeof(uint4) * n); if (s) s->ops = (uint4*)p;
+  p = take(sizeof(uint2) * n); if (s) s->tipl = (uint2*)p;
   p = take(sizeof(int) * slots * BD); if (s) s->stack_sc = (int*)p;
   p = take(sizeof(int) * IV_COUNT); if (s) s->ivars = (int*)p;
   p = take(sizeof(int) * 18); if (s) s->nz = (int*)p;
   p = take(sizeof(uint32_t) * n * 16); if (s) s->cnt = (uint32_t*)p;
-  p = take(sizeof(uint32_t) * XW * BD); if (s) s->xs = (uint32_t*)p;
+  p = take(sizeof(uint32_t) * n); if (s) s->hs = (uint32_t*)p;
   p = take(sizeof(int16_t) * n); if (s) s->parent = (int16_t*)p;
   p = take(sizeof(int16_t) * 2 * n); if (s) s->child = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->tiprow = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->su = (int16_t*)p;
   p = take(sizeof(int16_t) * n); if (s) s->intidx = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->intlist = (int16_t*)p;
   p = take(sizeof(int16_t) * n); if (s) s->up_nodes = (int16_t*)p;
   p = take(sizeof(int16_t) * (n + 1)); if (s) s->up_off = (int16_t*)p;
   p = take(sizeof(int16_t) * n); if (s) s->down_nodes = (int16_t*)p;
@@ -76,9 +77,9 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int n, int
   p = take(n); if (s) s->flags = p;
   p = take(n); if (s) s->fix = p;
   p = take(n); if (s) s->dirty = p;
-  p = take(n); if (s) s->stale = p;
+  p = take(n); if (s) s->sel = p;
   p = take((size_t)(BD / 32) * n * 16); if (s) s->cnt8 = p;
-  p = take(n); if (s) s->slot = (int8_t*)p;
+  p = take((size_t)((n + 1) / 2) * BD); if (s) s->xs8 = p;
   p = take(n); if (s) s->Z = (int8_t*)p;
   p = take(n); if (s) s->Znew = (int8_t*)p;
   return o;
@@ -96,25 +97,104 @@ __device__ __forceinline__ void mark_ancestors(const int16_t* parent, uint8_t* d
   }
 }
 
-// one pruning pass over all patterns of the element; returns sum_p w_p log L_p when REDUCE
-template <bool READ_G, bool WRITE_G, bool REDUCE>
-__device__ __forceinline__ double prune_all(const ElemView& ev, const Smem& S, const TreeSmem& ts, const double* Pm, const uint8_t* dirty,
-                                            double* gpart, int16_t* gsc, const double* pi, int tid) {
+struct Arena {
+  double* part;        // [2][n_max][P_max][4]
+  int16_t* sc;         // [2][n_max][P_max]
+  size_t part_stride;  // doubles between the two copies
+  size_t sc_stride;
+};
+
+// One Felsenstein pass over every pattern of the element (linear space, fp64).  Thread = pattern.  Nodes are visited
+// in the element's pruning order; with USE_DIRTY only flagged nodes are recomputed (their clean children are read
+// from the current arena copy).  Every recomputed node is written to copy sel[s]^wflip.  Returns sum_p w_p log L_p.
+template <bool USE_DIRTY>
+__device__ __forceinline__ double prune_pass(const ElemView& ev, const Smem& S, const double* __restrict__ Pm, int wflip, const Arena& A, int n_su,
+                                             const double* __restrict__ pi, int tid, bool reduce) {
+  const int P = ev.h->P, Ppad = ev.h->Ppad, half = Ppad >> 1;
   double acc = 0.0;
-  const int P = ev.h->P, Ppad = ev.h->Ppad;
   for (int p = tid; p < Ppad; p += kBD) {
     if (p < P) {
-      const double ll = prune_pattern<READ_G, WRITE_G>(ev.h, ts, ev.codes, Pm, dirty, S.stack, S.stack_sc, gpart, gsc, pi, p, kBD, tid);
-      if (REDUCE) acc += (double)ev.weights[p] * ll;
+      const uint8_t* __restrict__ cp = ev.codes + (p >> 1);
+      const int sh = (p & 1) * 4;
+      double o0 = 1.0, o1 = 1.0, o2 = 1.0, o3 = 1.0;
+      int sc = 0;
+      for (int k = 0; k < n_su; k++) {
+        const uint4 op = S.ops[k];
+        const int s = op.x & 0xffff;
+        if (USE_DIRTY && !S.dirty[s]) continue;
+        o0 = o1 = o2 = o3 = 1.0;
+        sc = 0;
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const int kind = (op.z >> (2 * cc)) & 3;
+          if (kind == 0) continue;  // missing child (bpp_c.cpp:660)
+          const int ch = cc ? (int)(op.y >> 16) : (int)(op.y & 0xffff);
+          const int x = cc ? (int)(op.w >> 16) : (int)(op.w & 0xffff);
+          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch * 16);
+          if (kind == 1) {
+            const uint32_t code = ((uint32_t)__ldg(cp + x * half) >> sh) & 15u;
+            if (code == 15u) continue;  // gap / N: Tg >= num_base (bpp_c.cpp:660)
+            if ((code & (code - 1)) == 0) {
+              const int b = __ffs(code) - 1;
+              const double* Pd = Pm + ch * 16 + b;
+              o0 *= Pd[0]; o1 *= Pd[4]; o2 *= Pd[8]; o3 *= Pd[12];
+            } else {
+              const double m0 = (code & 1u) ? 1.0 : 0.0, m1 = (code & 2u) ? 1.0 : 0.0, m2 = (code & 4u) ? 1.0 : 0.0, m3 = (code & 8u) ? 1.0 : 0.0;
+              const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
+              o0 *= ((m0 * r00.x + m1 * r00.y) + m2 * r01.x) + m3 * r01.y;
+              o1 *= ((m0 * r10.x + m1 * r10.y) + m2 * r11.x) + m3 * r11.y;
+              o2 *= ((m0 * r20.x + m1 * r20.y) + m2 * r21.x) + m3 * r21.y;
+              o3 *= ((m0 * r30.x + m1 * r30.y) + m2 * r31.x) + m3 * r31.y;
+            }
+          } else {
+            double L0, L1, L2, L3;
+            if (!USE_DIRTY || S.dirty[ch]) {
+              const int sl = (op.z >> (16 + 8 * cc)) & 0xff;
+              const double* st = S.stack + sl * 4 * kBD + tid;
+              L0 = st[0]; L1 = st[kBD]; L2 = st[2 * kBD]; L3 = st[3 * kBD];
+              sc += S.stack_sc[sl * kBD + tid];
+            } else {
+              const int a = S.sel[ch];
+              const double2* g2 = reinterpret_cast<const double2*>(A.part + a * A.part_stride + ((size_t)x * Ppad + p) * 4);
+              const double2 u = g2[0], v = g2[1];
+              L0 = u.x; L1 = u.y; L2 = v.x; L3 = v.y;
+              sc += A.sc[a * A.sc_stride + (size_t)x * Ppad + p];
+            }
+            const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
+            o0 *= ((r00.x * L0 + r00.y * L1) + r01.x * L2) + r01.y * L3;
+            o1 *= ((r10.x * L0 + r10.y * L1) + r11.x * L2) + r11.y * L3;
+            o2 *= ((r20.x * L0 + r20.y * L1) + r21.x * L2) + r21.y * L3;
+            o3 *= ((r30.x * L0 + r30.y * L1) + r31.x * L2) + r31.y * L3;
+          }
+        }
+        // rescale by 2^256 when every entry dropped below 2^-256 (compare high words: all values are >= 0)
+        const int hm = max(max(__double2hiint(o0), __double2hiint(o1)), max(__double2hiint(o2), __double2hiint(o3)));
+        if (hm < 0x2FF00000 && hm > 0) {
+          o0 *= PA_SCALE_UP; o1 *= PA_SCALE_UP; o2 *= PA_SCALE_UP; o3 *= PA_SCALE_UP;
+          sc += 1;
+        }
+        const int sl = (op.z >> 8) & 0xff;
+        double* st = S.stack + sl * 4 * kBD + tid;
+        st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
+        S.stack_sc[sl * kBD + tid] = sc;
+        const int q = op.x >> 16;
+        const int a = S.sel[s] ^ wflip;
+        double2* g2 = reinterpret_cast<double2*>(A.part + a * A.part_stride + ((size_t)q * Ppad + p) * 4);
+        g2[0] = make_double2(o0, o1);
+        g2[1] = make_double2(o2, o3);
+        A.sc[a * A.sc_stride + (size_t)q * Ppad + p] = (int16_t)sc;
+      }
+      // the last node of the program is the root (or nothing was computed: missing root -> likelihood 1)
+      const double lik = ((pi[0] * o0 + pi[1] * o1) + pi[2] * o2) + pi[3] * o3;
+      acc += (double)ev.weights[p] * (log(lik) - sc * PA_LOG_SCALE);
     }
   }
-  if (REDUCE) return block_sum(acc, S.red, tid, kBD);
+  if (reduce) return block_sum(acc, S.red, tid, kBD);
   return 0.0;
 }
 
-// log-space serial Z update, a literal restatement of Update_Z_subtree; used only when the scaled linear pass underflows
-__device__ void z_update_logspace(const Smem& S, int n, const double* Tlin, uint32_t* changed_flag) {
-  // log transition matrices
+// log-space serial Z update, a literal restatement of Update_Z_subtree; used only when the scaled linear pass degenerates
+__device__ void z_update_logspace(const Smem& S, int n, const double* Tlin) {
   double lt[2][9];
   for (int f = 0; f < 2; f++)
     for (int k = 0; k < 9; k++) lt[f][k] = log(Tlin[f * 9 + k]);
@@ -145,9 +225,25 @@ __device__ void z_update_logspace(const Smem& S, int n, const double* Tlin, uint
     const double* t = lt[S.fix[i] ? 1 : 0];
     const int zp = S.Znew[S.parent[i]];
     double v[3];
+    if (zp < 0 || zp > 2) { S.Znew[i] = -1; continue; }
     for (int a = 0; a < 3; a++) v[a] = t[a * 3 + zp] + S.back[i * 3 + a];
     const double mx = fmax(v[0], fmax(v[1], v[2]));
     S.Znew[i] = (int8_t)categorical3(exp(v[0] - mx), exp(v[1] - mx), exp(v[2] - mx), S.uz[i]);
+  }
+}
+
+// counts of (parent base, child base) pairs over the 32 sites of a warp, written to the warp's tile-count row
+__device__ __forceinline__ void warp_count16(uint32_t code, bool act, uint8_t* __restrict__ row, int lane) {
+  const uint32_t bv = __ballot_sync(0xffffffffu, act);
+  const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, code & 2u);
+  const uint32_t b2 = __ballot_sync(0xffffffffu, code & 4u), b3 = __ballot_sync(0xffffffffu, code & 8u);
+  if (lane < 16) {
+    uint32_t mm = bv;
+    mm &= (lane & 1) ? b0 : ~b0;
+    mm &= (lane & 2) ? b1 : ~b1;
+    mm &= (lane & 4) ? b2 : ~b2;
+    mm &= (lane & 8) ? b3 : ~b3;
+    row[lane] = (uint8_t)__popc(mm);
   }
 }
 
@@ -161,20 +257,23 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
   __shared__ double s_pi[4];
   if (tid < 4) s_pi[tid] = sd.pi[tid];
 
-  // this CTA's arena: partials [ni][Ppad][4] f64, scale counts [ni][Ppad] i16, log P tables [3][n_max][16] f64
+  // this CTA's arena: log P tables [3][n_max][16] f64, partials [2][n_max][P_max][4] f64, scale counts [2][n_max][P_max] i16
   unsigned char* arena = L.arena + (size_t)blockIdx.x * L.arena_stride;
   double* logP = reinterpret_cast<double*>(arena);
-  double* gpart = logP + (size_t)3 * L.n_max * 16;
-  int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)L.n_max * L.P_max * 4);
+  Arena A;
+  A.part = logP + (size_t)3 * L.n_max * 16;
+  A.part_stride = (size_t)L.n_max * L.P_max * 4;
+  A.sc = reinterpret_cast<int16_t*>(A.part + 2 * A.part_stride);
+  A.sc_stride = (size_t)L.n_max * L.P_max;
 
   unsigned long long w_npu = 0, w_root = 0, w_pt = 0, w_hist = 0, w_iter = 0;  // work counters (thread 0)
   long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, ph6 = 0, ph7 = 0, ph8 = 0, ph9 = 0;  // SM cycles per phase (thread 0)
   long long t_last = clock64();
-#define PA_PHASE(var)                \
-  if (tid == 0) {                    \
+#define PA_PHASE(var)                  \
+  if (tid == 0) {                      \
     const long long t_now = clock64(); \
-    var += t_now - t_last;           \
-    t_last = t_now;                  \
+    var += t_now - t_last;             \
+    t_last = t_now;                    \
   }
 
   for (;;) {
@@ -196,77 +295,100 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       S.parent[i] = ev.parent[i];
       S.child[2 * i] = ev.child[2 * i];
       S.child[2 * i + 1] = ev.child[2 * i + 1];
-      S.tiprow[i] = ev.tiprow[i];
       S.intidx[i] = ev.intidx[i];
       S.up_nodes[i] = ev.up_nodes[i];
       S.down_nodes[i] = ev.down_nodes[i];
       const uint8_t f = ev.flags[i];
       S.flags[i] = f;
       S.fix[i] = (f >> (2 + mdl)) & 1;
-      S.slot[i] = ev.slot[i];
       S.dist[i] = ev.dist[i];
       S.Z[i] = (i == root) ? 0 : 1;  // bpp_c.cpp:141-146
       S.dirty[i] = 0;
-      S.stale[i] = 0;
-    }
-    for (int i = tid; i < ni; i += kBD) {
-      S.su[i] = ev.su[i];
-      S.intlist[i] = ev.intlist[i];
+      S.sel[i] = 0;
     }
     for (int i = tid; i <= h->n_up; i += kBD) S.up_off[i] = ev.up_off[i];
     for (int i = tid; i <= h->n_down; i += kBD) S.down_off[i] = ev.down_off[i];
+    // pruning program: one packed descriptor per computed internal node, in the element's pruning order
+    for (int k = tid; k < ni; k += kBD) {
+      const int s = ev.su[k];
+      uint4 op = make_uint4(0, 0, 0, 0);
+      if (s >= 0) {
+        const int c0 = ev.child[2 * s], c1 = ev.child[2 * s + 1];
+        auto kind_of = [&](int c) { const uint8_t f = ev.flags[c]; return (f & PA_F_MISSING) ? 0u : ((f & PA_F_TIP) ? 1u : 2u); };
+        auto x_of = [&](int c) { return (uint32_t)((ev.flags[c] & PA_F_TIP) ? ev.tiprow[c] : ev.intidx[c]) & 0xffffu; };
+        const uint32_t k0 = kind_of(c0), k1 = kind_of(c1);
+        op.x = (uint32_t)s | ((uint32_t)ev.intidx[s] << 16);
+        op.y = (uint32_t)c0 | ((uint32_t)c1 << 16);
+        op.z = k0 | (k1 << 2) | ((uint32_t)(uint8_t)ev.slot[s] << 8) | ((uint32_t)(uint8_t)(k0 == 2 ? ev.slot[c0] : 0) << 16) |
+               ((uint32_t)(uint8_t)(k1 == 2 ? ev.slot[c1] : 0) << 24);
+        op.w = x_of(c0) | (x_of(c1) << 16);
+      }
+      S.ops[k] = op;
+      // history descriptor of internal node q = k (post-order)
+      const int sq = ev.intlist[k];
+      const int par = ev.parent[sq];
+      S.hs[k] = (uint32_t)sq | ((par >= 0 ? (uint32_t)ev.intidx[par] : 0xffffu) << 16);
+    }
     if (tid == 0) {
+      int nsu = 0;
+      while (nsu < ni && ev.su[nsu] >= 0) nsu++;
+      S.ivars[IV_NSU] = nsu;
+      int nt = 0;
+      for (int i = 0; i < n; i++) {
+        const uint8_t f = ev.flags[i];
+        if ((f & PA_F_TIP) && !(f & PA_F_MISSING)) {
+          S.tipl[nt] = make_uint2((uint32_t)i | ((uint32_t)ev.tiprow[i] << 16), (uint32_t)ev.intidx[ev.parent[i]]);
+          nt++;
+        }
+      }
+      S.ivars[IV_NTIPS] = nt;
       S.scal[SC_N] = cp.init_nrate;
       S.scal[SC_C] = cp.init_crate;
       S.scal[SC_G] = cp.init_grate;
       S.scal[SC_L] = cp.init_lrate;
       S.scal[SC_L2] = cp.init_lrate2;
-      S.scal[SC_PROPC] = 1.2;                      // bpp_c.cpp:135
-      S.scal[SC_PROPN] = (double)1 / GG * 10;      // bpp_c.cpp:136
+      S.scal[SC_PROPC] = 1.2;                  // bpp_c.cpp:135
+      S.scal[SC_PROPN] = (double)1 / GG * 10;  // bpp_c.cpp:136
       S.ivars[IV_ACC_N] = 0;
       S.ivars[IV_ACC_C] = 0;
-      S.ivars[IV_STALE] = 0;
-    }
-    __syncthreads();
-    const TreeSmem ts{S.child, S.flags, S.tiprow, S.su, S.slot, S.intidx};
-    // P(t) of every branch for its class, and the log P tables of the three classes (emission look-ups)
-    for (int task = tid; task < 3 * n; task += kBD) {
-      const int k = task / n, i = task - k * n;
-      double P16[16];
-      const double rate = (k == 0) ? 1.0 : (k == 1 ? cp.init_crate : cp.init_nrate);
-      build_P(sd, S.dist[i], rate, true, P16);
-      const int zi = S.Z[i];
-      const int kz = (zi == 0) ? 0 : (zi == 2 ? 2 : 1);
-#pragma unroll
-      for (int e = 0; e < 16; e++) {
-        logP[((size_t)k * L.n_max + i) * 16 + e] = log(P16[e]);
-        if (k == kz) S.Pcur[i * 16 + e] = P16[e];
-      }
-    }
-    if (tid == 0) {  // linear Z transition matrices (bpp_c.cpp:301-332), index [child state a][parent state j] -> a*3+j
+      // linear Z transition matrices (bpp_c.cpp:301-332), index [child state a][parent state j] -> a*3+j
       const double g = cp.init_grate, l = cp.init_lrate, l2 = cp.init_lrate2;
-      double* Tf = S.T;       // free
-      double* Tx = S.T + 9;   // fixZ == 1
+      double* Tf = S.T;      // free
+      double* Tx = S.T + 9;  // fixZ == 1
       const double y = 1 - l;
       Tf[0] = 1 - g; Tf[3] = g; Tf[6] = 0; Tf[1] = 0; Tf[4] = y; Tf[7] = 1 - y; Tf[2] = 0; Tf[5] = l2; Tf[8] = 1 - l2;
       Tx[0] = 1 - g; Tx[3] = g; Tx[6] = 0; Tx[1] = 0; Tx[4] = 1; Tx[7] = 0; Tx[2] = 1; Tx[5] = 1; Tx[8] = 1;
       w_pt += 3ull * n;
     }
     __syncthreads();
-    // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in the arena
+    const int n_su = S.ivars[IV_NSU], n_tips = S.ivars[IV_NTIPS];
+    // P(t) of every branch for its class, and the log P tables of the three classes (emission look-ups); task = (class, node, row)
+    for (int task = tid; task < 12 * n; task += kBD) {
+      const int k = task / (4 * n), rem = task - k * 4 * n, i = rem >> 2, j = rem & 3;
+      const double rate = (k == 0) ? 1.0 : (k == 1 ? cp.init_crate : cp.init_nrate);
+      double r0, r1, r2, r3;
+      build_P_row(sd, S.dist[i], rate, j, r0, r1, r2, r3);
+      double* lp = logP + ((size_t)k * L.n_max + i) * 16 + j * 4;
+      lp[0] = log(r0); lp[1] = log(r1); lp[2] = log(r2); lp[3] = log(r3);
+      const int zi = S.Z[i];
+      if (k == ((zi == 0) ? 0 : (zi == 2 ? 2 : 1))) {
+        double* pc = S.Pcur + i * 16 + j * 4;
+        pc[0] = r0; pc[1] = r1; pc[2] = r2; pc[3] = r3;
+      }
+    }
+    __syncthreads();
+    // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in arena copy 0
     {
-      const double ll = prune_all<false, true, true>(ev, S, ts, S.Pcur, nullptr, gpart, gsc, s_pi, tid);
+      const double ll = prune_pass<false>(ev, S, S.Pcur, 0, A, n_su, s_pi, tid, true);
       if (tid == 0) {
         S.scal[SC_LL] = ll;
-        int cnt_nodes = 0;
-        for (int k = 0; k < ni && S.su[k] >= 0; k++) cnt_nodes++;
-        w_npu += (unsigned long long)cnt_nodes * h->P;
+        w_npu += (unsigned long long)n_su * h->P;
         w_root += h->P;
       }
     }
     __syncthreads();
-
     PA_PHASE(ph0)
+
     double* tr_d = L.trace_d + (size_t)chain * 6 * T;
     uint32_t* tr_z = L.trace_z + (size_t)chain * T * L.ZW;
 
@@ -286,14 +408,13 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       if (m == T - 1) break;
       if (tid == 0) w_iter++;
-      PA_PHASE(ph1)
 
       // ---------------- sample ancestral histories site by site + count parent->child base pairs per branch
       for (int i = tid; i < n * 16; i += kBD) S.cnt[i] = 0;
       for (int i = tid; i < n * 3; i += kBD) S.eamb[i] = 0.0;
-      const int XW = (ni + 15) >> 4;
       const double cur_n = S.scal[SC_N], cur_c = S.scal[SC_C];
       __syncthreads();
+      PA_PHASE(ph1)
       for (int g0 = 0; g0 < GG; g0 += kBD) {
         const int g = g0 + tid;
         const bool valid = g < GG;
@@ -301,94 +422,72 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         uint32_t gw0 = 0, gw1 = 0;
         if (h->W >= 1) gw0 = ev.gap[pat];
         if (h->W >= 2) gw1 = ev.gap[Ppad + pat];
-        for (int w = 0; w < XW; w++) S.xs[w * kBD + tid] = 0;
+        const double* gp = A.part + (size_t)pat * 4;
         uint4 rnd = make_uint4(0, 0, 0, 0);
         int have = -1;
+        uint8_t* xs = S.xs8 + tid;
+        uint8_t* c8 = S.cnt8 + (size_t)warp * n * 16;
         for (int q = ni - 1; q >= 0; q--) {
-          const int s = S.intlist[q];
+          const uint32_t d = S.hs[q];
+          const int s = d & 0xffff;
           if (S.flags[s] & PA_F_MISSING) continue;
-          const bool isroot = (s == root);
+          const uint32_t qp = d >> 16;
+          const bool isroot = (qp == 0xffffu);
           bool gapbit;
           if (q < 32) gapbit = (gw0 >> q) & 1u;
           else if (q < 64) gapbit = (gw1 >> (q - 32)) & 1u;
           else gapbit = (ev.gap[(size_t)(q >> 5) * Ppad + pat] >> (q & 31)) & 1u;
           const bool active = valid && (isroot || !gapbit);
-          int x = 0, xp = 0;
-          if (!isroot) {
-            const int qp = S.intidx[S.parent[s]];
-            xp = (S.xs[(qp >> 4) * kBD + tid] >> (2 * (qp & 15))) & 3;
-          }
+          const int xp = isroot ? 0 : (int)xs[qp * kBD];
+          int x = 0;
           if (active) {
             if ((q >> 2) != have) {
               rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)(q >> 2), (uint32_t)m, PA_ST_HIST);
               have = q >> 2;
             }
             const double u = u01(pick(rnd, q & 3));
-            const double2* g2 = reinterpret_cast<const double2*>(gpart + ((size_t)q * Ppad + pat) * 4);
+            const double2* g2 = reinterpret_cast<const double2*>(gp + S.sel[s] * A.part_stride + (size_t)q * Ppad * 4);
             const double2 a = g2[0], b = g2[1];
             double p0, p1, p2, p3;
             if (isroot) {
               p0 = a.x * s_pi[0]; p1 = a.y * s_pi[1]; p2 = b.x * s_pi[2]; p3 = b.y * s_pi[3];
             } else {
-              const double* Pr = S.Pcur + s * 16 + xp * 4;
-              p0 = Pr[0] * a.x; p1 = Pr[1] * a.y; p2 = Pr[2] * b.x; p3 = Pr[3] * b.y;
+              const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
+              const double2 r0 = Pr[0], r1 = Pr[1];
+              p0 = r0.x * a.x; p1 = r0.y * a.y; p2 = r1.x * b.x; p3 = r1.y * b.y;
             }
-            x = categorical4(p0, p1, p2, p3, u);
-            if (x < 0) x = 0;
-            S.xs[(q >> 4) * kBD + tid] |= (uint32_t)x << (2 * (q & 15));
+            // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
+            const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
+            x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
+            xs[q * kBD] = (uint8_t)x;
           }
-          if (!isroot) {  // counts of (parent base, child base) over the 32 sites of this warp
-            const uint32_t code = (uint32_t)(xp * 4 + x);
-            const uint32_t bv = __ballot_sync(0xffffffffu, active);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, code & 2u);
-            const uint32_t b2 = __ballot_sync(0xffffffffu, code & 4u), b3 = __ballot_sync(0xffffffffu, code & 8u);
-            if (lane < 16) {
-              uint32_t mm = bv;
-              mm &= (lane & 1) ? b0 : ~b0;
-              mm &= (lane & 2) ? b1 : ~b1;
-              mm &= (lane & 4) ? b2 : ~b2;
-              mm &= (lane & 8) ? b3 : ~b3;
-              S.cnt8[((size_t)warp * n + s) * 16 + lane] = (uint8_t)__popc(mm);
-            }
-          }
+          if (!isroot) warp_count16((uint32_t)(xp * 4 + x), active, c8 + s * 16, lane);
         }
         // tip branches: the tip's base is data, the parent's base was just sampled
-        for (int i = 0; i < n; i++) {
-          const uint8_t f = S.flags[i];
-          if (!(f & PA_F_TIP) || (f & PA_F_MISSING)) continue;
+        for (int k = 0; k < n_tips; k++) {
+          const uint2 td = S.tipl[k];
+          const int i = td.x & 0xffff;
           uint32_t code4 = 15u;
-          if (valid) code4 = (ev.codes[(size_t)S.tiprow[i] * (Ppad >> 1) + (pat >> 1)] >> ((pat & 1) * 4)) & 15u;
-          const int qp = S.intidx[S.parent[i]];
-          const int xp = (S.xs[(qp >> 4) * kBD + tid] >> (2 * (qp & 15))) & 3;
+          if (valid) code4 = ((uint32_t)__ldg(ev.codes + (size_t)(td.x >> 16) * (Ppad >> 1) + (pat >> 1)) >> ((pat & 1) * 4)) & 15u;
+          const int xp = xs[td.y * kBD];
           const bool onehot = (code4 & (code4 - 1)) == 0;  // code4 is never 0
           const bool act = valid && code4 != 15u && onehot;
-          const uint32_t code = (uint32_t)(xp * 4 + (onehot ? (__ffs(code4) - 1) : 0));
-          const uint32_t bv = __ballot_sync(0xffffffffu, act);
-          const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, code & 2u);
-          const uint32_t b2 = __ballot_sync(0xffffffffu, code & 4u), b3 = __ballot_sync(0xffffffffu, code & 8u);
-          if (lane < 16) {
-            uint32_t mm = bv;
-            mm &= (lane & 1) ? b0 : ~b0;
-            mm &= (lane & 2) ? b1 : ~b1;
-            mm &= (lane & 4) ? b2 : ~b2;
-            mm &= (lane & 8) ? b3 : ~b3;
-            S.cnt8[((size_t)warp * n + i) * 16 + lane] = (uint8_t)__popc(mm);
-          }
+          warp_count16((uint32_t)(xp * 4 + (onehot ? (__ffs(code4) - 1) : 0)), act, c8 + i * 16, lane);
           if (valid && code4 != 15u && !onehot) {  // ambiguity code: log sum_{b in code} P_k(xp -> b) (bpp_c2.cpp:372-378)
-            for (int k = 0; k < 3; k++) {
-              const double* lp = logP + ((size_t)k * L.n_max + i) * 16 + xp * 4;
+            for (int kk = 0; kk < 3; kk++) {
+              const double* lp = logP + ((size_t)kk * L.n_max + i) * 16 + xp * 4;
               double sum = 0;
               for (int b = 0; b < 4; b++)
                 if ((code4 >> b) & 1u) sum += exp(lp[b]);
-              atomicAdd(&S.eamb[i * 3 + k], log(sum));
+              atomicAdd(&S.eamb[i * 3 + kk], log(sum));
             }
           }
         }
         __syncthreads();
         for (int idx = tid; idx < (n - 1) * 16; idx += kBD) {  // merge the per-warp tile counts
-          uint32_t sum = 0;
-          const int nd = idx >> 4;
-          if (!(S.flags[nd] & PA_F_MISSING)) {
+          if (!(S.flags[idx >> 4] & PA_F_MISSING)) {
+            uint32_t sum = 0;
+#pragma unroll
             for (int w = 0; w < kNW; w++) sum += S.cnt8[(size_t)w * n * 16 + idx];
             S.cnt[idx] += sum;
           }
@@ -396,9 +495,11 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         __syncthreads();
       }
       if (tid == 0) w_hist += (unsigned long long)GG * ni;
-
       PA_PHASE(ph2)
-      // ---------------- getEmission: e_s(k) = sum_bins count * log P_k (bpp_c2.cpp:355-390); missing nodes keep constants
+
+      // ---------------- getEmission (bpp_c2.cpp:355-390) fused with the start of Update_Z_subtree (bpp_c.cpp:1186-1200):
+      // e_s(k) = sum_bins count * log P_k, then b_s(k) = exp(e_s(k) - max) with state 2 masked on fixZ nodes, and the Z uniforms
+      if (tid == 0) S.ivars[IV_ZFALLBACK] = 0;
       for (int task = tid; task < n * 3; task += kBD) {
         const int i = task / 3, k = task - 3 * i;
         double e = 0.0;
@@ -407,6 +508,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
           else {
             e = S.eamb[task];
             const double* lp = logP + ((size_t)k * L.n_max + i) * 16;
+#pragma unroll 4
             for (int b = 0; b < 16; b++) {
               const uint32_t c = S.cnt[i * 16 + b];
               if (c) e += (double)c * lp[b];
@@ -416,22 +518,21 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         S.emis[task] = e;
       }
       __syncthreads();
-
+      for (int i = tid; i < n; i += kBD) {
+        double e0 = S.emis[i * 3], e1 = S.emis[i * 3 + 1], e2 = S.emis[i * 3 + 2];
+        if (S.fix[i]) e2 = -CUDART_INF;
+        const double mx = fmax(e0, fmax(e1, e2));
+        S.back[i * 3] = exp(e0 - mx);
+        S.back[i * 3 + 1] = exp(e1 - mx);
+        S.back[i * 3 + 2] = exp(e2 - mx);
+        S.uz[i] = u01(philox4(cp.seed, key, (uint32_t)i, 0u, (uint32_t)m, PA_ST_Z).x);
+        if (!(mx > -CUDART_INF) || mx != mx) S.ivars[IV_ZFALLBACK] = 1;
+      }
+      __syncthreads();
       PA_PHASE(ph3)
-      // ---------------- Update_Z_subtree (bpp_c.cpp:1182-1293): scaled linear messages by tree level, one warp
+
+      // ---------------- Update_Z_subtree (bpp_c.cpp:1204-1293): scaled linear messages by tree level, one warp
       if (warp == 0) {
-        if (lane == 0) S.ivars[IV_ZFALLBACK] = 0;
-        for (int i = lane; i < n; i += 32) {
-          double e0 = S.emis[i * 3], e1 = S.emis[i * 3 + 1], e2 = S.emis[i * 3 + 2];
-          if (S.fix[i]) e2 = -CUDART_INF;
-          const double mx = fmax(e0, fmax(e1, e2));
-          S.back[i * 3] = exp(e0 - mx);
-          S.back[i * 3 + 1] = exp(e1 - mx);
-          S.back[i * 3 + 2] = exp(e2 - mx);
-          S.uz[i] = u01(philox4(cp.seed, key, (uint32_t)i, 0u, (uint32_t)m, PA_ST_Z).x);
-          if (!(mx > -CUDART_INF) || mx != mx) S.ivars[IV_ZFALLBACK] = 1;
-        }
-        __syncwarp();
         for (int lv = 1; lv < h->n_up; lv++) {
           for (int idx = S.up_off[lv] + lane; idx < S.up_off[lv + 1]; idx += 32) {
             const int i = S.up_nodes[idx];
@@ -447,10 +548,13 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
             }
             const double mx = fmax(b0, fmax(b1, b2));
             if (!(mx > 0.0) || mx != mx) S.ivars[IV_ZFALLBACK] = 1;
-            const double inv = 1.0 / mx;
-            S.back[i * 3] = b0 * inv;
-            S.back[i * 3 + 1] = b1 * inv;
-            S.back[i * 3 + 2] = b2 * inv;
+            if (mx < 1e-100) {  // keep the scaled messages away from underflow; the scale cancels in the draws
+              const double inv = 1.0 / mx;
+              b0 *= inv; b1 *= inv; b2 *= inv;
+            }
+            S.back[i * 3] = b0;
+            S.back[i * 3 + 1] = b1;
+            S.back[i * 3 + 2] = b2;
           }
           __syncwarp();
         }
@@ -474,7 +578,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
           }
         }
         __syncwarp();
-        if (S.ivars[IV_ZFALLBACK] != 0 && lane == 0) z_update_logspace(S, n, S.T, nullptr);
+        if (S.ivars[IV_ZFALLBACK] != 0 && lane == 0) z_update_logspace(S, n, S.T);
         __syncwarp();
         if (lane == 0) {
           S.ivars[IV_ANY_CHANGED] = 0;
@@ -483,8 +587,8 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         }
       }
       __syncthreads();
-
       PA_PHASE(ph4)
+
       // ---------------- changed Z: dirty ancestors, class switch of P(t), class presence
       for (int i = tid; i < n; i += kBD) {
         const int zo = S.Z[i];
@@ -507,12 +611,12 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         }
       }
       __syncthreads();
-      if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431
-        const double ll = prune_all<true, true, true>(ev, S, ts, S.Pcur, S.dirty, gpart, gsc, s_pi, tid);
+      if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431 (recomputed partials overwrite the current copy in place)
+        const double ll = prune_pass<true>(ev, S, S.Pcur, 0, A, n_su, s_pi, tid, true);
         if (tid == 0) {
           S.scal[SC_LL] = ll;
           int cnt_nodes = 0;
-          for (int k = 0; k < ni && S.su[k] >= 0; k++) cnt_nodes += S.dirty[S.su[k]];
+          for (int k = 0; k < n_su; k++) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
           w_npu += (unsigned long long)cnt_nodes * h->P;
           w_root += h->P;
         }
@@ -520,8 +624,8 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       for (int i = tid; i < n; i += kBD) S.dirty[i] = 0;
       __syncthreads();
-
       PA_PHASE(ph5)
+
       // ---------------- sample_rate: accelerated rate n (cls 2), then conserved rate c (cls 1)  (bpp_c.cpp:930-1176)
       for (int step = 0; step < 2; step++) {
         const bool neut = (step == 0);
@@ -530,81 +634,88 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         const int has = neut ? S.ivars[IV_HAS2] : S.ivars[IV_HAS1];
         const double prior_a = neut ? cp.nprior_a : cp.cprior_a, prior_b = neut ? cp.nprior_b : cp.cprior_b;
         const double old_rate = neut ? S.scal[SC_N] : S.scal[SC_C];
-        // dirty set: ancestors of the class' branches, plus nodes whose stored partials are stale
-        for (int i = tid; i < n - 1; i += kBD) {
-          if (has && !(S.flags[i] & PA_F_MISSING) && S.Z[i] == cls) mark_ancestors(S.parent, S.dirty, i);
-          if (S.stale[i]) S.dirty[i] = 1;
-        }
-        if (tid == 0) {
-          if (S.stale[root]) S.dirty[root] = 1;
+        if (has)
+          for (int i = tid; i < n - 1; i += kBD)
+            if (!(S.flags[i] & PA_F_MISSING) && S.Z[i] == cls) mark_ancestors(S.parent, S.dirty, i);
+        if (warp == 0) {
+          // lane 0: proposal (or prior draw); lanes 0..3: the prior / Hastings terms of the MH ratio in parallel
           int valid = 0;
           double cur_r = old_rate, proposal = 0.0, r = 0.0;
-          if (!has) {  // no branch in this class: draw from the prior (bpp_c.cpp:940-964)
-            if (resZ != 0) {
-              cur_r = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, prior_a, prior_b);
-              if (neut) {
-                if (cp.ropt == 1 && cur_r < cp.nlb) cur_r = old_rate;
-                else if (cp.ropt == 2 && cur_r < S.scal[SC_C]) cur_r = old_rate;
-              } else {
-                if (cp.ropt == 1 && cur_r > cp.cub) cur_r = old_rate;
-                else if (cp.ropt == 2 && cur_r > S.scal[SC_N]) cur_r = old_rate;
+          if (lane == 0) {
+            if (!has) {  // no branch in this class: draw from the prior (bpp_c.cpp:940-964)
+              if (resZ != 0) {
+                cur_r = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, prior_a, prior_b);
+                if (neut) {
+                  if (cp.ropt == 1 && cur_r < cp.nlb) cur_r = old_rate;
+                  else if (cp.ropt == 2 && cur_r < S.scal[SC_C]) cur_r = old_rate;
+                } else {
+                  if (cp.ropt == 1 && cur_r > cp.cub) cur_r = old_rate;
+                  else if (cp.ropt == 2 && cur_r > S.scal[SC_N]) cur_r = old_rate;
+                }
               }
-            }
-          } else {
-            r = u01(philox4(cp.seed, key, which, 0u, (uint32_t)m, PA_ST_RATE).x);
-            valid = 1;
-            if (neut) {
-              proposal = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, old_rate / S.scal[SC_PROPN], S.scal[SC_PROPN]);
-              if (cp.ropt == 1 && proposal < cp.nlb) valid = 0;
-              else if (cp.ropt == 2 && proposal < S.scal[SC_C]) valid = 0;
             } else {
-              const double pc = S.scal[SC_PROPC];
-              const double u = r * (pc - 1 / pc) + 1 / pc;
-              proposal = old_rate * u;
-              if (cp.ropt == 1 && proposal > cp.cub) valid = 0;
-              else if (cp.ropt == 2 && proposal > S.scal[SC_N]) valid = 0;
+              r = u01(philox4(cp.seed, key, which, 0u, (uint32_t)m, PA_ST_RATE).x);
+              valid = 1;
+              if (neut) {
+                proposal = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, old_rate / S.scal[SC_PROPN], S.scal[SC_PROPN]);
+                if (cp.ropt == 1 && proposal < cp.nlb) valid = 0;
+                else if (cp.ropt == 2 && proposal < S.scal[SC_C]) valid = 0;
+              } else {
+                const double pc = S.scal[SC_PROPC];
+                const double u = r * (pc - 1 / pc) + 1 / pc;
+                proposal = old_rate * u;
+                if (cp.ropt == 1 && proposal > cp.cub) valid = 0;
+                else if (cp.ropt == 2 && proposal > S.scal[SC_N]) valid = 0;
+              }
+              if (proposal < 1e-12 || proposal > 1e8) valid = 0;
             }
-            if (proposal < 1e-12 || proposal > 1e8) valid = 0;
           }
-          S.scal[SC_PROPOSAL] = valid ? proposal : cur_r;
-          S.scal[SC_R] = r;
-          S.ivars[IV_VALID] = valid;
-          S.ivars[IV_ACCEPT] = 0;
-          S.ivars[IV_RATE_CHANGED] = (!valid && cur_r != old_rate) ? 1 : 0;
+          valid = __shfl_sync(0xffffffffu, valid, 0);
+          proposal = __shfl_sync(0xffffffffu, proposal, 0);
+          double term = 0.0;
+          if (valid) {
+            const double pn = S.scal[SC_PROPN];
+            double x = proposal, a = prior_a, b = prior_b, sgn = 1.0;               // lane 0: + log pdf(proposal | prior)
+            if (lane == 1) { x = old_rate; sgn = -1.0; }                             // lane 1: - log pdf(current  | prior)
+            if (lane == 2) { x = old_rate; a = proposal / pn; b = pn; }               // lane 2: + log q(current | proposal)   (n only)
+            if (lane == 3) { x = proposal; a = old_rate / pn; b = pn; sgn = -1.0; }  // lane 3: - log q(proposal | current)  (n only)
+            if (lane < 2 || (neut && lane < 4)) term = sgn * log_gamma_pdf(x, a, b);
+            else if (!neut && lane == 2) term = log(old_rate) - log(proposal);
+          }
+          const double t1 = __shfl_sync(0xffffffffu, term, 1), t2 = __shfl_sync(0xffffffffu, term, 2), t3 = __shfl_sync(0xffffffffu, term, 3);
+          if (lane == 0) {
+            S.scal[SC_MHPART] = ((term + t1) + t2) + t3;
+            S.scal[SC_PROPOSAL] = valid ? proposal : cur_r;
+            S.scal[SC_R] = r;
+            S.ivars[IV_VALID] = valid;
+            S.ivars[IV_ACCEPT] = 0;
+            S.ivars[IV_RATE_CHANGED] = (!valid && cur_r != old_rate) ? 1 : 0;
+          }
         }
         __syncthreads();
         if (S.ivars[IV_VALID]) {
           const double proposal = S.scal[SC_PROPOSAL];
-          for (int i = tid; i < n - 1; i += kBD) {  // P(t * proposal) for the class' branches, current P elsewhere
+          for (int task = tid; task < 4 * (n - 1); task += kBD) {  // P(t * proposal) for the class' branches, current P elsewhere
+            const int i = task >> 2, j = task & 3;
+            double* pp = S.Pprop + i * 16 + j * 4;
             if (S.Z[i] == cls) {
-              double P16[16];
-              build_P(sd, S.dist[i], proposal, true, P16);
-#pragma unroll
-              for (int e = 0; e < 16; e++) S.Pprop[i * 16 + e] = P16[e];
+              build_P_row(sd, S.dist[i], proposal, j, pp[0], pp[1], pp[2], pp[3]);
             } else {
-#pragma unroll
-              for (int e = 0; e < 16; e++) S.Pprop[i * 16 + e] = S.Pcur[i * 16 + e];
+              const double* pc = S.Pcur + i * 16 + j * 4;
+              pp[0] = pc[0]; pp[1] = pc[1]; pp[2] = pc[2]; pp[3] = pc[3];
             }
           }
           __syncthreads();
-          const double ll_new = prune_all<true, false, true>(ev, S, ts, S.Pprop, S.dirty, gpart, gsc, s_pi, tid);  // log_f_Xz
+          const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, s_pi, tid, true);  // log_f_Xz, into the non-current copy
           if (tid == 0) {
-            const double ll_old = S.scal[SC_LL], r = S.scal[SC_R];
-            double MH;
-            if (neut) {
-              const double pn = S.scal[SC_PROPN];
-              MH = ll_new - ll_old + log_gamma_pdf(proposal, prior_a, prior_b) - log_gamma_pdf(old_rate, prior_a, prior_b) +
-                   log_gamma_pdf(old_rate, proposal / pn, pn) - log_gamma_pdf(proposal, old_rate / pn, pn);
-            } else {
-              MH = ll_new - ll_old + log_gamma_pdf(proposal, prior_a, prior_b) - log_gamma_pdf(old_rate, prior_a, prior_b) + log(old_rate) - log(proposal);
-            }
-            if (log(r) < MH) {
+            const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
+            if (log(S.scal[SC_R]) < MH) {
               S.ivars[IV_ACCEPT] = 1;
               S.ivars[IV_RATE_CHANGED] = (proposal != old_rate) ? 1 : 0;
               S.scal[SC_LL] = ll_new;
             }
             int cnt_nodes = 0, cnt_cls = 0;
-            for (int k = 0; k < ni && S.su[k] >= 0; k++) cnt_nodes += S.dirty[S.su[k]];
+            for (int k = 0; k < n_su; k++) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
             for (int i = 0; i < n - 1; i++) cnt_cls += (S.Z[i] == cls);
             w_npu += (unsigned long long)cnt_nodes * h->P;
             w_root += h->P;
@@ -615,25 +726,24 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         const bool accepted = S.ivars[IV_ACCEPT] != 0;
         const bool rate_changed = S.ivars[IV_RATE_CHANGED] != 0;
         const double new_rate = (accepted || (!S.ivars[IV_VALID])) ? S.scal[SC_PROPOSAL] : old_rate;
-        if (rate_changed) {  // rebuild the class' P(t) / log P for every branch (bpp_c.cpp:1115-1131)
-          for (int i = tid; i < n - 1; i += kBD) {
-            double P16[16];
-            build_P(sd, S.dist[i], new_rate, true, P16);
-#pragma unroll
-            for (int e = 0; e < 16; e++) logP[((size_t)cls * L.n_max + i) * 16 + e] = log(P16[e]);
+        if (rate_changed) {  // rebuild the class' P(t) / log P for every branch (bpp_c.cpp:1115-1131); task = (node, row)
+          for (int task = tid; task < 4 * (n - 1); task += kBD) {
+            const int i = task >> 2, j = task & 3;
+            double r0, r1, r2, r3;
+            build_P_row(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
+            double* lp = logP + ((size_t)cls * L.n_max + i) * 16 + j * 4;
+            lp[0] = log(r0); lp[1] = log(r1); lp[2] = log(r2); lp[3] = log(r3);
             if (S.Z[i] == cls) {
-#pragma unroll
-              for (int e = 0; e < 16; e++) S.Pcur[i * 16 + e] = P16[e];
+              double* pc = S.Pcur + i * 16 + j * 4;
+              pc[0] = r0; pc[1] = r1; pc[2] = r2; pc[3] = r3;
             }
           }
         }
         for (int i = tid; i < n; i += kBD) {
-          if (accepted && S.dirty[i]) S.stale[i] = 1;
+          if (accepted && S.dirty[i]) S.sel[i] ^= 1;  // the proposal's partials become the current ones
           S.dirty[i] = 0;
         }
-        __syncthreads();
         if (tid == 0) {
-          if (accepted) S.ivars[IV_STALE] = 1;
           if (neut) S.scal[SC_N] = new_rate; else S.scal[SC_C] = new_rate;
           if (rate_changed) {
             if (neut) S.ivars[IV_ACC_N] += 1; else S.ivars[IV_ACC_C] += 1;
@@ -663,21 +773,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         if (neut) { PA_PHASE(ph6) } else { PA_PHASE(ph7) }
       }
 
-      // ---------------- commit: bring the stored partials of stale nodes up to date with the accepted rates
-      if (S.ivars[IV_STALE]) {
-        prune_all<true, true, false>(ev, S, ts, S.Pcur, S.stale, gpart, gsc, s_pi, tid);
-        if (tid == 0) {
-          int cnt_nodes = 0;
-          for (int k = 0; k < ni && S.su[k] >= 0; k++) cnt_nodes += S.stale[S.su[k]];
-          w_npu += (unsigned long long)cnt_nodes * h->P;
-          S.ivars[IV_STALE] = 0;
-        }
-        __syncthreads();
-        for (int i = tid; i < n; i += kBD) S.stale[i] = 0;
-      }
-
-      PA_PHASE(ph8)
-      // ---------------- sample_transition (bpp_c.cpp:522-613)
+      // ---------------- sample_transition (bpp_c.cpp:522-613): six gamma draws on six lanes
       if (tid < 18) S.nz[tid] = 0;
       __syncthreads();
       for (int i = tid; i < n - 1; i += kBD) {
@@ -686,12 +782,21 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         if (!S.fix[i]) atomicAdd(&S.nz[9 + k], 1);
       }
       __syncthreads();
-      if (tid < 3) {
+      if (warp == 0) {
         const int* nZ = S.nz;
         const int* nF = S.nz + 9;
-        if (tid == 0) S.scal[SC_G] = sched_beta(cp.seed, key, 0u, (uint32_t)m, cp.prior_g_a + nZ[1 * 3 + 0] + nZ[2 * 3 + 0], cp.prior_g_b + nZ[0]);
-        else if (tid == 1) S.scal[SC_L] = sched_beta(cp.seed, key, 1u, (uint32_t)m, cp.prior_l_a + nF[2 * 3 + 1], cp.prior_l_b + nF[1 * 3 + 1]);
-        else S.scal[SC_L2] = (cp.prior_l2_a == 0) ? 0.0 : sched_beta(cp.seed, key, 2u, (uint32_t)m, cp.prior_l2_a + nF[1 * 3 + 2], cp.prior_l2_b + nF[2 * 3 + 2]);
+        const int whichb = lane >> 1;  // 0: g, 1: l, 2: l2
+        double a = 1.0, b = 1.0;
+        if (whichb == 0) { a = cp.prior_g_a + nZ[1 * 3 + 0] + nZ[2 * 3 + 0]; b = cp.prior_g_b + nZ[0]; }
+        else if (whichb == 1) { a = cp.prior_l_a + nF[2 * 3 + 1]; b = cp.prior_l_b + nF[1 * 3 + 1]; }
+        else if (whichb == 2) { a = cp.prior_l2_a + nF[1 * 3 + 2]; b = cp.prior_l2_b + nF[2 * 3 + 2]; }
+        double x = 0.0;
+        if (lane < 6 && !(whichb == 2 && cp.prior_l2_a == 0))
+          x = sched_gamma(cp.seed, key, (uint32_t)whichb, (lane & 1) ? 4096u : 0u, (uint32_t)m, PA_ST_TRANS, (lane & 1) ? b : a, 1.0);
+        const double y = __shfl_down_sync(0xffffffffu, x, 1);
+        if (lane == 0) S.scal[SC_G] = x / (x + y);
+        if (lane == 2) S.scal[SC_L] = x / (x + y);
+        if (lane == 4) S.scal[SC_L2] = (cp.prior_l2_a == 0) ? 0.0 : x / (x + y);
       }
       __syncthreads();
       if (tid == 0) {
@@ -723,7 +828,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
 size_t chain_smem_bytes(int n_max, int slots_max, int BD) { return carve(nullptr, nullptr, n_max, slots_max, BD) + 64; }
 
 size_t chain_arena_bytes(int n_max, int P_max) {
-  size_t b = (size_t)3 * n_max * 16 * 8 + (size_t)n_max * P_max * 4 * 8 + (size_t)n_max * P_max * 2;
+  size_t b = (size_t)3 * n_max * 16 * 8 + 2 * ((size_t)n_max * P_max * 4 * 8 + (size_t)n_max * P_max * 2);
   return (b + 255) & ~size_t(255);
 }
 

@@ -107,6 +107,20 @@ __device__ __forceinline__ void build_P(const SubstDev& sd, double t, double rat
   for (int k = 0; k < 16; k++) P16[k] = ((e0 * sd.A[0][k] + e1 * sd.A[1][k]) + e2 * sd.A[2][k]) + e3 * sd.A[3][k];
 }
 
+// one row j of P(t * rate): r_i = P(j -> i); same arithmetic as build_P
+__device__ __forceinline__ void build_P_row(const SubstDev& sd, double t, double rate, int j, double& r0, double& r1, double& r2, double& r3) {
+  if (!(t > 1e-10)) {
+    r0 = (j == 0) ? 1.0 : 0.0; r1 = (j == 1) ? 1.0 : 0.0; r2 = (j == 2) ? 1.0 : 0.0; r3 = (j == 3) ? 1.0 : 0.0;
+    return;
+  }
+  const double e0 = exp(sd.eval[0] * t * rate), e1 = exp(sd.eval[1] * t * rate), e2 = exp(sd.eval[2] * t * rate), e3 = exp(sd.eval[3] * t * rate);
+  const int k = j * 4;
+  r0 = ((e0 * sd.A[0][k] + e1 * sd.A[1][k]) + e2 * sd.A[2][k]) + e3 * sd.A[3][k];
+  r1 = ((e0 * sd.A[0][k + 1] + e1 * sd.A[1][k + 1]) + e2 * sd.A[2][k + 1]) + e3 * sd.A[3][k + 1];
+  r2 = ((e0 * sd.A[0][k + 2] + e1 * sd.A[1][k + 2]) + e2 * sd.A[2][k + 2]) + e3 * sd.A[3][k + 2];
+  r3 = ((e0 * sd.A[0][k + 3] + e1 * sd.A[1][k + 3]) + e2 * sd.A[2][k + 3]) + e3 * sd.A[3][k + 3];
+}
+
 // ---------------------------------------------------------------- element view (pointers into the blob)
 struct ElemView {
   const ElemHeader* h;
