@@ -9,11 +9,13 @@
 //   sample_rate (n, then c): MH with the histories integrated out (log_f_Xz)                 bpp_c.cpp:860-1176
 //   sample_transition: Beta draws for g, l, l2                                               bpp_c.cpp:522-613
 //
-// Data layout.  Tip codes (4 bit), weights, gap masks and the tree of the element come from its blob in HBM.  The
-// per-pattern partials of every internal node live in this CTA's arena in HBM (L2-resident while the chain runs) in
-// TWO copies; a per-node selector says which copy is current.  A pruning pass keeps the partials it recomputes in a
-// per-thread shared-memory stack (for its own parents) and streams them to the non-current copy; accepting a
-// proposal just flips the selectors of the recomputed nodes, rejecting leaves everything untouched.
+// Data layout.  The element's tree, pruning program, weights and gap masks come from its blob in HBM; the packed 4-bit
+// tip codes of the current 256-pattern tile are staged in shared memory.  The per-pattern partials of every internal
+// node live in this CTA's arena in HBM (L2-resident while the chain runs) in TWO copies; a per-node selector says
+// which copy is current.  A pruning pass keeps the partials it recomputes in a per-thread shared-memory stack (for
+// its own parents) and streams them to the non-current copy; accepting a proposal flips the selectors of the
+// recomputed nodes, rejecting leaves everything untouched.  The shared-memory layout is a compile-time struct
+// (SmemT<NMAX, SLOTS>) so that every address is an immediate.
 // Random numbers: Philox4x32-10 indexed by (chain, iteration, purpose, site/node), see oracle/oracle.h.
 #include <cuda_runtime.h>
 
@@ -28,62 +30,38 @@ namespace {
 
 constexpr int kBD = 256;
 constexpr int kNW = kBD / 32;
+constexpr int kTile = 256;       // patterns / sites per tile
+constexpr int kCodeRow = 132;    // staged bytes per tip row: 264 patterns
 
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R, SC_COUNT = 16 };
-enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_NTIPS, IV_COUNT = 16 };
+enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_COUNT = 16 };
 
-struct Smem {
-  double *Pcur, *Pprop, *stack, *red, *emis, *back, *eamb, *dist, *uz, *scal, *T;  // T: [2][9] linear Z transition (free, fixed)
-  uint4* ops;        // [ni] pruning program (SU order), see build in init
-  uint2* tipl;       // [n] non-missing tips: {node | tiprow << 16, parent's internal index}
-  int *stack_sc, *ivars, *nz;
-  uint32_t *cnt, *hs;  // hs: [ni] history descriptors: node | parent's internal index << 16 (0xffff for the root)
-  int16_t *parent, *child, *intidx, *up_nodes, *up_off, *down_nodes, *down_off;
-  uint8_t *flags, *fix, *dirty, *sel, *cnt8, *xs8;
-  int8_t *Z, *Znew;
+template <int NMAX, int SLOTS>
+struct SmemT {
+  static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
+  alignas(16) double Pcur[NMAX * 16];
+  alignas(16) double Pprop[NMAX * 16];
+  alignas(16) double stack[SLOTS * 4 * kBD];  // [slot][base][thread]
+  double red[34];
+  double emis[NMAX * 3], back[NMAX * 3], eamb[NMAX * 3];
+  double dist[NMAX], uz[NMAX];
+  double scal[SC_COUNT];
+  double T[18];   // linear Z transition matrices [free, fixZ==1][child state a][parent state j]
+  double pi[4];
+  alignas(16) uint4 ops[NI];  // pruning program, see init
+  alignas(8) uint2 hs[NI];    // history descriptor of internal node q: {node | parent's q << 16 (0xffff root), unused}
+  alignas(8) uint2 ht[NI];    // its non-missing tip children: {node | tip row << 16} each, 0xffffffff = none
+  int ivars[IV_COUNT];
+  int nz[18];
+  uint32_t cnt[NMAX * 16];
+  int16_t stack_sc[SLOTS * kBD];
+  int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
+  uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
+  int8_t Z[NMAX], Znew[NMAX];
+  uint8_t cnt8[kNW * NMAX * 16];
+  uint8_t xs8[NI * kBD];
+  alignas(4) uint8_t codes[NI * kCodeRow];
 };
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-
-__host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int n, int slots, int BD) {
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o = align16(o + bytes); return base ? base + r : (unsigned char*)nullptr; };
-  unsigned char* p;
-  p = take(sizeof(double) * n * 16); if (s) s->Pcur = (double*)p;
-  p = take(sizeof(double) * n * 16); if (s) s->Pprop = (double*)p;
-  p = take(sizeof(double) * slots * 4 * BD); if (s) s->stack = (double*)p;
-  p = take(sizeof(double) * 34); if (s) s->red = (double*)p;
-  p = take(sizeof(double) * n * 3); if (s) s->emis = (double*)p;
-  p = take(sizeof(double) * n * 3); if (s) s->back = (double*)p;
-  p = take(sizeof(double) * n * 3); if (s) s->eamb = (double*)p;
-  p = take(sizeof(double) * n); if (s) s->dist = (double*)p;
-  p = take(sizeof(double) * n); if (s) s->uz = (double*)p;
-  p = take(sizeof(double) * SC_COUNT); if (s) s->scal = (double*)p;
-  p = take(sizeof(double) * 18); if (s) s->T = (double*)p;
-  p = take(sizeof(uint4) * n); if (s) s->ops = (uint4*)p;
-  p = take(sizeof(uint2) * n); if (s) s->tipl = (uint2*)p;
-  p = take(sizeof(int) * slots * BD); if (s) s->stack_sc = (int*)p;
-  p = take(sizeof(int) * IV_COUNT); if (s) s->ivars = (int*)p;
-  p = take(sizeof(int) * 18); if (s) s->nz = (int*)p;
-  p = take(sizeof(uint32_t) * n * 16); if (s) s->cnt = (uint32_t*)p;
-  p = take(sizeof(uint32_t) * n); if (s) s->hs = (uint32_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->parent = (int16_t*)p;
-  p = take(sizeof(int16_t) * 2 * n); if (s) s->child = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->intidx = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->up_nodes = (int16_t*)p;
-  p = take(sizeof(int16_t) * (n + 1)); if (s) s->up_off = (int16_t*)p;
-  p = take(sizeof(int16_t) * n); if (s) s->down_nodes = (int16_t*)p;
-  p = take(sizeof(int16_t) * (n + 1)); if (s) s->down_off = (int16_t*)p;
-  p = take(n); if (s) s->flags = p;
-  p = take(n); if (s) s->fix = p;
-  p = take(n); if (s) s->dirty = p;
-  p = take(n); if (s) s->sel = p;
-  p = take((size_t)(BD / 32) * n * 16); if (s) s->cnt8 = p;
-  p = take((size_t)((n + 1) / 2) * BD); if (s) s->xs8 = p;
-  p = take(n); if (s) s->Z = (int8_t*)p;
-  p = take(n); if (s) s->Znew = (int8_t*)p;
-  return o;
-}
 
 __device__ __forceinline__ double class_rate(int z, double n_rate, double c_rate) { return z == 2 ? n_rate : (z == 0 ? 1.0 : c_rate); }
 
@@ -98,23 +76,42 @@ __device__ __forceinline__ void mark_ancestors(const int16_t* parent, uint8_t* d
 }
 
 struct Arena {
-  double* part;        // [2][n_max][P_max][4]
-  int16_t* sc;         // [2][n_max][P_max]
-  size_t part_stride;  // doubles between the two copies
-  size_t sc_stride;
+  double* part;          // [2][n_max][P_max][4]
+  int16_t* sc;           // [2][n_max][P_max]
+  uint32_t part_stride;  // doubles between the two copies
+  uint32_t sc_stride;
 };
+
+// stage the packed tip codes of patterns [pb, pb + 264) (pb a multiple of 8) into shared memory
+template <class SM>
+__device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb, int n_rows, int tid) {
+  if (S.ivars[IV_STAGED] == pb) return;
+  __syncthreads();
+  const int half = ev.h->Ppad >> 1;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(ev.codes);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(S.codes);
+  for (int idx = tid; idx < n_rows * (kCodeRow / 4); idx += kBD) {
+    const int r = idx / (kCodeRow / 4), w = idx - r * (kCodeRow / 4);
+    const int byte = (pb >> 1) + 4 * w;
+    dst[r * (kCodeRow / 4) + w] = (byte < half) ? src[(r * half + byte) >> 2] : 0xffffffffu;
+  }
+  if (tid == 0) S.ivars[IV_STAGED] = pb;
+  __syncthreads();
+}
 
 // One Felsenstein pass over every pattern of the element (linear space, fp64).  Thread = pattern.  Nodes are visited
 // in the element's pruning order; with USE_DIRTY only flagged nodes are recomputed (their clean children are read
 // from the current arena copy).  Every recomputed node is written to copy sel[s]^wflip.  Returns sum_p w_p log L_p.
-template <bool USE_DIRTY>
-__device__ __forceinline__ double prune_pass(const ElemView& ev, const Smem& S, const double* __restrict__ Pm, int wflip, const Arena& A, int n_su,
-                                             const double* __restrict__ pi, int tid, bool reduce) {
-  const int P = ev.h->P, Ppad = ev.h->Ppad, half = Ppad >> 1;
+template <bool USE_DIRTY, class SM>
+__device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, int wflip, const Arena& A, int n_su, int n_rows,
+                                             int tid) {
+  const int P = ev.h->P, Ppad = ev.h->Ppad;
   double acc = 0.0;
-  for (int p = tid; p < Ppad; p += kBD) {
+  for (int p0 = 0; p0 < Ppad; p0 += kTile) {
+    ensure_staged(S, ev, p0, n_rows, tid);
+    const int p = p0 + tid;
     if (p < P) {
-      const uint8_t* __restrict__ cp = ev.codes + (p >> 1);
+      const uint8_t* __restrict__ cp = S.codes + (tid >> 1);
       const int sh = (p & 1) * 4;
       double o0 = 1.0, o1 = 1.0, o2 = 1.0, o3 = 1.0;
       int sc = 0;
@@ -132,7 +129,7 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, const Smem& S, 
           const int x = cc ? (int)(op.w >> 16) : (int)(op.w & 0xffff);
           const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch * 16);
           if (kind == 1) {
-            const uint32_t code = ((uint32_t)__ldg(cp + x * half) >> sh) & 15u;
+            const uint32_t code = ((uint32_t)cp[x * kCodeRow] >> sh) & 15u;
             if (code == 15u) continue;  // gap / N: Tg >= num_base (bpp_c.cpp:660)
             if ((code & (code - 1)) == 0) {
               const int b = __ffs(code) - 1;
@@ -154,11 +151,11 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, const Smem& S, 
               L0 = st[0]; L1 = st[kBD]; L2 = st[2 * kBD]; L3 = st[3 * kBD];
               sc += S.stack_sc[sl * kBD + tid];
             } else {
-              const int a = S.sel[ch];
-              const double2* g2 = reinterpret_cast<const double2*>(A.part + a * A.part_stride + ((size_t)x * Ppad + p) * 4);
+              const uint32_t a = S.sel[ch];
+              const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x * Ppad + p) * 4u));
               const double2 u = g2[0], v = g2[1];
               L0 = u.x; L1 = u.y; L2 = v.x; L3 = v.y;
-              sc += A.sc[a * A.sc_stride + (size_t)x * Ppad + p];
+              sc += A.sc[a * A.sc_stride + (uint32_t)x * Ppad + p];
             }
             const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
             o0 *= ((r00.x * L0 + r00.y * L1) + r01.x * L2) + r01.y * L3;
@@ -176,28 +173,28 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, const Smem& S, 
         const int sl = (op.z >> 8) & 0xff;
         double* st = S.stack + sl * 4 * kBD + tid;
         st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
-        S.stack_sc[sl * kBD + tid] = sc;
-        const int q = op.x >> 16;
-        const int a = S.sel[s] ^ wflip;
-        double2* g2 = reinterpret_cast<double2*>(A.part + a * A.part_stride + ((size_t)q * Ppad + p) * 4);
+        S.stack_sc[sl * kBD + tid] = (int16_t)sc;
+        const uint32_t q = op.x >> 16;
+        const uint32_t a = S.sel[s] ^ wflip;
+        double2* g2 = reinterpret_cast<double2*>(A.part + (a * A.part_stride + (q * Ppad + p) * 4u));
         g2[0] = make_double2(o0, o1);
         g2[1] = make_double2(o2, o3);
-        A.sc[a * A.sc_stride + (size_t)q * Ppad + p] = (int16_t)sc;
+        A.sc[a * A.sc_stride + q * Ppad + p] = (int16_t)sc;
       }
       // the last node of the program is the root (or nothing was computed: missing root -> likelihood 1)
-      const double lik = ((pi[0] * o0 + pi[1] * o1) + pi[2] * o2) + pi[3] * o3;
+      const double lik = ((S.pi[0] * o0 + S.pi[1] * o1) + S.pi[2] * o2) + S.pi[3] * o3;
       acc += (double)ev.weights[p] * (log(lik) - sc * PA_LOG_SCALE);
     }
   }
-  if (reduce) return block_sum(acc, S.red, tid, kBD);
-  return 0.0;
+  return block_sum(acc, S.red, tid, kBD);
 }
 
 // log-space serial Z update, a literal restatement of Update_Z_subtree; used only when the scaled linear pass degenerates
-__device__ void z_update_logspace(const Smem& S, int n, const double* Tlin) {
+template <class SM>
+__device__ void z_update_logspace(SM& S, int n) {
   double lt[2][9];
   for (int f = 0; f < 2; f++)
-    for (int k = 0; k < 9; k++) lt[f][k] = log(Tlin[f * 9 + k]);
+    for (int k = 0; k < 9; k++) lt[f][k] = log(S.T[f * 9 + k]);
   for (int i = 0; i < n; i++) {
     for (int k = 0; k < 3; k++) S.back[i * 3 + k] = S.emis[i * 3 + k];
     if (S.fix[i]) S.back[i * 3 + 2] = -CUDART_INF;
@@ -232,39 +229,37 @@ __device__ void z_update_logspace(const Smem& S, int n, const double* Tlin) {
   }
 }
 
-// counts of (parent base, child base) pairs over the 32 sites of a warp, written to the warp's tile-count row
-__device__ __forceinline__ void warp_count16(uint32_t code, bool act, uint8_t* __restrict__ row, int lane) {
+// counts of (parent base, child base) pairs over the 32 sites of a warp, written to the warp's tile-count row;
+// m0..m3 are per-lane masks: m_i = (lane bit i set) ? 0 : ~0, so that (b_i ^ m_i) selects lanes whose code bit i equals the lane's
+__device__ __forceinline__ void warp_count16(uint32_t code, bool act, uint8_t* __restrict__ row, int lane, uint32_t m0, uint32_t m1, uint32_t m2,
+                                             uint32_t m3) {
   const uint32_t bv = __ballot_sync(0xffffffffu, act);
   const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, code & 2u);
   const uint32_t b2 = __ballot_sync(0xffffffffu, code & 4u), b3 = __ballot_sync(0xffffffffu, code & 8u);
-  if (lane < 16) {
-    uint32_t mm = bv;
-    mm &= (lane & 1) ? b0 : ~b0;
-    mm &= (lane & 2) ? b1 : ~b1;
-    mm &= (lane & 4) ? b2 : ~b2;
-    mm &= (lane & 8) ? b3 : ~b3;
-    row[lane] = (uint8_t)__popc(mm);
-  }
+  if (lane < 16) row[lane] = (uint8_t)__popc(bv & (b0 ^ m0) & (b1 ^ m1) & (b2 ^ m2) & (b3 ^ m3));
 }
 
+template <int NMAX, int SLOTS>
 __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem S;
-  carve(&S, smem_raw, L.n_max, L.slots_max, kBD);
+  typedef SmemT<NMAX, SLOTS> SM;
+  SM& S = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ChainParams& cp = L.cp;
   const SubstDev& sd = L.sd;
-  __shared__ double s_pi[4];
-  if (tid < 4) s_pi[tid] = sd.pi[tid];
+  if (tid < 4) S.pi[tid] = sd.pi[tid];
+  const uint32_t lm0 = (lane & 1) ? 0u : 0xffffffffu, lm1 = (lane & 2) ? 0u : 0xffffffffu, lm2 = (lane & 4) ? 0u : 0xffffffffu,
+                 lm3 = (lane & 8) ? 0u : 0xffffffffu;
 
   // this CTA's arena: log P tables [3][n_max][16] f64, partials [2][n_max][P_max][4] f64, scale counts [2][n_max][P_max] i16
   unsigned char* arena = L.arena + (size_t)blockIdx.x * L.arena_stride;
   double* logP = reinterpret_cast<double*>(arena);
   Arena A;
   A.part = logP + (size_t)3 * L.n_max * 16;
-  A.part_stride = (size_t)L.n_max * L.P_max * 4;
-  A.sc = reinterpret_cast<int16_t*>(A.part + 2 * A.part_stride);
-  A.sc_stride = (size_t)L.n_max * L.P_max;
+  A.part_stride = (uint32_t)L.n_max * L.P_max * 4;
+  A.sc = reinterpret_cast<int16_t*>(A.part + 2 * (size_t)A.part_stride);
+  A.sc_stride = (uint32_t)L.n_max * L.P_max;
+  const int n_rows = L.S_rows;
 
   unsigned long long w_npu = 0, w_root = 0, w_pt = 0, w_hist = 0, w_iter = 0;  // work counters (thread 0)
   long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, ph6 = 0, ph7 = 0, ph8 = 0, ph9 = 0;  // SM cycles per phase (thread 0)
@@ -278,7 +273,10 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) S.ivars[IV_CHAIN] = atomicAdd(L.queue, 1);
+    if (tid == 0) {
+      S.ivars[IV_CHAIN] = atomicAdd(L.queue, 1);
+      S.ivars[IV_STAGED] = -1;
+    }
     __syncthreads();
     const int chain = S.ivars[IV_CHAIN];
     if (chain >= L.n_chains) break;
@@ -295,7 +293,6 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       S.parent[i] = ev.parent[i];
       S.child[2 * i] = ev.child[2 * i];
       S.child[2 * i + 1] = ev.child[2 * i + 1];
-      S.intidx[i] = ev.intidx[i];
       S.up_nodes[i] = ev.up_nodes[i];
       S.down_nodes[i] = ev.down_nodes[i];
       const uint8_t f = ev.flags[i];
@@ -308,13 +305,15 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
     }
     for (int i = tid; i <= h->n_up; i += kBD) S.up_off[i] = ev.up_off[i];
     for (int i = tid; i <= h->n_down; i += kBD) S.down_off[i] = ev.down_off[i];
-    // pruning program: one packed descriptor per computed internal node, in the element's pruning order
+    // pruning program: one packed descriptor per computed internal node, in the element's pruning order:
+    //   x = node | q << 16;  y = child0 | child1 << 16;  z = kind0 | kind1 << 2 | slot << 8 | slot0 << 16 | slot1 << 24;
+    //   w = x0 | x1 << 16 (tip row of a tip child, internal index of an internal child); kind 0 missing, 1 tip, 2 internal
     for (int k = tid; k < ni; k += kBD) {
       const int s = ev.su[k];
       uint4 op = make_uint4(0, 0, 0, 0);
+      auto kind_of = [&](int c) { const uint8_t f = ev.flags[c]; return (f & PA_F_MISSING) ? 0u : ((f & PA_F_TIP) ? 1u : 2u); };
       if (s >= 0) {
         const int c0 = ev.child[2 * s], c1 = ev.child[2 * s + 1];
-        auto kind_of = [&](int c) { const uint8_t f = ev.flags[c]; return (f & PA_F_MISSING) ? 0u : ((f & PA_F_TIP) ? 1u : 2u); };
         auto x_of = [&](int c) { return (uint32_t)((ev.flags[c] & PA_F_TIP) ? ev.tiprow[c] : ev.intidx[c]) & 0xffffu; };
         const uint32_t k0 = kind_of(c0), k1 = kind_of(c1);
         op.x = (uint32_t)s | ((uint32_t)ev.intidx[s] << 16);
@@ -324,24 +323,20 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         op.w = x_of(c0) | (x_of(c1) << 16);
       }
       S.ops[k] = op;
-      // history descriptor of internal node q = k (post-order)
+      // history descriptors of internal node q = k (post-order): parent's q, and the node's non-missing tip children
       const int sq = ev.intlist[k];
       const int par = ev.parent[sq];
-      S.hs[k] = (uint32_t)sq | ((par >= 0 ? (uint32_t)ev.intidx[par] : 0xffffu) << 16);
+      S.hs[k] = make_uint2((uint32_t)sq | ((par >= 0 ? (uint32_t)ev.intidx[par] : 0xffffu) << 16), 0u);
+      uint2 t2 = make_uint2(0xffffffffu, 0xffffffffu);
+      const int c0 = ev.child[2 * sq], c1 = ev.child[2 * sq + 1];
+      if (kind_of(c0) == 1u) t2.x = (uint32_t)c0 | ((uint32_t)ev.tiprow[c0] << 16);
+      if (kind_of(c1) == 1u) t2.y = (uint32_t)c1 | ((uint32_t)ev.tiprow[c1] << 16);
+      S.ht[k] = t2;
     }
     if (tid == 0) {
       int nsu = 0;
       while (nsu < ni && ev.su[nsu] >= 0) nsu++;
       S.ivars[IV_NSU] = nsu;
-      int nt = 0;
-      for (int i = 0; i < n; i++) {
-        const uint8_t f = ev.flags[i];
-        if ((f & PA_F_TIP) && !(f & PA_F_MISSING)) {
-          S.tipl[nt] = make_uint2((uint32_t)i | ((uint32_t)ev.tiprow[i] << 16), (uint32_t)ev.intidx[ev.parent[i]]);
-          nt++;
-        }
-      }
-      S.ivars[IV_NTIPS] = nt;
       S.scal[SC_N] = cp.init_nrate;
       S.scal[SC_C] = cp.init_crate;
       S.scal[SC_G] = cp.init_grate;
@@ -361,7 +356,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       w_pt += 3ull * n;
     }
     __syncthreads();
-    const int n_su = S.ivars[IV_NSU], n_tips = S.ivars[IV_NTIPS];
+    const int n_su = S.ivars[IV_NSU];
     // P(t) of every branch for its class, and the log P tables of the three classes (emission look-ups); task = (class, node, row)
     for (int task = tid; task < 12 * n; task += kBD) {
       const int k = task / (4 * n), rem = task - k * 4 * n, i = rem >> 2, j = rem & 3;
@@ -379,7 +374,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
     __syncthreads();
     // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in arena copy 0
     {
-      const double ll = prune_pass<false>(ev, S, S.Pcur, 0, A, n_su, s_pi, tid, true);
+      const double ll = prune_pass<false>(ev, S, S.Pcur, 0, A, n_su, n_rows, tid);
       if (tid == 0) {
         S.scal[SC_LL] = ll;
         w_npu += (unsigned long long)n_su * h->P;
@@ -415,71 +410,88 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       const double cur_n = S.scal[SC_N], cur_c = S.scal[SC_C];
       __syncthreads();
       PA_PHASE(ph1)
-      for (int g0 = 0; g0 < GG; g0 += kBD) {
+      for (int g0 = 0; g0 < GG; g0 += kTile) {
+        const int pb = (int)ev.sitepat[g0] & ~7;  // sites are sorted by pattern: this tile spans < 264 patterns from pb
+        ensure_staged(S, ev, pb, n_rows, tid);
         const int g = g0 + tid;
         const bool valid = g < GG;
-        const int pat = valid ? ev.sitepat[g] : 0;
+        const int pat = valid ? ev.sitepat[g] : pb;
         uint32_t gw0 = 0, gw1 = 0;
         if (h->W >= 1) gw0 = ev.gap[pat];
         if (h->W >= 2) gw1 = ev.gap[Ppad + pat];
-        const double* gp = A.part + (size_t)pat * 4;
-        uint4 rnd = make_uint4(0, 0, 0, 0);
-        int have = -1;
+        const double* gp = A.part + (uint32_t)pat * 4u;
+        const uint8_t* cpat = S.codes + ((pat - pb) >> 1);
+        const int csh = (pat & 1) * 4;
         uint8_t* xs = S.xs8 + tid;
-        uint8_t* c8 = S.cnt8 + (size_t)warp * n * 16;
-        for (int q = ni - 1; q >= 0; q--) {
-          const uint32_t d = S.hs[q];
-          const int s = d & 0xffff;
-          if (S.flags[s] & PA_F_MISSING) continue;
-          const uint32_t qp = d >> 16;
-          const bool isroot = (qp == 0xffffu);
-          bool gapbit;
-          if (q < 32) gapbit = (gw0 >> q) & 1u;
-          else if (q < 64) gapbit = (gw1 >> (q - 32)) & 1u;
-          else gapbit = (ev.gap[(size_t)(q >> 5) * Ppad + pat] >> (q & 31)) & 1u;
-          const bool active = valid && (isroot || !gapbit);
-          const int xp = isroot ? 0 : (int)xs[qp * kBD];
-          int x = 0;
-          if (active) {
-            if ((q >> 2) != have) {
-              rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)(q >> 2), (uint32_t)m, PA_ST_HIST);
-              have = q >> 2;
+        uint8_t* c8 = S.cnt8 + warp * (n * 16);
+        for (int G = (ni - 1) >> 2; G >= 0; G--) {
+          // the partials of the group's nodes do not depend on the draws: fetch them first (one L2 round trip per 4 nodes)
+          double2 pa[4], pc[4];
+#pragma unroll
+          for (int j = 3; j >= 0; j--) {
+            const int q = 4 * G + j;
+            pa[j] = make_double2(0.0, 0.0);
+            pc[j] = make_double2(0.0, 0.0);
+            if (q < ni && valid) {
+              const int s = S.hs[q].x & 0xffff;
+              const double2* g2 = reinterpret_cast<const double2*>(gp + ((uint32_t)S.sel[s] * A.part_stride + (uint32_t)q * Ppad * 4u));
+              pa[j] = g2[0];
+              pc[j] = g2[1];
             }
-            const double u = u01(pick(rnd, q & 3));
-            const double2* g2 = reinterpret_cast<const double2*>(gp + S.sel[s] * A.part_stride + (size_t)q * Ppad * 4);
-            const double2 a = g2[0], b = g2[1];
-            double p0, p1, p2, p3;
-            if (isroot) {
-              p0 = a.x * s_pi[0]; p1 = a.y * s_pi[1]; p2 = b.x * s_pi[2]; p3 = b.y * s_pi[3];
-            } else {
-              const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
-              const double2 r0 = Pr[0], r1 = Pr[1];
-              p0 = r0.x * a.x; p1 = r0.y * a.y; p2 = r1.x * b.x; p3 = r1.y * b.y;
-            }
-            // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
-            const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
-            x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
-            xs[q * kBD] = (uint8_t)x;
           }
-          if (!isroot) warp_count16((uint32_t)(xp * 4 + x), active, c8 + s * 16, lane);
-        }
-        // tip branches: the tip's base is data, the parent's base was just sampled
-        for (int k = 0; k < n_tips; k++) {
-          const uint2 td = S.tipl[k];
-          const int i = td.x & 0xffff;
-          uint32_t code4 = 15u;
-          if (valid) code4 = ((uint32_t)__ldg(ev.codes + (size_t)(td.x >> 16) * (Ppad >> 1) + (pat >> 1)) >> ((pat & 1) * 4)) & 15u;
-          const int xp = xs[td.y * kBD];
-          const bool onehot = (code4 & (code4 - 1)) == 0;  // code4 is never 0
-          const bool act = valid && code4 != 15u && onehot;
-          warp_count16((uint32_t)(xp * 4 + (onehot ? (__ffs(code4) - 1) : 0)), act, c8 + i * 16, lane);
-          if (valid && code4 != 15u && !onehot) {  // ambiguity code: log sum_{b in code} P_k(xp -> b) (bpp_c2.cpp:372-378)
-            for (int kk = 0; kk < 3; kk++) {
-              const double* lp = logP + ((size_t)kk * L.n_max + i) * 16 + xp * 4;
-              double sum = 0;
-              for (int b = 0; b < 4; b++)
-                if ((code4 >> b) & 1u) sum += exp(lp[b]);
-              atomicAdd(&S.eamb[i * 3 + kk], log(sum));
+          const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
+#pragma unroll
+          for (int j = 3; j >= 0; j--) {
+            const int q = 4 * G + j;
+            if (q >= ni) continue;
+            const uint32_t d = S.hs[q].x;
+            const int s = d & 0xffff;
+            if (S.flags[s] & PA_F_MISSING) continue;
+            const uint32_t qp = d >> 16;
+            const bool isroot = (qp == 0xffffu);
+            bool gapbit;
+            if (q < 32) gapbit = (gw0 >> q) & 1u;
+            else if (q < 64) gapbit = (gw1 >> (q - 32)) & 1u;
+            else gapbit = (ev.gap[(size_t)(q >> 5) * Ppad + pat] >> (q & 31)) & 1u;
+            const bool active = valid && (isroot || !gapbit);
+            const int xp = isroot ? 0 : (int)xs[qp * kBD];
+            int x = 0;
+            if (active) {
+              const double u = u01(j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w)));
+              double p0, p1, p2, p3;
+              if (isroot) {
+                p0 = pa[j].x * S.pi[0]; p1 = pa[j].y * S.pi[1]; p2 = pc[j].x * S.pi[2]; p3 = pc[j].y * S.pi[3];
+              } else {
+                const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
+                const double2 r0 = Pr[0], r1 = Pr[1];
+                p0 = r0.x * pa[j].x; p1 = r0.y * pa[j].y; p2 = r1.x * pc[j].x; p3 = r1.y * pc[j].y;
+              }
+              // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
+              const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
+              x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
+              xs[q * kBD] = (uint8_t)x;
+            }
+            if (!isroot) warp_count16((uint32_t)(xp * 4 + x), active, c8 + s * 16, lane, lm0, lm1, lm2, lm3);
+            // tip children of this node: the tip's base is data, the parent's base was just drawn
+            const uint2 tc = S.ht[q];
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++) {
+              const uint32_t td = cc ? tc.y : tc.x;
+              if (td == 0xffffffffu) continue;
+              const int ti = td & 0xffff;
+              const uint32_t code4 = valid ? (((uint32_t)cpat[(td >> 16) * kCodeRow] >> csh) & 15u) : 15u;
+              const bool onehot = (code4 & (code4 - 1)) == 0;  // code4 is never 0
+              const bool act = code4 != 15u && onehot;
+              warp_count16((uint32_t)(x * 4 + (__ffs(code4) - 1)), act, c8 + ti * 16, lane, lm0, lm1, lm2, lm3);
+              if (code4 != 15u && !onehot) {  // ambiguity code: log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
+                for (int kk = 0; kk < 3; kk++) {
+                  const double* lp = logP + ((size_t)kk * L.n_max + ti) * 16 + x * 4;
+                  double sum = 0;
+                  for (int b = 0; b < 4; b++)
+                    if ((code4 >> b) & 1u) sum += exp(lp[b]);
+                  atomicAdd(&S.eamb[ti * 3 + kk], log(sum));
+                }
+              }
             }
           }
         }
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
           if (!(S.flags[idx >> 4] & PA_F_MISSING)) {
             uint32_t sum = 0;
 #pragma unroll
-            for (int w = 0; w < kNW; w++) sum += S.cnt8[(size_t)w * n * 16 + idx];
+            for (int w = 0; w < kNW; w++) sum += S.cnt8[w * (n * 16) + idx];
             S.cnt[idx] += sum;
           }
         }
@@ -578,7 +590,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
           }
         }
         __syncwarp();
-        if (S.ivars[IV_ZFALLBACK] != 0 && lane == 0) z_update_logspace(S, n, S.T);
+        if (S.ivars[IV_ZFALLBACK] != 0 && lane == 0) z_update_logspace(S, n);
         __syncwarp();
         if (lane == 0) {
           S.ivars[IV_ANY_CHANGED] = 0;
@@ -612,7 +624,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
       }
       __syncthreads();
       if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431 (recomputed partials overwrite the current copy in place)
-        const double ll = prune_pass<true>(ev, S, S.Pcur, 0, A, n_su, s_pi, tid, true);
+        const double ll = prune_pass<true>(ev, S, S.Pcur, 0, A, n_su, n_rows, tid);
         if (tid == 0) {
           S.scal[SC_LL] = ll;
           int cnt_nodes = 0;
@@ -706,7 +718,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
             }
           }
           __syncthreads();
-          const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, s_pi, tid, true);  // log_f_Xz, into the non-current copy
+          const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, n_rows, tid);  // log_f_Xz, into the non-current copy
           if (tid == 0) {
             const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
             if (log(S.scal[SC_R]) < MH) {
@@ -823,9 +835,32 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
   }
 }
 
+struct Variant {
+  int nmax, slots;
+  size_t smem;
+  void (*kernel)(ChainLaunch);
+};
+
+template <int NMAX, int SLOTS>
+Variant make_variant() {
+  return Variant{NMAX, SLOTS, sizeof(SmemT<NMAX, SLOTS>) + 16, chain_kernel<NMAX, SLOTS>};
+}
+
+// compiled shared-memory layouts: (max nodes of the tree incl. 2 * tip rows - 1, temp slots)
+const Variant* pick_variant(int n_max, int slots_max, int s_rows) {
+  static const Variant variants[] = {make_variant<32, 4>(), make_variant<96, 4>(), make_variant<96, 6>(), make_variant<160, 6>()};
+  const int need = n_max > 2 * s_rows - 1 ? n_max : 2 * s_rows - 1;
+  for (const Variant& v : variants)
+    if (need <= v.nmax && slots_max <= v.slots && s_rows <= v.nmax / 2 + 1) return &v;
+  return nullptr;
+}
+
 }  // namespace
 
-size_t chain_smem_bytes(int n_max, int slots_max, int BD) { return carve(nullptr, nullptr, n_max, slots_max, BD) + 64; }
+size_t chain_smem_bytes(int n_max, int slots_max, int s_rows) {
+  const Variant* v = pick_variant(n_max, slots_max, s_rows);
+  return v ? v->smem : (size_t)1 << 30;
+}
 
 size_t chain_arena_bytes(int n_max, int P_max) {
   size_t b = (size_t)3 * n_max * 16 * 8 + 2 * ((size_t)n_max * P_max * 4 * 8 + (size_t)n_max * P_max * 2);
@@ -836,13 +871,17 @@ int chain_block_dim() { return kBD; }
 
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream) {
   if (BD != kBD) return PA_ERR_ARG;
-  const size_t smem = chain_smem_bytes(L.n_max, L.slots_max, kBD);
-  cudaError_t err = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const Variant* v = pick_variant(L.n_max, L.slots_max, L.S_rows);
+  if (!v) {
+    set_error("tree too large for the compiled chain-kernel shared-memory layouts");
+    return PA_ERR_LIMIT;
+  }
+  cudaError_t err = cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
   if (err != cudaSuccess) {
     set_error(std::string("chain kernel shared memory: ") + cudaGetErrorString(err));
     return PA_ERR_LIMIT;
   }
-  chain_kernel<<<grid, kBD, smem, stream>>>(L);
+  v->kernel<<<grid, kBD, v->smem, stream>>>(L);
   err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error(std::string("chain kernel launch: ") + cudaGetErrorString(err));

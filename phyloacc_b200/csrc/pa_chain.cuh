@@ -8,12 +8,12 @@ struct ChainLaunch {
   const int32_t* chain_list;  // [n_chains][2]
   int n_chains;
   SubstDev sd; ChainParams cp;
-  int n_max, slots_max, P_max, T, ZW;
+  int n_max, slots_max, P_max, T, ZW, S_rows;
   double* trace_d; uint32_t* trace_z;
   uint8_t* arena; size_t arena_stride;
   unsigned long long* counters; int* queue;
 };
-size_t chain_smem_bytes(int n_max, int slots_max, int BD);
+size_t chain_smem_bytes(int n_max, int slots_max, int s_rows);
 size_t chain_arena_bytes(int n_max, int P_max);
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
 int chain_block_dim();

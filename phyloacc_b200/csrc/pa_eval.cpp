@@ -106,7 +106,7 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
   auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
   const int BD = chain_block_dim();
-  const size_t smem = chain_smem_bytes(n_max, slots_max, BD);
+  const size_t smem = chain_smem_bytes(n_max, slots_max, model.tree.S);
   if ((int)smem > smem_optin) {
     set_error("tree too large for the chain kernel's shared memory (" + std::to_string(smem) + " bytes needed)");
     return PA_ERR_LIMIT;
@@ -141,7 +141,7 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
   cp.ropt = P.ropt; cp.num_burn = P.burnin; cp.num_mcmc = P.mcmc; cp.adaptive_freq = P.adapt_freq;
   cp.seed = (uint32_t)P.seed;
   cp.pad_ = 0;
-  L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T; L.ZW = ZW;
+  L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T; L.ZW = ZW; L.S_rows = model.tree.S;
   L.trace_d = d_trace_d; L.trace_z = d_trace_z;
   L.arena = d_arena; L.arena_stride = stride;
   L.counters = d_counters; L.queue = d_queue;
