@@ -102,6 +102,8 @@ __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb,
 // One Felsenstein pass over every pattern of the element (linear space, fp64).  Thread = pattern.  Nodes are visited
 // in the element's pruning order; with USE_DIRTY only flagged nodes are recomputed (their clean children are read
 // from the current arena copy).  Every recomputed node is written to copy sel[s]^wflip.  Returns sum_p w_p log L_p.
+// The result of an op is forwarded in registers when the next op is its parent (descriptor bits 4..6), so the
+// shared-memory stack only holds results that have to wait for a sibling subtree.
 template <bool USE_DIRTY, class SM>
 __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, int wflip, const Arena& A, int n_su, int n_rows,
                                              int tid) {
@@ -115,65 +117,108 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
       const int sh = (p & 1) * 4;
       double o0 = 1.0, o1 = 1.0, o2 = 1.0, o3 = 1.0;
       int sc = 0;
+      uint4 nxt = S.ops[0];
       for (int k = 0; k < n_su; k++) {
-        const uint4 op = S.ops[k];
+        const uint4 op = nxt;
+        if (k + 1 < n_su) nxt = S.ops[k + 1];  // next descriptor is in flight while this node is computed
         const int s = op.x & 0xffff;
         if (USE_DIRTY && !S.dirty[s]) continue;
-        o0 = o1 = o2 = o3 = 1.0;
-        sc = 0;
-#pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-          const int kind = (op.z >> (2 * cc)) & 3;
-          if (kind == 0) continue;  // missing child (bpp_c.cpp:660)
-          const int ch = cc ? (int)(op.y >> 16) : (int)(op.y & 0xffff);
-          const int x = cc ? (int)(op.w >> 16) : (int)(op.w & 0xffff);
-          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch * 16);
-          if (kind == 1) {
-            const uint32_t code = ((uint32_t)cp[x * kCodeRow] >> sh) & 15u;
-            if (code == 15u) continue;  // gap / N: Tg >= num_base (bpp_c.cpp:660)
-            if ((code & (code - 1)) == 0) {
-              const int b = __ffs(code) - 1;
-              const double* Pd = Pm + ch * 16 + b;
-              o0 *= Pd[0]; o1 *= Pd[4]; o2 *= Pd[8]; o3 *= Pd[12];
-            } else {
-              const double m0 = (code & 1u) ? 1.0 : 0.0, m1 = (code & 2u) ? 1.0 : 0.0, m2 = (code & 4u) ? 1.0 : 0.0, m3 = (code & 8u) ? 1.0 : 0.0;
-              const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
-              o0 *= ((m0 * r00.x + m1 * r00.y) + m2 * r01.x) + m3 * r01.y;
-              o1 *= ((m0 * r10.x + m1 * r10.y) + m2 * r11.x) + m3 * r11.y;
-              o2 *= ((m0 * r20.x + m1 * r20.y) + m2 * r21.x) + m3 * r21.y;
-              o3 *= ((m0 * r30.x + m1 * r30.y) + m2 * r31.x) + m3 * r31.y;
-            }
+        const int k0 = op.z & 3, k1 = (op.z >> 2) & 3;
+        const int ch0 = op.y & 0xffff, ch1 = op.y >> 16;
+        const int x0 = op.w & 0xffff, x1 = op.w >> 16;
+        // ---- gather: partials of internal children (registers / stack / arena), codes of tip children
+        double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0, b0 = 1.0, b1 = 1.0, b2 = 1.0, b3 = 1.0;
+        int sc0 = 0, sc1 = 0;
+        uint32_t code0 = 15u, code1 = 15u;
+        if (k0 == 2) {
+          const bool dch = !USE_DIRTY || S.dirty[ch0];
+          if (dch && (op.z & 16u)) { a0 = o0; a1 = o1; a2 = o2; a3 = o3; sc0 = sc; }
+          else if (dch) {
+            const int sl = (op.z >> 16) & 0xff;
+            const double* st = S.stack + sl * 4 * kBD + tid;
+            a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];
+            sc0 = S.stack_sc[sl * kBD + tid];
           } else {
-            double L0, L1, L2, L3;
-            if (!USE_DIRTY || S.dirty[ch]) {
-              const int sl = (op.z >> (16 + 8 * cc)) & 0xff;
-              const double* st = S.stack + sl * 4 * kBD + tid;
-              L0 = st[0]; L1 = st[kBD]; L2 = st[2 * kBD]; L3 = st[3 * kBD];
-              sc += S.stack_sc[sl * kBD + tid];
-            } else {
-              const uint32_t a = S.sel[ch];
-              const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x * Ppad + p) * 4u));
-              const double2 u = g2[0], v = g2[1];
-              L0 = u.x; L1 = u.y; L2 = v.x; L3 = v.y;
-              sc += A.sc[a * A.sc_stride + (uint32_t)x * Ppad + p];
-            }
-            const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
-            o0 *= ((r00.x * L0 + r00.y * L1) + r01.x * L2) + r01.y * L3;
-            o1 *= ((r10.x * L0 + r10.y * L1) + r11.x * L2) + r11.y * L3;
-            o2 *= ((r20.x * L0 + r20.y * L1) + r21.x * L2) + r21.y * L3;
-            o3 *= ((r30.x * L0 + r30.y * L1) + r31.x * L2) + r31.y * L3;
+            const uint32_t a = S.sel[ch0];
+            const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x0 * Ppad + p) * 4u));
+            const double2 u = g2[0], v = g2[1];
+            a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;
+            sc0 = A.sc[a * A.sc_stride + (uint32_t)x0 * Ppad + p];
+          }
+        } else if (k0 == 1) code0 = ((uint32_t)cp[x0 * kCodeRow] >> sh) & 15u;
+        if (k1 == 2) {
+          const bool dch = !USE_DIRTY || S.dirty[ch1];
+          if (dch && (op.z & 32u)) { b0 = o0; b1 = o1; b2 = o2; b3 = o3; sc1 = sc; }
+          else if (dch) {
+            const int sl = (op.z >> 24) & 0xff;
+            const double* st = S.stack + sl * 4 * kBD + tid;
+            b0 = st[0]; b1 = st[kBD]; b2 = st[2 * kBD]; b3 = st[3 * kBD];
+            sc1 = S.stack_sc[sl * kBD + tid];
+          } else {
+            const uint32_t a = S.sel[ch1];
+            const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x1 * Ppad + p) * 4u));
+            const double2 u = g2[0], v = g2[1];
+            b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
+            sc1 = A.sc[a * A.sc_stride + (uint32_t)x1 * Ppad + p];
+          }
+        } else if (k1 == 1) code1 = ((uint32_t)cp[x1 * kCodeRow] >> sh) & 15u;
+        // ---- messages: m_j = sum_i P_child(j -> i) L_child(i); tips select / add columns; gaps and missing children give 1
+        double m0 = 1.0, m1 = 1.0, m2 = 1.0, m3 = 1.0, n0 = 1.0, n1 = 1.0, n2 = 1.0, n3 = 1.0;
+        if (k0 == 2) {
+          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch0 * 16);
+          const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
+          m0 = ((r00.x * a0 + r00.y * a1) + r01.x * a2) + r01.y * a3;
+          m1 = ((r10.x * a0 + r10.y * a1) + r11.x * a2) + r11.y * a3;
+          m2 = ((r20.x * a0 + r20.y * a1) + r21.x * a2) + r21.y * a3;
+          m3 = ((r30.x * a0 + r30.y * a1) + r31.x * a2) + r31.y * a3;
+        } else if (code0 != 15u) {
+          const double* Pd = Pm + ch0 * 16;
+          if ((code0 & (code0 - 1)) == 0) {
+            const int b = __ffs(code0) - 1;
+            m0 = Pd[b]; m1 = Pd[4 + b]; m2 = Pd[8 + b]; m3 = Pd[12 + b];
+          } else {
+            const double e0 = (code0 & 1u) ? 1.0 : 0.0, e1 = (code0 & 2u) ? 1.0 : 0.0, e2 = (code0 & 4u) ? 1.0 : 0.0, e3 = (code0 & 8u) ? 1.0 : 0.0;
+            m0 = ((e0 * Pd[0] + e1 * Pd[1]) + e2 * Pd[2]) + e3 * Pd[3];
+            m1 = ((e0 * Pd[4] + e1 * Pd[5]) + e2 * Pd[6]) + e3 * Pd[7];
+            m2 = ((e0 * Pd[8] + e1 * Pd[9]) + e2 * Pd[10]) + e3 * Pd[11];
+            m3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];
           }
         }
+        if (k1 == 2) {
+          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch1 * 16);
+          const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
+          n0 = ((r00.x * b0 + r00.y * b1) + r01.x * b2) + r01.y * b3;
+          n1 = ((r10.x * b0 + r10.y * b1) + r11.x * b2) + r11.y * b3;
+          n2 = ((r20.x * b0 + r20.y * b1) + r21.x * b2) + r21.y * b3;
+          n3 = ((r30.x * b0 + r30.y * b1) + r31.x * b2) + r31.y * b3;
+        } else if (code1 != 15u) {
+          const double* Pd = Pm + ch1 * 16;
+          if ((code1 & (code1 - 1)) == 0) {
+            const int b = __ffs(code1) - 1;
+            n0 = Pd[b]; n1 = Pd[4 + b]; n2 = Pd[8 + b]; n3 = Pd[12 + b];
+          } else {
+            const double e0 = (code1 & 1u) ? 1.0 : 0.0, e1 = (code1 & 2u) ? 1.0 : 0.0, e2 = (code1 & 4u) ? 1.0 : 0.0, e3 = (code1 & 8u) ? 1.0 : 0.0;
+            n0 = ((e0 * Pd[0] + e1 * Pd[1]) + e2 * Pd[2]) + e3 * Pd[3];
+            n1 = ((e0 * Pd[4] + e1 * Pd[5]) + e2 * Pd[6]) + e3 * Pd[7];
+            n2 = ((e0 * Pd[8] + e1 * Pd[9]) + e2 * Pd[10]) + e3 * Pd[11];
+            n3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];
+          }
+        }
+        // child 0's factor is applied first, then child 1's (same order as the reference's accumulation)
+        o0 = (1.0 * m0) * n0; o1 = (1.0 * m1) * n1; o2 = (1.0 * m2) * n2; o3 = (1.0 * m3) * n3;
+        sc = sc0 + sc1;
         // rescale by 2^256 when every entry dropped below 2^-256 (compare high words: all values are >= 0)
         const int hm = max(max(__double2hiint(o0), __double2hiint(o1)), max(__double2hiint(o2), __double2hiint(o3)));
         if (hm < 0x2FF00000 && hm > 0) {
           o0 *= PA_SCALE_UP; o1 *= PA_SCALE_UP; o2 *= PA_SCALE_UP; o3 *= PA_SCALE_UP;
           sc += 1;
         }
-        const int sl = (op.z >> 8) & 0xff;
-        double* st = S.stack + sl * 4 * kBD + tid;
-        st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
-        S.stack_sc[sl * kBD + tid] = (int16_t)sc;
+        if (!(op.z & 64u)) {  // the parent is not the next op: park the result on the stack
+          const int sl = (op.z >> 8) & 0xff;
+          double* st = S.stack + sl * 4 * kBD + tid;
+          st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
+          S.stack_sc[sl * kBD + tid] = (int16_t)sc;
+        }
         const uint32_t q = op.x >> 16;
         const uint32_t a = S.sel[s] ^ wflip;
         double2* g2 = reinterpret_cast<double2*>(A.part + (a * A.part_stride + (q * Ppad + p) * 4u));
@@ -306,7 +351,7 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
     for (int i = tid; i <= h->n_up; i += kBD) S.up_off[i] = ev.up_off[i];
     for (int i = tid; i <= h->n_down; i += kBD) S.down_off[i] = ev.down_off[i];
     // pruning program: one packed descriptor per computed internal node, in the element's pruning order:
-    //   x = node | q << 16;  y = child0 | child1 << 16;  z = kind0 | kind1 << 2 | slot << 8 | slot0 << 16 | slot1 << 24;
+    //   x = node | q << 16;  y = child0 | child1 << 16;  z = kind0 | kind1 << 2 | fwd bits 4..6 | slot << 8 | slot0 << 16 | slot1 << 24;
     //   w = x0 | x1 << 16 (tip row of a tip child, internal index of an internal child); kind 0 missing, 1 tip, 2 internal
     for (int k = tid; k < ni; k += kBD) {
       const int s = ev.su[k];
@@ -320,6 +365,10 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
         op.y = (uint32_t)c0 | ((uint32_t)c1 << 16);
         op.z = k0 | (k1 << 2) | ((uint32_t)(uint8_t)ev.slot[s] << 8) | ((uint32_t)(uint8_t)(k0 == 2 ? ev.slot[c0] : 0) << 16) |
                ((uint32_t)(uint8_t)(k1 == 2 ? ev.slot[c1] : 0) << 24);
+        // register forwarding: bit 4 / 5 = child 0 / 1 is the previous op, bit 6 = the parent is the next op
+        if (k > 0 && k0 == 2 && ev.su[k - 1] == c0) op.z |= 16u;
+        if (k > 0 && k1 == 2 && ev.su[k - 1] == c1) op.z |= 32u;
+        if (k + 1 < ni && ev.su[k + 1] >= 0 && ev.su[k + 1] == ev.parent[s]) op.z |= 64u;
         op.w = x_of(c0) | (x_of(c1) << 16);
       }
       S.ops[k] = op;
