@@ -323,7 +323,7 @@ class Engine:
         _check(self._lib.pa_engine_get_trace(self._h, i, model, C.byref(t)))
         return b
 
-    PHASES = ["init", "trace", "history", "emission", "z_update", "z_dirty_prune", "n_rate", "c_rate", "commit", "transitions"]
+    PHASES = ["init", "trace", "history", "emission", "z_update", "z_dirty_prune", "n_rate", "c_rate", "c_pass_only", "transitions"]
 
     def phase_cycles(self) -> dict:
         buf = (C.c_uint64 * 10)()

@@ -28,6 +28,9 @@ namespace pa {
 
 namespace {
 
+#ifndef PA_CTAS_PER_SM
+#define PA_CTAS_PER_SM 3
+#endif
 constexpr int kBD = 256;
 constexpr int kNW = kBD / 32;
 constexpr int kTile = 256;       // patterns / sites per tile
@@ -40,10 +43,24 @@ template <int NMAX, int SLOTS>
 struct SmemT {
   static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
   alignas(16) double Pcur[NMAX * 16];
-  alignas(16) double Pprop[NMAX * 16];
-  alignas(16) double stack[SLOTS * 4 * kBD];  // [slot][base][thread]
+  union {  // buffers that are live in disjoint phases of an iteration share storage
+    struct { alignas(16) double Pprop[NMAX * 16]; };  // rate steps: proposal P(t)
+    struct {                                          // history sampling .. Z update
+      double emis[NMAX * 3], back[NMAX * 3], eamb[NMAX * 3];
+      uint32_t cnt[NMAX * 16];
+    };
+  };
+  union {
+    struct {  // pruning passes: per-thread temp stack [slot][base][thread] + scale counts
+      alignas(16) double stack[SLOTS * 4 * kBD];
+      int16_t stack_sc[SLOTS * kBD];
+    };
+    struct {  // history sampling: per-warp tile counts, sampled bases [internal node][site]
+      uint8_t cnt8[kNW * NMAX * 16];
+      uint8_t xs8[NI * kBD];
+    };
+  };
   double red[34];
-  double emis[NMAX * 3], back[NMAX * 3], eamb[NMAX * 3];
   double dist[NMAX], uz[NMAX];
   double scal[SC_COUNT];
   double T[18];   // linear Z transition matrices [free, fixZ==1][child state a][parent state j]
@@ -53,13 +70,9 @@ struct SmemT {
   alignas(8) uint2 ht[NI];    // its non-missing tip children: {node | tip row << 16} each, 0xffffffff = none
   int ivars[IV_COUNT];
   int nz[18];
-  uint32_t cnt[NMAX * 16];
-  int16_t stack_sc[SLOTS * kBD];
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
-  uint8_t cnt8[kNW * NMAX * 16];
-  uint8_t xs8[NI * kBD];
   alignas(4) uint8_t codes[NI * kCodeRow];
 };
 
@@ -285,7 +298,7 @@ __device__ __forceinline__ void warp_count16(uint32_t code, bool act, uint8_t* _
 }
 
 template <int NMAX, int SLOTS>
-__global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
+__global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef SmemT<NMAX, SLOTS> SM;
   SM& S = *reinterpret_cast<SM*>(smem_raw);
@@ -767,7 +780,9 @@ __global__ void __launch_bounds__(kBD, 2) chain_kernel(ChainLaunch L) {
             }
           }
           __syncthreads();
+          const long long tp0 = clock64();
           const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, n_rows, tid);  // log_f_Xz, into the non-current copy
+          if (tid == 0 && !neut) ph8 += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
           if (tid == 0) {
             const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
             if (log(S.scal[SC_R]) < MH) {
@@ -917,6 +932,7 @@ size_t chain_arena_bytes(int n_max, int P_max) {
 }
 
 int chain_block_dim() { return kBD; }
+int chain_ctas_per_sm() { return PA_CTAS_PER_SM; }
 
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream) {
   if (BD != kBD) return PA_ERR_ARG;

@@ -18,6 +18,7 @@
 namespace pa {
 
 int chain_block_dim();
+int chain_ctas_per_sm();
 
 #define PA_CUDA(call)                                                                         \
   do {                                                                                        \
@@ -111,8 +112,8 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
     set_error("tree too large for the chain kernel's shared memory (" + std::to_string(smem) + " bytes needed)");
     return PA_ERR_LIMIT;
   }
-  int per_sm = std::max(1, std::min(2, (int)((size_t)smem_optin / smem)));
-  if (smem * 2 + 2048 > 233472) per_sm = 1;
+  // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and by the kernel's launch bounds
+  const int per_sm = std::max(1, std::min(chain_ctas_per_sm(), (int)(233472 / (smem + 1024))));
   const int grid = std::min(n_chains, num_sms * per_sm);
   const size_t stride = chain_arena_bytes(n_max, P_max);
   PA_CUDA(cudaMalloc(&d_chain_list, sizeof(int32_t) * 2 * n_chains));
