@@ -15,7 +15,7 @@ import numpy as np
 from . import build as _build
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = _build.LIB
+LIB_PATH = os.environ.get("PA_LIB", _build.LIB)  # PA_LIB: load an alternative build of the same library (A/B timing)
 BIN_PATH = _build.BIN
 
 PA_OK = 0

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphyloacc_b200.so")
 BIN = os.path.join(HERE, "PhyloAcc-ST-b200")
-LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu"]
+LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu", "pa_chain_warp.cu"]
 NVCC = os.environ.get("PA_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOSTCXX = "/usr/bin/g++"
@@ -40,6 +40,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
                    "-x", "cu", "-dc" if False else "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
+            for extra in os.environ.get("PA_NVCC_FLAGS", "").split():
+                cmd.insert(1, extra)
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         for s, p in procs:
             out, _ = p.communicate()

@@ -336,8 +336,9 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       S.ivars[IV_STAGED] = -1;
     }
     __syncthreads();
-    const int chain = S.ivars[IV_CHAIN];
-    if (chain >= L.n_chains) break;
+    const int qslot = S.ivars[IV_CHAIN];
+    if (qslot >= L.n_sel) break;
+    const int chain = L.sel ? L.sel[qslot] : qslot;
     const int elem = L.chain_list[2 * chain], mdl = L.chain_list[2 * chain + 1];
     const int resZ = (mdl == PA_M0) ? 0 : (mdl == PA_M1 ? 2 : 1);
     const uint32_t key = (uint32_t)elem * 4u + (uint32_t)mdl;

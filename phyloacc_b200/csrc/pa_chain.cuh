@@ -7,6 +7,7 @@ struct ChainLaunch {
   const uint8_t* blobs; const int64_t* blob_off;
   const int32_t* chain_list;  // [n_chains][2]
   int n_chains;
+  const int32_t* sel; int n_sel;  // chains this launch works through (indices into chain_list); sel == nullptr: 0..n_sel-1
   SubstDev sd; ChainParams cp;
   int n_max, slots_max, P_max, T, ZW, S_rows;
   double* trace_d; uint32_t* trace_z;
@@ -17,5 +18,10 @@ size_t chain_smem_bytes(int n_max, int slots_max, int s_rows);
 size_t chain_arena_bytes(int n_max, int P_max);
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
 int chain_block_dim();
+// one-warp-per-chain kernel (pa_chain_warp.cu)
+size_t chain_warp_smem_bytes(int n_max, int warps);
+int chain_warp_pst(int P_max);
+size_t chain_warp_arena_bytes(int n_max, int P_max);
+int launch_chains_warp(const ChainLaunch& L, int grid, int warps, cudaStream_t stream);
 }  // namespace pa
 #endif

@@ -23,12 +23,22 @@ prm.num_thread = 4
 eng = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup, conserve=tree.conserve, device=0)
 eng.load_alignment(batch.X, batch.elem_start, batch.elem_len)
 ids = np.arange(batch.C, dtype=np.int32)
-t0 = time.time()
-eng.sample(ids)
+import torch  # noqa: E402  (stream / events only)
+
+reps = int(os.environ.get("PA_PROF_REPS", "3"))
+stream = torch.cuda.Stream()
+eng.set_stream(stream.cuda_stream)
+for _ in range(reps):  # the last repetition is the timed one (the first pays module load and allocation)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    eng.sample(ids)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) * 1e-3
 res = eng.collect()
-dt = time.time() - t0
 c = eng.counters()
-print(f"elems={elems} iters={iters} wall={dt:.3f}s  el-iter/s={elems * 3 * iters / dt:.0f}  counters={c}")
+print(f"elems={elems} iters={iters} kernel={dt:.4f}s  el-iter/s={elems * 3 * iters / dt:.0f}  counters={c}")
 ph = eng.phase_cycles()
 tot = sum(v for k, v in ph.items() if k != 'c_pass_only')
 print("phase cycles per chain-iteration:", {k: round(v / max(c["chain_iterations"], 1)) for k, v in ph.items()}, "total", round(tot / max(c["chain_iterations"], 1)))
