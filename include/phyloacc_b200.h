@@ -141,6 +141,24 @@ int pa_engine_loglik_replay(pa_engine* e, int32_t n_states, const int32_t* elem,
  * pa_engine_run = sample + collect. */
 int pa_engine_sample(pa_engine* e, const int32_t* ids, int32_t n_ids);
 int pa_engine_collect(pa_engine* e, pa_results* out);
+
+/* Outer CHAIN iterations and SAMPLE_HYPER (main.cpp:445-516).  pa_engine_sample_ex runs the models in `model_mask`
+ * (bit PA_M0..PA_M2; the reference runs only the full model M2 under SAMPLE_HYPER 1, main.cpp:463-494); with
+ * `warm_start` != 0 every chain continues from the last state of its previous run on this handle -- Z, n, c, g, l,
+ * l2 -- as initMCMC does for iter > 0 (bpp_c.cpp:148-177, state saved by Gibbs, bpp_c.cpp:474-485); `chain_iter`
+ * selects the random streams of this outer iteration.  The state of a run is captured by pa_engine_collect.
+ * pa_engine_sample_hyper is BPP::sample_hyperparam (bpp.cpp:324-477): one independence-MH sweep over the five
+ * hyper-parameter pairs given the current rates of the full-model chains of `ids`; the accepted values take effect
+ * for the next pa_engine_sample(_ex) and are returned in `out`. */
+typedef struct pa_hyper {
+  double nprior_a, nprior_b, cprior_a, cprior_b;          /* ACCE_PRIOR_A/B, CONSERVE_PRIOR_A/B */
+  double prior_l_a, prior_l_b, prior_g_a, prior_g_b;      /* HYPER_LRATE_A/B, HYPER_GRATE_A/B */
+  double prior_l2_a, prior_l2_b;                          /* HYPER_LRATE2_A/B */
+} pa_hyper;
+int pa_engine_sample_ex(pa_engine* e, const int32_t* ids, int32_t n_ids, int32_t model_mask, int32_t warm_start, int32_t chain_iter);
+int pa_engine_get_hyper(const pa_engine* e, pa_hyper* out);
+int pa_engine_set_hyper(pa_engine* e, const pa_hyper* in);
+int pa_engine_sample_hyper(pa_engine* e, int32_t iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
 int pa_engine_run(pa_engine* e, const int32_t* ids, int32_t n_ids, pa_results* out);
 
 /* Trace of one chain of the last pa_engine_sample (i = position in ids, model = PA_M0..PA_M2). */

@@ -243,6 +243,37 @@ int main(int argc, char** argv) {
       for (int s = 0; s < N; s++) {
         printf("back %d %a %a %a\n", s, el->log_prob_back[s][0], el->log_prob_back[s][1], el->log_prob_back[s][2]);
       }
+    } else if (cmd == "hyper") {
+      // hyper <iter> <C> then C lines "r <n> <c> <g> <l> <l2>" : set bpp.cur_* and run the reference's own
+      // BPP::sample_hyperparam (bpp.cpp:324-477); its cout lines carry the MH ratios and the proposals
+      int iter, Cn;
+      ss >> iter >> Cn;
+      vector<int> ids;
+      for (int c = 0; c < Cn; c++) {
+        string rl;
+        getline(script, rl);
+        istringstream rs(rl);
+        string tag; double a, b, g, l, l2;
+        rs >> tag >> a >> b >> g >> l >> l2;
+        if (c < bpp.C) {
+          bpp.cur_nrate[c] = a; bpp.cur_crate[c] = b; bpp.cur_grate[c] = g; bpp.cur_lrate[c] = l; bpp.cur_lrate2[c] = l2;
+          ids.push_back(c);
+        }
+      }
+      printf("hyper_before %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", bpp.nprior_a, bpp.nprior_b, bpp.cprior_a, bpp.cprior_b,
+             bpp.prior_l_a, bpp.prior_l_b, bpp.prior_g_a, bpp.prior_g_b, bpp.prior_l2_a, bpp.prior_l2_b);
+      ostringstream cap;
+      streambuf* prev = cout.rdbuf(cap.rdbuf());
+      const streamsize old_prec = cout.precision(17);
+      ofstream devnull("/dev/null");
+      bpp.sample_hyperparam(iter, ids, devnull);
+      cout.rdbuf(prev);
+      cout.precision(old_prec);
+      istringstream lines(cap.str());
+      string ln;
+      while (getline(lines, ln)) printf("hyper_log %s\n", ln.c_str());
+      printf("hyper_after %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", bpp.nprior_a, bpp.nprior_b, bpp.cprior_a, bpp.cprior_b,
+             bpp.prior_l_a, bpp.prior_l_b, bpp.prior_g_a, bpp.prior_g_b, bpp.prior_l2_a, bpp.prior_l2_b);
     } else if (cmd == "eval2") {
       // eval2 <resZ> <T> then T lines "t <loglik> <n> <c> <Z[0..N-1]>" : fills the traces as Gibbs would, then runs
       // MonitorChain-equivalent bookkeeping (full loglik, Max_Z) through the reference's own MonitorChain and Eval2.

@@ -69,6 +69,14 @@ class PaElementInfo(C.Structure):
                 ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p)]
 
 
+class PaHyper(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("nprior_a", "nprior_b", "cprior_a", "cprior_b", "prior_l_a", "prior_l_b", "prior_g_a", "prior_g_b",
+                                          "prior_l2_a", "prior_l2_b")]
+
+    def as_dict(self):
+        return {k: float(getattr(self, k)) for k, _ in self._fields_}
+
+
 class PaCounters(C.Structure):
     _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
                 ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
@@ -80,6 +88,7 @@ EXPORTS = [
     "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters", "pa_engine_phase_cycles",
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
+    "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper",
 ]
 
 _lib = None
@@ -116,6 +125,10 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_sample.argtypes = [C.c_void_p, _i32p, C.c_int32]
     lib.pa_engine_collect.argtypes = [C.c_void_p, C.POINTER(PaResults)]
     lib.pa_engine_run.argtypes = [C.c_void_p, _i32p, C.c_int32, C.POINTER(PaResults)]
+    lib.pa_engine_sample_ex.argtypes = [C.c_void_p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.pa_engine_get_hyper.argtypes = [C.c_void_p, C.POINTER(PaHyper)]
+    lib.pa_engine_set_hyper.argtypes = [C.c_void_p, C.POINTER(PaHyper)]
+    lib.pa_engine_sample_hyper.argtypes = [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.POINTER(PaHyper)]
     lib.pa_engine_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PaTrace)]
     lib.pa_engine_counters.argtypes = [C.c_void_p, C.POINTER(PaCounters)]
     lib.pa_engine_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -300,6 +313,31 @@ class Engine:
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         self._last_ids = ids
         _check(self._lib.pa_engine_sample(self._h, ids.ctypes.data_as(_i32p), len(ids)))
+
+    def sample_ex(self, ids, model_mask: int = 7, warm_start: bool = False, chain_iter: int = 0):
+        """One outer CHAIN iteration (main.cpp:445-500): models in `model_mask`, optionally continuing every chain from its last state."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        self._last_ids = ids
+        _check(self._lib.pa_engine_sample_ex(self._h, ids.ctypes.data_as(_i32p), len(ids), model_mask, int(bool(warm_start)), chain_iter))
+
+    def hyper(self) -> dict:
+        h = PaHyper()
+        _check(self._lib.pa_engine_get_hyper(self._h, C.byref(h)))
+        return h.as_dict()
+
+    def set_hyper(self, **kw):
+        h = PaHyper()
+        _check(self._lib.pa_engine_get_hyper(self._h, C.byref(h)))
+        for k, v in kw.items():
+            setattr(h, k, float(v))
+        _check(self._lib.pa_engine_set_hyper(self._h, C.byref(h)))
+
+    def sample_hyper(self, it: int, ids) -> dict:
+        """BPP::sample_hyperparam (bpp.cpp:324-477) from the current states of the full-model chains of `ids`."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        h = PaHyper()
+        _check(self._lib.pa_engine_sample_hyper(self._h, it, ids.ctypes.data_as(_i32p), len(ids), C.byref(h)))
+        return h.as_dict()
 
     def collect(self) -> Results:
         res = Results(len(self._last_ids), self.N)

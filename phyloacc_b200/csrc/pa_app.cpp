@@ -114,7 +114,12 @@ static int run_from_config(const char* cfg_path) {
   out_hyper << "iter\tnprior_a\tnprior_b\tcprior_a\tcprior_b\tprior_l_a\tprior_l_b\tprior_g_a\tprior_g_b\n";
   out_hyper << 0 << "\t" << P.num.acce_prior_a << "\t" << P.num.acce_prior_b << "\t" << P.num.conserve_prior_a << "\t" << P.num.conserve_prior_b
             << "\t" << P.num.hyper_lrate_a << "\t" << P.num.hyper_lrate_b << "\t" << P.num.hyper_grate_a << "\t" << P.num.hyper_grate_b << std::endl;
-  out_hyper.close();
+  std::ofstream out_lik_hyper;  // SAMPLE_HYPER 1: _elem_lik.txt is opened once and appended to by every outer iteration (main.cpp:373-378)
+  if (P.sample_hyper) {
+    out_lik_hyper.open((prefix + "_elem_lik.txt").c_str());
+    out_lik_hyper.precision(8);
+    out_lik_hyper << "No.\tID\tloglik_all\tloglik_Max" << std::endl;
+  }
   std::ofstream out_Z[3];
   for (int m = 0; m < 3; m++) {
     out_Z[m].open((prefix + "_rate_postZ_M" + std::to_string(m) + ".txt").c_str());
@@ -128,7 +133,6 @@ static int run_from_config(const char* cfg_path) {
     for (int s = 0; s < N; s++) sp << tree.names[s] << std::endl;
   }
   std::cout << e->ids.size() << " of elements to be computed" << std::endl;
-  if (P.sample_hyper) std::cout << "SAMPLE_HYPER is not supported by this engine; running with fixed hyper-parameters." << std::endl;
 
   const int C = (int)e->eng.plans.size();
   std::vector<int32_t> ids;
@@ -153,7 +157,9 @@ static int run_from_config(const char* cfg_path) {
       const int wn = std::min(wave, n - w0);
       pa_results wres{wn, N, filtered.data() + w0, loglik.data() + (size_t)w0 * 3, loglik_max.data() + (size_t)w0 * 3,
                       maxZ.data() + (size_t)w0 * 3 * N, med.data() + (size_t)w0 * 15, postZ.data() + (size_t)w0 * 3 * N * 4};
-      rc = e->eng.sample(ids.data() + w0, wn);
+      // SAMPLE_HYPER 1 runs only the full model (main.cpp:463-494); outer iterations after the first continue every chain
+      // from its last state (initMCMC with iter > 0, bpp_c.cpp:148-177)
+      rc = e->eng.sample(ids.data() + w0, wn, P.sample_hyper ? (1 << PA_M2) : 7, iter > 0, iter);
       if (rc == PA_OK) rc = e->eng.collect(&wres);
       if (rc != PA_OK) {
         std::cerr << "(Error. " << get_error() << ")" << std::endl;
@@ -191,6 +197,7 @@ static int run_from_config(const char* cfg_path) {
     for (int i = 0; i < n; i++) {
       if (filtered[i]) continue;
       for (int m = 0; m < 3; m++) {
+        if (P.sample_hyper && m != PA_M2) continue;
         const double* md = &med[((size_t)i * 3 + m) * 5];
         out_Z[m] << ids[i] << "\t" << md[0] << "\t" << md[1] << "\t" << md[2] << "\t" << md[3] << "\t" << md[4];
         const double* pz = &postZ[(((size_t)i * 3 + m) * N) * 4];
@@ -198,6 +205,20 @@ static int run_from_config(const char* cfg_path) {
           for (int k = 0; k < 4; k++) out_Z[m] << "\t" << pz[s * 4 + k];
         out_Z[m] << std::endl;
       }
+    }
+    if (P.sample_hyper) {
+      // BPP::sample_hyperparam + BPP::Output_init0 (main.cpp:504-506, bpp.cpp:324-477, 622-635)
+      pa_hyper hy;
+      rc = e->eng.sample_hyper(iter, e->ids.data(), (int32_t)e->ids.size(), &hy);
+      if (rc != PA_OK) {
+        std::cout << " 2 Standard exception: " << get_error() << std::endl;
+      } else {
+        out_hyper << iter << "\t" << hy.nprior_a << "\t" << hy.nprior_b << "\t" << hy.cprior_a << "\t" << hy.cprior_b << "\t" << hy.prior_l_a << "\t"
+                  << hy.prior_l_b << "\t" << hy.prior_g_a << "\t" << hy.prior_g_b << "\t" << hy.prior_l2_a << "\t" << hy.prior_l2_b << std::endl;
+      }
+      for (int i = 0; i < n; i++)
+        out_lik_hyper << ids[i] << "\t" << e->element_names[ids[i]] << "\t" << loglik[i * 3 + PA_M2] << "\t" << loglik_max[i * 3 + PA_M2] << std::endl;
+      continue;
     }
     // _elem_lik.txt and _M{k}_elem_Z.txt (BPP::Output_init, bpp.cpp:568-619): one row per id, zeros for filtered ones
     {

@@ -114,6 +114,46 @@ int pa_engine_sample(pa_engine* e, const int32_t* ids, int32_t n_ids) {
   return guarded([&]() { return e->eng.sample(ids, n_ids); });
 }
 
+int pa_engine_sample_ex(pa_engine* e, const int32_t* ids, int32_t n_ids, int32_t model_mask, int32_t warm_start, int32_t chain_iter) {
+  if (!e || (n_ids > 0 && !ids) || (model_mask & ~7) || model_mask == 0 || chain_iter < 0) {
+    g_last = "bad argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.sample(ids, n_ids, model_mask, warm_start != 0, chain_iter); });
+}
+
+int pa_engine_get_hyper(const pa_engine* e, pa_hyper* out) {
+  if (!e || !out) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  const pa_params& P = e->eng.model.prm;
+  out->nprior_a = P.acce_prior_a; out->nprior_b = P.acce_prior_b; out->cprior_a = P.conserve_prior_a; out->cprior_b = P.conserve_prior_b;
+  out->prior_l_a = P.hyper_lrate_a; out->prior_l_b = P.hyper_lrate_b; out->prior_g_a = P.hyper_grate_a; out->prior_g_b = P.hyper_grate_b;
+  out->prior_l2_a = P.hyper_lrate2_a; out->prior_l2_b = P.hyper_lrate2_b;
+  return PA_OK;
+}
+
+int pa_engine_set_hyper(pa_engine* e, const pa_hyper* in) {
+  if (!e || !in) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  pa_params& P = e->eng.model.prm;
+  P.acce_prior_a = in->nprior_a; P.acce_prior_b = in->nprior_b; P.conserve_prior_a = in->cprior_a; P.conserve_prior_b = in->cprior_b;
+  P.hyper_lrate_a = in->prior_l_a; P.hyper_lrate_b = in->prior_l_b; P.hyper_grate_a = in->prior_g_a; P.hyper_grate_b = in->prior_g_b;
+  P.hyper_lrate2_a = in->prior_l2_a; P.hyper_lrate2_b = in->prior_l2_b;
+  return PA_OK;
+}
+
+int pa_engine_sample_hyper(pa_engine* e, int32_t iter, const int32_t* ids, int32_t n_ids, pa_hyper* out) {
+  if (!e || (n_ids > 0 && !ids)) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.sample_hyper(iter, ids, n_ids, out); });
+}
+
 int pa_engine_collect(pa_engine* e, pa_results* out) {
   if (!e || !out) {
     g_last = "null argument";

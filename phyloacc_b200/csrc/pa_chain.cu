@@ -346,6 +346,11 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
     const ElemHeader* h = ev.h;
     const int n = h->n, ni = h->ni, GG = h->GG, Ppad = h->Ppad, root = n - 1;
     const int T = L.T;
+    // warm start (initMCMC with iter > 0, bpp_c.cpp:148-177): Z and the five rates continue from the last state of the
+    // chain's previous run; otherwise the INIT_* values
+    const double* warm = (L.init_rates && L.init_rates[(size_t)chain * 8 + 5] != 0.0) ? L.init_rates + (size_t)chain * 8 : nullptr;
+    const double init_n = warm ? warm[0] : cp.init_nrate, init_c = warm ? warm[1] : cp.init_crate, init_g = warm ? warm[2] : cp.init_grate,
+                 init_l = warm ? warm[3] : cp.init_lrate, init_l2 = warm ? warm[4] : cp.init_lrate2;
 
     // ---------------- initMCMC (bpp_c.cpp:131-343)
     for (int i = tid; i < n; i += kBD) {
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       S.flags[i] = f;
       S.fix[i] = (f >> (2 + mdl)) & 1;
       S.dist[i] = ev.dist[i];
-      S.Z[i] = (i == root) ? 0 : 1;  // bpp_c.cpp:141-146
+      S.Z[i] = warm ? (int8_t)((L.init_z[(size_t)chain * L.ZW + (i >> 4)] >> (2 * (i & 15))) & 3u) : (int8_t)((i == root) ? 0 : 1);  // bpp_c.cpp:141-151
       S.dirty[i] = 0;
       S.sel[i] = 0;
     }
@@ -400,17 +405,17 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       int nsu = 0;
       while (nsu < ni && ev.su[nsu] >= 0) nsu++;
       S.ivars[IV_NSU] = nsu;
-      S.scal[SC_N] = cp.init_nrate;
-      S.scal[SC_C] = cp.init_crate;
-      S.scal[SC_G] = cp.init_grate;
-      S.scal[SC_L] = cp.init_lrate;
-      S.scal[SC_L2] = cp.init_lrate2;
+      S.scal[SC_N] = init_n;
+      S.scal[SC_C] = init_c;
+      S.scal[SC_G] = init_g;
+      S.scal[SC_L] = init_l;
+      S.scal[SC_L2] = init_l2;
       S.scal[SC_PROPC] = 1.2;                  // bpp_c.cpp:135
       S.scal[SC_PROPN] = (double)1 / GG * 10;  // bpp_c.cpp:136
       S.ivars[IV_ACC_N] = 0;
       S.ivars[IV_ACC_C] = 0;
       // linear Z transition matrices (bpp_c.cpp:301-332), index [child state a][parent state j] -> a*3+j
-      const double g = cp.init_grate, l = cp.init_lrate, l2 = cp.init_lrate2;
+      const double g = init_g, l = init_l, l2 = init_l2;
       double* Tf = S.T;      // free
       double* Tx = S.T + 9;  // fixZ == 1
       const double y = 1 - l;
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
     // P(t) of every branch for its class, and the log P tables of the three classes (emission look-ups); task = (class, node, row)
     for (int task = tid; task < 12 * n; task += kBD) {
       const int k = task / (4 * n), rem = task - k * 4 * n, i = rem >> 2, j = rem & 3;
-      const double rate = (k == 0) ? 1.0 : (k == 1 ? cp.init_crate : cp.init_nrate);
+      const double rate = (k == 0) ? 1.0 : (k == 1 ? init_c : init_n);
       double r0, r1, r2, r3;
       build_P_row(sd, S.dist[i], rate, j, r0, r1, r2, r3);
       double* lp = logP + ((size_t)k * L.n_max + i) * 16 + j * 4;
@@ -688,12 +693,15 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       __syncthreads();
       if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431 (recomputed partials overwrite the current copy in place)
         const double ll = prune_pass<true>(ev, S, S.Pcur, 0, A, n_su, n_rows, tid);
-        if (tid == 0) {
-          S.scal[SC_LL] = ll;
+        if (warp == 0) {  // work counters: lane-parallel, not a serial loop on one thread
           int cnt_nodes = 0;
-          for (int k = 0; k < n_su; k++) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
-          w_npu += (unsigned long long)cnt_nodes * h->P;
-          w_root += h->P;
+          for (int k = lane; k < n_su; k += 32) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
+          cnt_nodes = __reduce_add_sync(0xffffffffu, cnt_nodes);
+          if (lane == 0) {
+            S.scal[SC_LL] = ll;
+            w_npu += (unsigned long long)cnt_nodes * h->P;
+            w_root += h->P;
+          }
         }
         __syncthreads();
       }
@@ -784,19 +792,23 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
           const long long tp0 = clock64();
           const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, n_rows, tid);  // log_f_Xz, into the non-current copy
           if (tid == 0 && !neut) ph8 += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
-          if (tid == 0) {
-            const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
-            if (log(S.scal[SC_R]) < MH) {
-              S.ivars[IV_ACCEPT] = 1;
-              S.ivars[IV_RATE_CHANGED] = (proposal != old_rate) ? 1 : 0;
-              S.scal[SC_LL] = ll_new;
+          if (warp == 0) {
+            int cnt_nodes = 0, cnt_cls = 0;  // work counters: lane-parallel, not a serial loop on one thread
+            for (int k = lane; k < n_su; k += 32) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
+            for (int i = lane; i < n - 1; i += 32) cnt_cls += (S.Z[i] == cls);
+            cnt_nodes = __reduce_add_sync(0xffffffffu, cnt_nodes);
+            cnt_cls = __reduce_add_sync(0xffffffffu, cnt_cls);
+            if (lane == 0) {
+              const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
+              if (log(S.scal[SC_R]) < MH) {
+                S.ivars[IV_ACCEPT] = 1;
+                S.ivars[IV_RATE_CHANGED] = (proposal != old_rate) ? 1 : 0;
+                S.scal[SC_LL] = ll_new;
+              }
+              w_npu += (unsigned long long)cnt_nodes * h->P;
+              w_root += h->P;
+              w_pt += cnt_cls;
             }
-            int cnt_nodes = 0, cnt_cls = 0;
-            for (int k = 0; k < n_su; k++) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
-            for (int i = 0; i < n - 1; i++) cnt_cls += (S.Z[i] == cls);
-            w_npu += (unsigned long long)cnt_nodes * h->P;
-            w_root += h->P;
-            w_pt += cnt_cls;
           }
           __syncthreads();
         }

@@ -11,6 +11,8 @@ struct ChainLaunch {
   SubstDev sd; ChainParams cp;
   int n_max, slots_max, P_max, T, ZW, S_rows;
   double* trace_d; uint32_t* trace_z;
+  const double* init_rates;   // [n_chains][8]: n, c, g, l, l2 rates, flag (0: cold start), 2 unused; nullptr: all cold
+  const uint32_t* init_z;     // [n_chains][ZW] packed Z of a warm start
   uint8_t* arena; size_t arena_stride;
   unsigned long long* counters; int* queue;
 };

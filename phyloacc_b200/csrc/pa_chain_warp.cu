@@ -665,6 +665,11 @@ __global__ void __launch_bounds__(32 * W, MINB) chain_warp_kernel(ChainLaunch L)
     const int resZ = (mdl == PA_M0) ? 0 : (mdl == PA_M1 ? 2 : 1);
     const uint32_t key = (uint32_t)elem * 4u + (uint32_t)mdl;
     const int T = L.T;
+    // warm start (initMCMC with iter > 0, bpp_c.cpp:148-177): Z and the five rates continue from the last state of the
+    // chain's previous run; otherwise the INIT_* values
+    const double* warm = (L.init_rates && L.init_rates[(size_t)chain * 8 + 5] != 0.0) ? L.init_rates + (size_t)chain * 8 : nullptr;
+    const double init_n = warm ? warm[0] : cp.init_nrate, init_c = warm ? warm[1] : cp.init_crate, init_g = warm ? warm[2] : cp.init_grate,
+                 init_l = warm ? warm[3] : cp.init_lrate, init_l2 = warm ? warm[4] : cp.init_lrate2;
     int n, ni, GG, root, P;
     {
       // ---------------- initMCMC (bpp_c.cpp:131-343)
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(32 * W, MINB) chain_warp_kernel(ChainLaunch L)
         S.flags[i] = f;
         S.fix[i] = (f >> (2 + mdl)) & 1;
         S.dist[i] = ev.dist[i];
-        S.Z[i] = (i == root) ? 0 : 1;  // bpp_c.cpp:141-146
+        S.Z[i] = warm ? (int8_t)((L.init_z[(size_t)chain * L.ZW + (i >> 4)] >> (2 * (i & 15))) & 3u) : (int8_t)((i == root) ? 0 : 1);  // bpp_c.cpp:141-151
         S.dirty[i] = 0;
         S.sel[i] = 0;
       }
@@ -733,17 +738,17 @@ __global__ void __launch_bounds__(32 * W, MINB) chain_warp_kernel(ChainLaunch L)
         for (int q = ni - 1; q >= 0; q--)
           if (!(ev.flags[ev.intlist[q]] & PA_F_MISSING)) S.hq[nh++] = (uint16_t)q;
         S.ivars[IV_NH] = nh;
-        S.scal[SC_N] = cp.init_nrate;
-        S.scal[SC_C] = cp.init_crate;
-        S.scal[SC_G] = cp.init_grate;
-        S.scal[SC_L] = cp.init_lrate;
-        S.scal[SC_L2] = cp.init_lrate2;
+        S.scal[SC_N] = init_n;
+        S.scal[SC_C] = init_c;
+        S.scal[SC_G] = init_g;
+        S.scal[SC_L] = init_l;
+        S.scal[SC_L2] = init_l2;
         S.scal[SC_PROPC] = 1.2;                  // bpp_c.cpp:135
         S.scal[SC_PROPN] = (double)1 / GG * 10;  // bpp_c.cpp:136
         S.ivars[IV_ACC_N] = 0;
         S.ivars[IV_ACC_C] = 0;
         // linear Z transition matrices (bpp_c.cpp:301-332), index [child state a][parent state j] -> a*3+j
-        const double g = cp.init_grate, l = cp.init_lrate, l2 = cp.init_lrate2;
+        const double g = init_g, l = init_l, l2 = init_l2;
         double* Tf = S.T;      // free
         double* Tx = S.T + 9;  // fixZ == 1
         const double y = 1 - l;
@@ -757,7 +762,7 @@ __global__ void __launch_bounds__(32 * W, MINB) chain_warp_kernel(ChainLaunch L)
     // P(t) of every branch for its class, and the log P tables of the three classes (emission look-ups); task = (class, node)
     for (int task = tid; task < 3 * n; task += BD) {
       const int k = task / n, i = task - k * n;
-      const double rate = (k == 0) ? 1.0 : (k == 1 ? cp.init_crate : cp.init_nrate);
+      const double rate = (k == 0) ? 1.0 : (k == 1 ? init_c : init_n);
       const int zi = S.Z[i];
       const bool mine = (k == ((zi == 0) ? 0 : (zi == 2 ? 2 : 1)));
       build_P_to<SM>(S.dist[i], rate, mine ? (S.Pcur + i * 16) : nullptr, logP + ((size_t)k * L.n_max + i) * 16);

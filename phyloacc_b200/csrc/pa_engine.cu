@@ -106,7 +106,8 @@ void Engine::release_device() {
   auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
   fr((void*&)d_blobs); fr((void*&)d_blob_off);
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
-  fr((void*&)d_arena_w); fr((void*&)d_sel);
+  fr((void*&)d_arena_w); fr((void*&)d_sel); fr((void*&)d_init_rates); fr((void*&)d_init_z);
+  cap_init_rates = cap_init_z = 0;
   cap_chain_list = cap_sel = cap_trace_d = cap_trace_z = cap_arena = cap_arena_w = cap_counters = cap_queue = 0;
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
@@ -158,6 +159,8 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
       return PA_ERR_ARG;
     }
   plans.assign(C, ElemPlan());
+  cur_set.clear();  // a new batch: no chain has a previous state
+
   const int nt = std::max(1, model.prm.num_thread);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
   for (int c = 0; c < C; c++) plan_element(model, X, G, elem_start[c], elem_len[c], c, plans[c]);

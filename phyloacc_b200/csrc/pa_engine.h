@@ -49,6 +49,14 @@ struct Engine {
   size_t cap_chain_list = 0, cap_sel = 0, cap_trace_d = 0, cap_trace_z = 0, cap_arena = 0, cap_arena_w = 0, cap_counters = 0, cap_queue = 0;
   unsigned long long* d_counters = nullptr;
   int* d_queue = nullptr;
+  // last state of every (element, model) chain that has run: the warm start of the next outer CHAIN iteration
+  // (bpp.cur_Z / cur_nrate / cur_crate / cur_grate / cur_lrate / cur_lrate2, bpp_c.cpp:474-485)
+  std::vector<double> cur_rates;         // [C][3][5] n, c, g, l, l2
+  std::vector<uint32_t> cur_z;           // [C][3][ZW] packed local Z
+  std::vector<uint8_t> cur_set;          // [C][3]
+  double* d_init_rates = nullptr;
+  uint32_t* d_init_z = nullptr;
+  size_t cap_init_rates = 0, cap_init_z = 0;
   std::vector<double> h_trace_d;
   std::vector<uint32_t> h_trace_z;
   bool sampled = false, collected = false;
@@ -60,7 +68,8 @@ struct Engine {
   int init(const pa_tree* tree, const pa_subst* subst, const pa_params* params, int dev);
   int load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len);
   int loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out);
-  int sample(const int32_t* ids, int32_t n_ids);
+  int sample(const int32_t* ids, int32_t n_ids, int model_mask = 7, bool warm_start = false, int chain_iter = 0);
+  int sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
   int fetch_traces();
   int collect(pa_results* out);
   int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);

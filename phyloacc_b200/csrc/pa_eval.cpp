@@ -38,8 +38,130 @@ static double gamma_pdf(double x, double a, double b) {  // gsl_ran_gamma_pdf
 }
 static double lnbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
 
+// ------------------------------------------------------------------------------------------ hyper-parameters
+namespace {
+
+// host copy of the device draw schedule (pa_device.cuh: philox4 / u01 / sched_gamma)
+struct U4 { uint32_t x, y, z, w; };
+U4 philox4_host(uint32_t seed, uint32_t key, uint32_t idx, uint32_t sub, uint32_t iter, uint32_t stream) {
+  uint32_t c0 = idx, c1 = sub, c2 = iter, c3 = stream, k0 = seed, k1 = key;
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return U4{c0, c1, c2, c3};
+}
+double u01_host(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
+double gamma_host(uint32_t seed, uint32_t key, uint32_t idx, uint32_t sub0, uint32_t iter, uint32_t stream, double a, double b) {
+  U4 w = philox4_host(seed, key, idx, sub0, iter, stream);
+  double boost = 1.0;
+  if (a < 1.0) {
+    boost = std::pow(u01_host(w.w), 1.0 / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0, c = (1.0 / 3.0) / std::sqrt(d);
+  for (uint32_t attempt = 0;; attempt++) {
+    if (attempt > 0) w = philox4_host(seed, key, idx, sub0 + attempt, iter, stream);
+    if (attempt > 1000) return NAN;
+    const double x = std::sqrt(-2.0 * std::log(u01_host(w.x))) * std::cos(6.283185307179586 * u01_host(w.y));
+    double v = 1.0 + c * x;
+    if (v <= 0) continue;
+    v = v * v * v;
+    const double u = u01_host(w.z);
+    if (u < 1 - 0.0331 * x * x * x * x) return b * d * v * boost;
+    if (std::log(u) < 0.5 * x * x + d * (1 - v + std::log(v))) return b * d * v * boost;
+  }
+}
+
+}  // namespace
+
+#define PA_ST_HYPER 4u
+#define PA_KEY_HYPER 3u  // element keys are 4 * element + model, model < 3
+
+// BPP::sample_hyperparam (bpp.cpp:324-477): independence MH on the Gamma priors of the two rates and multiplicative
+// uniform MH on the Beta priors of l, l2, g, from the CURRENT states of the full-model chains (bpp.cur_*; elements
+// whose chain never ran keep the INIT_* values, as in the reference).  Draws come from the Philox schedule (stream
+// PA_ST_HYPER) in the reference's order of consumption.
+int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out) {
+  pa_params& P = model.prm;
+  const size_t C = plans.size();
+  std::vector<double> rn(n_ids), rc(n_ids), rl(n_ids), rl2(n_ids), rg(n_ids);
+  for (int i = 0; i < n_ids; i++) {
+    const int c = ids[i];
+    if (c < 0 || (size_t)c >= C) {
+      set_error("element id out of range");
+      return PA_ERR_ARG;
+    }
+    const size_t slot = (size_t)c * 3 + PA_M2;
+    const bool have = cur_set.size() == C * 3 && cur_set[slot];
+    rn[i] = have ? cur_rates[slot * 5 + 0] : P.init_acce_rate;
+    rc[i] = have ? cur_rates[slot * 5 + 1] : P.init_conserve_rate;
+    rg[i] = have ? cur_rates[slot * 5 + 2] : P.init_grate;
+    rl[i] = have ? cur_rates[slot * 5 + 3] : P.init_lrate;
+    rl2[i] = have ? cur_rates[slot * 5 + 4] : P.init_lrate2;
+  }
+  const uint32_t seed = (uint32_t)P.seed, it = (uint32_t)iter;
+  uint32_t n_draw = 0;
+  auto gam = [&](double a, double b) { return gamma_host(seed, PA_KEY_HYPER, n_draw++, 0u, it, PA_ST_HYPER, a, b); };
+  auto uni = [&]() { return u01_host(philox4_host(seed, PA_KEY_HYPER, n_draw++, 0u, it, PA_ST_HYPER).x); };
+  const double p = 1, r = 1, q = 0.1, sc = 0.1;  // hyper-priors of the Gamma shapes / scales (bpp.cpp:328-329)
+  const double vna = 100, vnb = 100, vca = 100, vcb = 100;
+  const double n_ids_d = (double)n_ids;
+  double& nprior_a = P.acce_prior_a; double& nprior_b = P.acce_prior_b;
+  double& cprior_a = P.conserve_prior_a; double& cprior_b = P.conserve_prior_b;
+  const double nprior_a_prop = gam(vna, nprior_a / vna);
+  const double cprior_a_prop = gam(vca, cprior_a / vca);
+  const double nprior_b_prop = gam(vnb, nprior_b / vnb);
+  const double cprior_b_prop = gam(vcb, cprior_b / vcb);
+  auto rate_step = [&](const std::vector<double>& rates, double& a, double& b, double a_prop, double b_prop, double va, double vb) {
+    double sum_r = 0, log_prod_r = 0;
+    for (double x : rates) {
+      sum_r += x;
+      log_prod_r += std::log(x);
+    }
+    double M = (a_prop - 1) * (std::log(p) + log_prod_r) - (q + sum_r) / b_prop - (n_ids_d + r) * std::lgamma(a_prop) - std::log(b_prop) * a_prop * (sc + n_ids_d);
+    M -= (a - 1) * (std::log(p) + log_prod_r) - (q + sum_r) / b - (n_ids_d + r) * std::lgamma(a) - std::log(b) * a * (sc + n_ids_d);
+    const double H = std::log(gamma_pdf(a, va, a_prop / va)) - std::log(gamma_pdf(a_prop, va, a / va)) + std::log(gamma_pdf(b, vb, b_prop / vb)) -
+                     std::log(gamma_pdf(b_prop, vb, b / vb));
+    if (std::log(uni()) < M + H) {
+      a = a_prop;
+      b = b_prop;
+    }
+  };
+  rate_step(rn, nprior_a, nprior_b, nprior_a_prop, nprior_b_prop, vna, vnb);
+  rate_step(rc, cprior_a, cprior_b, cprior_a_prop, cprior_b_prop, vca, vcb);
+  auto beta_step = [&](const std::vector<double>& rates, double& a, double& b) {
+    const double a_prop = a * (uni() * (1.3 - 0.7) + 0.7);
+    const double b_prop = b * (uni() * (1.3 - 0.7) + 0.7);
+    double log_p = 0, log_pc = 0;
+    for (double x : rates) {
+      log_p += std::log(x);
+      log_pc += std::log(1 - x);
+    }
+    double M = (a_prop - a) * (log_p - 1) + (b_prop - b) * (log_pc - 1);
+    M += n_ids_d * (lnbeta(a, b) - lnbeta(a_prop, b_prop));
+    const double H = std::log(a) - std::log(a_prop) + std::log(b) - std::log(b_prop);
+    if (std::log(uni()) < M + H) {
+      a = a_prop;
+      b = b_prop;
+    }
+  };
+  beta_step(rl, P.hyper_lrate_a, P.hyper_lrate_b);
+  beta_step(rl2, P.hyper_lrate2_a, P.hyper_lrate2_b);
+  beta_step(rg, P.hyper_grate_a, P.hyper_grate_b);
+  if (out) {
+    out->nprior_a = nprior_a; out->nprior_b = nprior_b; out->cprior_a = cprior_a; out->cprior_b = cprior_b;
+    out->prior_l_a = P.hyper_lrate_a; out->prior_l_b = P.hyper_lrate_b; out->prior_g_a = P.hyper_grate_a; out->prior_g_b = P.hyper_grate_b;
+    out->prior_l2_a = P.hyper_lrate2_a; out->prior_l2_b = P.hyper_lrate2_b;
+  }
+  return PA_OK;
+}
+
 // ------------------------------------------------------------------------------------------ launch
-int Engine::sample(const int32_t* ids, int32_t n_ids) {
+int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_start, int chain_iter) {
   if (!loaded) {
     set_error("pa_engine_sample called before pa_engine_load_alignment");
     return PA_ERR_STATE;
@@ -67,6 +189,7 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
     }
     if (plans[c].filtered) continue;
     for (int mdl = 0; mdl < 3; mdl++) {
+      if (!((model_mask >> mdl) & 1)) continue;
       chain_of[(size_t)i * 3 + mdl] = (int)chain_elem_pos.size();
       chain_elem_pos.push_back(i);
       chain_model.push_back(mdl);
@@ -179,6 +302,26 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
   PA_CUDA(cudaMemcpyAsync(d_sel, sel_all.data(), sizeof(int32_t) * n_chains, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 24, stream));
   PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int) * 2, stream));
+  bool any_warm = false;
+  if (warm_start && !cur_set.empty()) {
+    std::vector<double> ir((size_t)n_chains * 8, 0.0);
+    std::vector<uint32_t> iz((size_t)n_chains * ZW, 0u);
+    for (int k = 0; k < n_chains; k++) {
+      const size_t slot = (size_t)list[2 * k] * 3 + list[2 * k + 1];
+      if (!cur_set[slot]) continue;
+      any_warm = true;
+      for (int j = 0; j < 5; j++) ir[(size_t)k * 8 + j] = cur_rates[slot * 5 + j];
+      ir[(size_t)k * 8 + 5] = 1.0;
+      for (int w = 0; w < ZW; w++) iz[(size_t)k * ZW + w] = cur_z[slot * ZW + w];
+    }
+    if (any_warm) {
+      PA_CUDA(reserve((void*&)d_init_rates, cap_init_rates, sizeof(double) * ir.size()));
+      PA_CUDA(reserve((void*&)d_init_z, cap_init_z, sizeof(uint32_t) * iz.size()));
+      PA_CUDA(cudaMemcpyAsync(d_init_rates, ir.data(), sizeof(double) * ir.size(), cudaMemcpyHostToDevice, stream));
+      PA_CUDA(cudaMemcpyAsync(d_init_z, iz.data(), sizeof(uint32_t) * iz.size(), cudaMemcpyHostToDevice, stream));
+      PA_CUDA(cudaStreamSynchronize(stream));  // the staging vectors go out of scope
+    }
+  }
 
   ChainLaunch L;
   L.blobs = d_blobs;
@@ -194,10 +337,12 @@ int Engine::sample(const int32_t* ids, int32_t n_ids) {
   cp.init_lrate = P.init_lrate; cp.init_lrate2 = (P.hyper_lrate2_a == 0) ? 0.0 : P.init_lrate2; cp.init_grate = P.init_grate;
   cp.cub = P.cub; cp.nlb = P.nlb; cp.log_constomis = std::log(P.constomis);
   cp.ropt = P.ropt; cp.num_burn = P.burnin; cp.num_mcmc = P.mcmc; cp.adaptive_freq = P.adapt_freq;
-  cp.seed = (uint32_t)P.seed;
+  cp.seed = (uint32_t)P.seed + 0x9E3779B9u * (uint32_t)chain_iter;  // outer CHAIN iterations draw from distinct streams
   cp.pad_ = 0;
   L.n_max = n_max; L.slots_max = slots_max; L.T = T; L.ZW = ZW; L.S_rows = model.tree.S;
   L.trace_d = d_trace_d; L.trace_z = d_trace_z;
+  L.init_rates = any_warm ? d_init_rates : nullptr;
+  L.init_z = any_warm ? d_init_z : nullptr;
   L.counters = d_counters;
   counters.kernel_launches = 0;
   // the long chains go first, on the side stream, so that both kernels share the SMs; `stream` joins at the end
@@ -251,6 +396,22 @@ int Engine::fetch_traces() {
   counters.history_draws = hc[3];
   counters.chain_iterations = hc[4];
   for (int k = 0; k < 10; k++) phase_cycles[k] = hc[8 + k];
+  // the last state of every chain becomes the warm start of its next run (Gibbs with UpHyper, bpp_c.cpp:474-485)
+  {
+    const size_t C = plans.size();
+    if (cur_set.size() != C * 3 || cur_z.size() != C * 3 * (size_t)ZW) {
+      cur_set.assign(C * 3, 0);
+      cur_rates.assign(C * 15, 0.0);
+      cur_z.assign(C * 3 * (size_t)ZW, 0u);
+    }
+    for (int ch = 0; ch < n_chains; ch++) {
+      const size_t slot = (size_t)run_ids[chain_elem_pos[ch]] * 3 + chain_model[ch];
+      const double* d = &h_trace_d[(size_t)ch * 6 * T];
+      for (int j = 0; j < 5; j++) cur_rates[slot * 5 + j] = d[(size_t)(j + 1) * T + (T - 1)];
+      for (int w = 0; w < ZW; w++) cur_z[slot * ZW + w] = h_trace_z[((size_t)ch * T + (T - 1)) * ZW + w];
+      cur_set[slot] = 1;
+    }
+  }
   collected = true;
   return PA_OK;
 }
