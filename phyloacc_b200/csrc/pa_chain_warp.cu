@@ -1147,7 +1147,8 @@ WVariant make_wvariant() {
 const WVariant* pick_wvariant(int n_max, int warps) {
   // (max nodes, warps per chain, site rows per warp per history tile, resident CTAs per SM the register budget allows)
   static const WVariant variants[] = {make_wvariant<86, 1, 2, 8>(), make_wvariant<86, 2, 2, 7>(), make_wvariant<86, 4, 2, 4>(), make_wvariant<86, 8, 1, 2>(),
-                                      make_wvariant<160, 1, 2, 4>(), make_wvariant<160, 2, 2, 4>(), make_wvariant<160, 4, 2, 4>(), make_wvariant<160, 8, 1, 2>()};
+                                      make_wvariant<160, 1, 2, 4>(), make_wvariant<160, 2, 2, 4>(), make_wvariant<160, 4, 2, 4>(), make_wvariant<160, 8, 1, 2>(),
+                                      make_wvariant<512, 8, 1, 1>()};  // deep trees (Zoonomia-scale, 2 * 240 - 1 nodes): one CTA per SM
   for (const WVariant& v : variants)
     if (n_max <= v.nmax && warps == v.warps) return &v;
   return nullptr;

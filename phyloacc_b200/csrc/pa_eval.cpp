@@ -247,6 +247,10 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   const char* force = getenv("PA_CHAIN_KERNEL");
   int warps_per_chain = 2;
   if (const char* env = getenv("PA_WARPS_PER_CHAIN")) { const int w = atoi(env); warps_per_chain = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 2; }
+  // trees too large for the 256-thread kernel's shared-memory layouts (temp stack, per-warp pair counters, staged tip
+  // codes) go to the small-CTA kernel, which needs none of them: 8 warps per chain, one CTA per SM
+  const bool wide_fits = (int)chain_smem_bytes(n_max, slots_max, model.tree.S) <= smem_optin;
+  if (!wide_fits) warps_per_chain = 8;
   const bool warp_fits = (int)chain_warp_smem_bytes(n_max, warps_per_chain) <= smem_optin;
   int warp_pmax = 384;
   if (const char* env = getenv("PA_WARP_PMAX")) warp_pmax = atoi(env);
@@ -256,9 +260,9 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     const int Pk = plans[list[2 * k]].P;
     bool to_warp = false;
     if (force && !strcmp(force, "split")) to_warp = warp_fits && Pk <= warp_pmax;
-    if (force && !strcmp(force, "warp")) to_warp = true;
+    if ((force && !strcmp(force, "warp")) || !wide_fits) to_warp = true;
     if (to_warp && !warp_fits) {
-      set_error("PA_CHAIN_KERNEL=warp: tree too large for the warp kernel's shared memory");
+      set_error("tree too large for the chain kernels' shared memory (" + std::to_string(n_max) + " nodes)");
       return PA_ERR_LIMIT;
     }
     if (to_warp) { sel_warp.push_back(k); P_max_warp = std::max(P_max_warp, Pk); }

@@ -92,3 +92,69 @@ def test_chain_is_deterministic_and_seed_dependent(native_lib):
     eng2.close()
     case.close()
     case2.close()
+
+
+def _synthetic_case(tmp, S, C, length, params, tree_seed=9, seed=4, **sim_kw):
+    from phyloacc_b200 import synth
+
+    tree = synth.make_tree(S=S, seed=tree_seed, n_out=max(2, S // 6), n_target=max(2, S // 5))
+    batch = synth.simulate(tree, C=C, length=length, seed=seed, **sim_kw)
+    cfg = synth.write_files(batch, tmp, prefix="syn", params=params)
+    P = fe.load_params(cfg)
+    otree = fe.parse_mod(P.PHYTREE_FILE)
+    names, X = fe.load_fasta(P.ALIGN_FILE)
+    _, pos = fe.load_bed(P.SEG_FILE)
+    starts, lens = fe.element_layout(pos)
+    model = fe.build_model(otree, P)
+    X = fe.reorder_alignment(otree, names, X)
+    return cfg, P, otree, model, X, starts, lens
+
+
+def _compare_with_oracle(eng, P, model, X, starts, lens, ids, tol=1e-9):
+    res = eng.run(ids)
+    n = 0
+    for i, c in enumerate(ids):
+        el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
+        assert bool(res.filtered[i]) == el.filter
+        if el.filter:
+            continue
+        h = coracle.ElementHandle(model, el, fe.compress_patterns(el.masks).site_order)
+        for mdl in (pab.M0, pab.M1, pab.M2):
+            otr = h.chain(pab.MODEL_RESZ[mdl], P.SEED, c * 4 + mdl)
+            tr = eng.trace(i, mdl)
+            assert (tr["Z"] == otr["Z"]).all(), (c, mdl, np.argwhere(tr["Z"] != otr["Z"])[:5])
+            for k in ("loglik", "n_rate", "c_rate", "g_rate", "l_rate", "l2_rate"):
+                assert np.all(np.abs(tr[k] - otr[k]) <= tol * np.maximum(1e-300, np.abs(otr[k]))), (c, mdl, k)
+            n += 1
+    return n
+
+
+def test_deep_tree_240_taxa_matches_oracle(native_lib, oracle_lib, tmp_path):
+    """BASELINE config 3 shape (Zoonomia-like, 240 species = 479 nodes): beyond the 256-thread kernel's shared-memory
+    layouts, served by the small-CTA kernel (8 warps per chain, one CTA per SM); rescaling by 2^256 is exercised."""
+    cfg, P, otree, model, X, starts, lens = _synthetic_case(str(tmp_path), S=240, C=3, length=90, gap_frac=0.02, missing_frac=0.02,
+                                                            params=dict(BURNIN=4, MCMC=10, CHAIN=1, ADAPT_FREQ=5, SEED=6))
+    eng = pab.Engine.from_config(cfg, device=0)
+    assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2]) >= 6
+    # replayed likelihood of the initial state on the deep tree
+    el = fe.element_frontend(model, X, int(starts[0]), int(lens[0]))
+    Z = -np.ones(otree.N, dtype=np.int8)
+    Z[el.nodes] = 1
+    Z[el.root] = 0
+    want, _ = coracle.ElementHandle(model, el).loglik(1, Z, 1.0, 0.5)
+    got = eng.loglik_replay([0], Z[None], [1.0], [0.5])[0]
+    assert abs(got - want) <= 1e-10 * abs(want)
+    eng.close()
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_small_cta_kernel_matches_oracle(warps, native_lib, oracle_lib, tmp_path, monkeypatch):
+    """The opt-in small-CTA kernel (pa_chain_warp.cu) follows the same draw schedule: every warps-per-chain layout gives the
+    oracle's chains on a 43-taxon case with ambiguity codes, gaps and missing species."""
+    monkeypatch.setenv("PA_CHAIN_KERNEL", "warp")
+    monkeypatch.setenv("PA_WARPS_PER_CHAIN", str(warps))
+    cfg, P, otree, model, X, starts, lens = _synthetic_case(str(tmp_path), S=43, C=4, length=150, gap_frac=0.03, missing_frac=0.08, ambig_frac=0.01,
+                                                            params=dict(BURNIN=10, MCMC=30, CHAIN=1, ADAPT_FREQ=10, SEED=8), tree_seed=43)
+    eng = pab.Engine.from_config(cfg, device=0)
+    assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2, 3]) >= 6
+    eng.close()
