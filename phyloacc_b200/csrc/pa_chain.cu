@@ -247,9 +247,15 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
   return block_sum(acc, S.red, tid, kBD);
 }
 
+// scalar helpers that run on a few lanes once per iteration: one out-of-line copy each keeps the iteration loop small
+__device__ __noinline__ double sched_gamma_ol(uint32_t seed, uint32_t key, uint32_t idx, uint32_t sub0, uint32_t iter, uint32_t stream, double a, double b) {
+  return sched_gamma(seed, key, idx, sub0, iter, stream, a, b);
+}
+__device__ __noinline__ double log_gamma_pdf_ol(double x, double a, double b) { return log_gamma_pdf(x, a, b); }
+
 // log-space serial Z update, a literal restatement of Update_Z_subtree; used only when the scaled linear pass degenerates
 template <class SM>
-__device__ void z_update_logspace(SM& S, int n) {
+__device__ __noinline__ void z_update_logspace(SM& S, int n) {
   double lt[2][9];
   for (int f = 0; f < 2; f++)
     for (int k = 0; k < 9; k++) lt[f][k] = log(S.T[f * 9 + k]);
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
             }
           }
           const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
+          uint32_t amb = 0u, xpk = 0u;  // ambiguity-coded tip children met in this group (bit 2j + child), sampled bases (2 bit per node)
 #pragma unroll
           for (int j = 3; j >= 0; j--) {
             const int q = 4 * G + j;
@@ -539,6 +546,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
               x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
               xs[q * kBD] = (uint8_t)x;
             }
+            xpk |= (uint32_t)x << (2 * j);
             if (!isroot) warp_count16((uint32_t)(xp * 4 + x), active, c8 + s * 16, lane, lm0, lm1, lm2, lm3);
             // tip children of this node: the tip's base is data, the parent's base was just drawn
             const uint2 tc = S.ht[q];
@@ -551,14 +559,26 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
               const bool onehot = (code4 & (code4 - 1)) == 0;  // code4 is never 0
               const bool act = code4 != 15u && onehot;
               warp_count16((uint32_t)(x * 4 + (__ffs(code4) - 1)), act, c8 + ti * 16, lane, lm0, lm1, lm2, lm3);
-              if (code4 != 15u && !onehot) {  // ambiguity code: log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
-                for (int kk = 0; kk < 3; kk++) {
-                  const double* lp = logP + ((size_t)kk * L.n_max + ti) * 16 + x * 4;
-                  double sum = 0;
-                  for (int b = 0; b < 4; b++)
-                    if ((code4 >> b) & 1u) sum += exp(lp[b]);
-                  atomicAdd(&S.eamb[ti * 3 + kk], log(sum));
-                }
+              if (code4 != 15u && !onehot) amb |= 1u << (2 * j + cc);
+            }
+          }
+          if (amb) {  // ambiguity codes (rare, one copy of the code): log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
+#pragma unroll 1
+            for (int e = 0; e < 8; e++) {
+              if (!((amb >> e) & 1u)) continue;
+              const int q = 4 * G + (e >> 1);
+              const uint2 tc = S.ht[q];
+              const uint32_t td = (e & 1) ? tc.y : tc.x;
+              const int ti = td & 0xffff;
+              const uint32_t code4 = ((uint32_t)cpat[(td >> 16) * kCodeRow] >> csh) & 15u;
+              const int x = (xpk >> (2 * (e >> 1))) & 3;
+#pragma unroll 1
+              for (int kk = 0; kk < 3; kk++) {
+                const double* lp = logP + ((size_t)kk * L.n_max + ti) * 16 + x * 4;
+                double sum = 0;
+                for (int b = 0; b < 4; b++)
+                  if ((code4 >> b) & 1u) sum += exp(lp[b]);
+                atomicAdd(&S.eamb[ti * 3 + kk], log(sum));
               }
             }
           }
@@ -727,7 +747,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
           if (lane == 0) {
             if (!has) {  // no branch in this class: draw from the prior (bpp_c.cpp:940-964)
               if (resZ != 0) {
-                cur_r = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, prior_a, prior_b);
+                cur_r = sched_gamma_ol(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, prior_a, prior_b);
                 if (neut) {
                   if (cp.ropt == 1 && cur_r < cp.nlb) cur_r = old_rate;
                   else if (cp.ropt == 2 && cur_r < S.scal[SC_C]) cur_r = old_rate;
@@ -740,7 +760,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
               r = u01(philox4(cp.seed, key, which, 0u, (uint32_t)m, PA_ST_RATE).x);
               valid = 1;
               if (neut) {
-                proposal = sched_gamma(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, old_rate / S.scal[SC_PROPN], S.scal[SC_PROPN]);
+                proposal = sched_gamma_ol(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, old_rate / S.scal[SC_PROPN], S.scal[SC_PROPN]);
                 if (cp.ropt == 1 && proposal < cp.nlb) valid = 0;
                 else if (cp.ropt == 2 && proposal < S.scal[SC_C]) valid = 0;
               } else {
@@ -762,7 +782,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
             if (lane == 1) { x = old_rate; sgn = -1.0; }                             // lane 1: - log pdf(current  | prior)
             if (lane == 2) { x = old_rate; a = proposal / pn; b = pn; }               // lane 2: + log q(current | proposal)   (n only)
             if (lane == 3) { x = proposal; a = old_rate / pn; b = pn; sgn = -1.0; }  // lane 3: - log q(proposal | current)  (n only)
-            if (lane < 2 || (neut && lane < 4)) term = sgn * log_gamma_pdf(x, a, b);
+            if (lane < 2 || (neut && lane < 4)) term = sgn * log_gamma_pdf_ol(x, a, b);
             else if (!neut && lane == 2) term = log(old_rate) - log(proposal);
           }
           const double t1 = __shfl_sync(0xffffffffu, term, 1), t2 = __shfl_sync(0xffffffffu, term, 2), t3 = __shfl_sync(0xffffffffu, term, 3);
@@ -881,7 +901,7 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
         else if (whichb == 2) { a = cp.prior_l2_a + nF[1 * 3 + 2]; b = cp.prior_l2_b + nF[2 * 3 + 2]; }
         double x = 0.0;
         if (lane < 6 && !(whichb == 2 && cp.prior_l2_a == 0))
-          x = sched_gamma(cp.seed, key, (uint32_t)whichb, (lane & 1) ? 4096u : 0u, (uint32_t)m, PA_ST_TRANS, (lane & 1) ? b : a, 1.0);
+          x = sched_gamma_ol(cp.seed, key, (uint32_t)whichb, (lane & 1) ? 4096u : 0u, (uint32_t)m, PA_ST_TRANS, (lane & 1) ? b : a, 1.0);
         const double y = __shfl_down_sync(0xffffffffu, x, 1);
         if (lane == 0) S.scal[SC_G] = x / (x + y);
         if (lane == 2) S.scal[SC_L] = x / (x + y);
