@@ -35,6 +35,7 @@ constexpr int kBD = 256;
 constexpr int kNW = kBD / 32;
 constexpr int kTile = 256;       // patterns / sites per tile
 constexpr int kCodeRow = 132;    // staged bytes per tip row: 264 patterns
+constexpr int kXS = kBD + 4;     // bytes per row of sampled bases: 65 words, so that rows of different nodes fall into different banks
 
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R, SC_COUNT = 16 };
 enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_COUNT = 16 };
@@ -55,9 +56,9 @@ struct SmemT {
       alignas(16) double stack[SLOTS * 4 * kBD];
       int16_t stack_sc[SLOTS * kBD];
     };
-    struct {  // history sampling: per-warp tile counts, sampled bases [internal node][site]
-      uint8_t cnt8[kNW * NMAX * 16];
-      uint8_t xs8[NI * kBD];
+    struct {  // history sampling: sampled bases [internal node][site] (4 = no draw), pattern offsets of the tile's sites
+      alignas(4) uint8_t xs8[NI * kXS];
+      uint16_t spat[kTile];
     };
   };
   double red[34];
@@ -67,7 +68,7 @@ struct SmemT {
   double pi[4];
   alignas(16) uint4 ops[NI];  // pruning program, see init
   alignas(8) uint2 hs[NI];    // history descriptor of internal node q: {node | parent's q << 16 (0xffff root), unused}
-  alignas(8) uint2 ht[NI];    // its non-missing tip children: {node | tip row << 16} each, 0xffffffff = none
+  uint32_t cb[NMAX];          // pair-count descriptor of the branch above node i: child (tip row | internal q) | parent q << 16 | tip << 31
   int ivars[IV_COUNT];
   int nz[18];
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
@@ -293,16 +294,6 @@ __device__ __noinline__ void z_update_logspace(SM& S, int n) {
   }
 }
 
-// counts of (parent base, child base) pairs over the 32 sites of a warp, written to the warp's tile-count row;
-// m0..m3 are per-lane masks: m_i = (lane bit i set) ? 0 : ~0, so that (b_i ^ m_i) selects lanes whose code bit i equals the lane's
-__device__ __forceinline__ void warp_count16(uint32_t code, bool act, uint8_t* __restrict__ row, int lane, uint32_t m0, uint32_t m1, uint32_t m2,
-                                             uint32_t m3) {
-  const uint32_t bv = __ballot_sync(0xffffffffu, act);
-  const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, code & 2u);
-  const uint32_t b2 = __ballot_sync(0xffffffffu, code & 4u), b3 = __ballot_sync(0xffffffffu, code & 8u);
-  if (lane < 16) row[lane] = (uint8_t)__popc(bv & (b0 ^ m0) & (b1 ^ m1) & (b2 ^ m2) & (b3 ^ m3));
-}
-
 template <int NMAX, int SLOTS>
 __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -312,8 +303,6 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
   const ChainParams& cp = L.cp;
   const SubstDev& sd = L.sd;
   if (tid < 4) S.pi[tid] = sd.pi[tid];
-  const uint32_t lm0 = (lane & 1) ? 0u : 0xffffffffu, lm1 = (lane & 2) ? 0u : 0xffffffffu, lm2 = (lane & 4) ? 0u : 0xffffffffu,
-                 lm3 = (lane & 8) ? 0u : 0xffffffffu;
 
   // this CTA's arena: log P tables [3][n_max][16] f64, partials [2][n_max][P_max][4] f64, scale counts [2][n_max][P_max] i16
   unsigned char* arena = L.arena + (size_t)blockIdx.x * L.arena_stride;
@@ -373,6 +362,16 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       S.dirty[i] = 0;
       S.sel[i] = 0;
     }
+    // pair-count descriptors: the branch above node i joins the sampled base of its parent with the node's own sampled
+    // base (internal node) or its data (tip)
+    for (int i = tid; i < n; i += kBD) {
+      const uint8_t f = ev.flags[i];
+      const int par = ev.parent[i];
+      uint32_t d = 0xffffffffu;
+      if (par >= 0 && !(f & PA_F_MISSING))
+        d = ((f & PA_F_TIP) ? (0x80000000u | (uint32_t)ev.tiprow[i]) : (uint32_t)ev.intidx[i]) | ((uint32_t)ev.intidx[par] << 16);
+      S.cb[i] = d;
+    }
     for (int i = tid; i <= h->n_up; i += kBD) S.up_off[i] = ev.up_off[i];
     for (int i = tid; i <= h->n_down; i += kBD) S.down_off[i] = ev.down_off[i];
     // pruning program: one packed descriptor per computed internal node, in the element's pruning order:
@@ -401,11 +400,6 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       const int sq = ev.intlist[k];
       const int par = ev.parent[sq];
       S.hs[k] = make_uint2((uint32_t)sq | ((par >= 0 ? (uint32_t)ev.intidx[par] : 0xffffu) << 16), 0u);
-      uint2 t2 = make_uint2(0xffffffffu, 0xffffffffu);
-      const int c0 = ev.child[2 * sq], c1 = ev.child[2 * sq + 1];
-      if (kind_of(c0) == 1u) t2.x = (uint32_t)c0 | ((uint32_t)ev.tiprow[c0] << 16);
-      if (kind_of(c1) == 1u) t2.y = (uint32_t)c1 | ((uint32_t)ev.tiprow[c1] << 16);
-      S.ht[k] = t2;
     }
     if (tid == 0) {
       int nsu = 0;
@@ -494,10 +488,8 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
         if (h->W >= 1) gw0 = ev.gap[pat];
         if (h->W >= 2) gw1 = ev.gap[Ppad + pat];
         const double* gp = A.part + (uint32_t)pat * 4u;
-        const uint8_t* cpat = S.codes + ((pat - pb) >> 1);
-        const int csh = (pat & 1) * 4;
+        S.spat[tid] = (uint16_t)(pat - pb);
         uint8_t* xs = S.xs8 + tid;
-        uint8_t* c8 = S.cnt8 + warp * (n * 16);
         for (int G = (ni - 1) >> 2; G >= 0; G--) {
           // the partials of the group's nodes do not depend on the draws: fetch them first (one L2 round trip per 4 nodes)
           double2 pa[4], pc[4];
@@ -514,7 +506,6 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
             }
           }
           const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
-          uint32_t amb = 0u, xpk = 0u;  // ambiguity-coded tip children met in this group (bit 2j + child), sampled bases (2 bit per node)
 #pragma unroll
           for (int j = 3; j >= 0; j--) {
             const int q = 4 * G + j;
@@ -529,9 +520,9 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
             else if (q < 64) gapbit = (gw1 >> (q - 32)) & 1u;
             else gapbit = (ev.gap[(size_t)(q >> 5) * Ppad + pat] >> (q & 31)) & 1u;
             const bool active = valid && (isroot || !gapbit);
-            const int xp = isroot ? 0 : (int)xs[qp * kBD];
-            int x = 0;
+            int x = 4;  // no draw: the node is "all-gap" at this site (bpp_c.cpp:686-690), or the lane has no site
             if (active) {
+              const int xp = isroot ? 0 : (int)xs[qp * kXS];
               const double u = u01(j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w)));
               double p0, p1, p2, p3;
               if (isroot) {
@@ -544,52 +535,72 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
               // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
               const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
               x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
-              xs[q * kBD] = (uint8_t)x;
             }
-            xpk |= (uint32_t)x << (2 * j);
-            if (!isroot) warp_count16((uint32_t)(xp * 4 + x), active, c8 + s * 16, lane, lm0, lm1, lm2, lm3);
-            // tip children of this node: the tip's base is data, the parent's base was just drawn
-            const uint2 tc = S.ht[q];
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-              const uint32_t td = cc ? tc.y : tc.x;
-              if (td == 0xffffffffu) continue;
-              const int ti = td & 0xffff;
-              const uint32_t code4 = valid ? (((uint32_t)cpat[(td >> 16) * kCodeRow] >> csh) & 15u) : 15u;
-              const bool onehot = (code4 & (code4 - 1)) == 0;  // code4 is never 0
-              const bool act = code4 != 15u && onehot;
-              warp_count16((uint32_t)(x * 4 + (__ffs(code4) - 1)), act, c8 + ti * 16, lane, lm0, lm1, lm2, lm3);
-              if (code4 != 15u && !onehot) amb |= 1u << (2 * j + cc);
-            }
-          }
-          if (amb) {  // ambiguity codes (rare, one copy of the code): log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
-#pragma unroll 1
-            for (int e = 0; e < 8; e++) {
-              if (!((amb >> e) & 1u)) continue;
-              const int q = 4 * G + (e >> 1);
-              const uint2 tc = S.ht[q];
-              const uint32_t td = (e & 1) ? tc.y : tc.x;
-              const int ti = td & 0xffff;
-              const uint32_t code4 = ((uint32_t)cpat[(td >> 16) * kCodeRow] >> csh) & 15u;
-              const int x = (xpk >> (2 * (e >> 1))) & 3;
-#pragma unroll 1
-              for (int kk = 0; kk < 3; kk++) {
-                const double* lp = logP + ((size_t)kk * L.n_max + ti) * 16 + x * 4;
-                double sum = 0;
-                for (int b = 0; b < 4; b++)
-                  if ((code4 >> b) & 1u) sum += exp(lp[b]);
-                atomicAdd(&S.eamb[ti * 3 + kk], log(sum));
-              }
-            }
+            xs[q * kXS] = (uint8_t)x;
           }
         }
         __syncthreads();
-        for (int idx = tid; idx < (n - 1) * 16; idx += kBD) {  // merge the per-warp tile counts
-          if (!(S.flags[idx >> 4] & PA_F_MISSING)) {
-            uint32_t sum = 0;
+        // ---- parent->child base pairs of every branch over the tile's sites (getEmission's sufficient statistic,
+        // bpp_c2.cpp:355-390): thread = (branch, slice of the sites); 16 bins in 8-bit fields of four registers
+        {
+          const int tile_sites = min(kTile, GG - g0);
+          const int nb = n - 1;
+          const int K = max(1, kBD / nb);                               // site slices per branch
+          const int sub = min(128, (((tile_sites + K - 1) / K) + 3) & ~3);  // sites per slice: multiple of 4, <= 128 (8-bit fields)
+          if (tid < nb * K) {
+            const int i = tid % nb, k = tid / nb;
+            const uint32_t d = S.cb[i];
+            if (d != 0xffffffffu) {
+              const uint8_t* __restrict__ prow = S.xs8 + ((d >> 16) & 0x7fffu) * kXS;
+              const bool tip = (d >> 31) != 0;
+              const uint8_t* __restrict__ crow = tip ? (S.codes + (d & 0xffffu) * kCodeRow) : (S.xs8 + (d & 0xffffu) * kXS);
+              for (int s0 = k * sub; s0 < tile_sites; s0 += K * sub) {
+                const int s1 = min(s0 + sub, tile_sites);
+                uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+                for (int t = s0; t < s1; t += 4) {
+                  const uint32_t pw = *reinterpret_cast<const uint32_t*>(prow + t);
+                  uint32_t cw = 0u;
+                  if (!tip) cw = *reinterpret_cast<const uint32_t*>(crow + t);
 #pragma unroll
-            for (int w = 0; w < kNW; w++) sum += S.cnt8[w * (n * 16) + idx];
-            S.cnt[idx] += sum;
+                  for (int e = 0; e < 4; e++) {
+                    if (t + e >= s1) break;
+                    const uint32_t xp = (pw >> (8 * e)) & 0xffu;
+                    uint32_t xc;
+                    if (tip) {
+                      const uint32_t po = S.spat[t + e];
+                      const uint32_t code4 = ((uint32_t)crow[po >> 1] >> ((po & 1u) * 4u)) & 15u;
+                      if (code4 == 15u) continue;
+                      if (code4 & (code4 - 1u)) {  // ambiguity code (rare): log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
+#pragma unroll 1
+                        for (int kk = 0; kk < 3; kk++) {
+                          const double* lp = logP + ((size_t)kk * L.n_max + i) * 16 + xp * 4;
+                          double sum = 0;
+                          for (int b = 0; b < 4; b++)
+                            if ((code4 >> b) & 1u) sum += exp(lp[b]);
+                          atomicAdd(&S.eamb[i * 3 + kk], log(sum));
+                        }
+                        continue;
+                      }
+                      xc = (uint32_t)__ffs(code4) - 1u;
+                    } else {
+                      xc = (cw >> (8 * e)) & 0xffu;
+                      if (xc >= 4u) continue;
+                    }
+                    const uint32_t bin = xp * 4u + xc, inc = 1u << (8u * (bin & 3u)), w = bin >> 2;
+                    c0 += (w == 0u) ? inc : 0u;
+                    c1 += (w == 1u) ? inc : 0u;
+                    c2 += (w == 2u) ? inc : 0u;
+                    c3 += (w == 3u) ? inc : 0u;
+                  }
+                }
+#pragma unroll
+                for (int b = 0; b < 16; b++) {
+                  const uint32_t cw4 = (b < 4) ? c0 : ((b < 8) ? c1 : ((b < 12) ? c2 : c3));
+                  const uint32_t c = (cw4 >> (8 * (b & 3))) & 0xffu;
+                  if (c) atomicAdd(&S.cnt[i * 16 + b], c);
+                }
+              }
+            }
           }
         }
         __syncthreads();
