@@ -38,7 +38,7 @@ constexpr int kCodeRow = 132;    // staged bytes per tip row: 264 patterns
 constexpr int kXS = kBD + 4;     // bytes per row of sampled bases: 65 words, so that rows of different nodes fall into different banks
 
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R, SC_COUNT = 16 };
-enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_COUNT = 16 };
+enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_COUNT = 16 };
 
 template <int NMAX, int SLOTS>
 struct SmemT {
@@ -67,6 +67,8 @@ struct SmemT {
   double T[18];   // linear Z transition matrices [free, fixZ==1][child state a][parent state j]
   double pi[4];
   alignas(16) uint4 ops[NI];  // pruning program, see init
+  alignas(16) uint4 act[NI];  // program of the current pass: only the nodes to recompute, operands resolved (build_pass_program)
+  int16_t actk[NI];           // their positions in ops
   alignas(8) uint2 hs[NI];    // history descriptor of internal node q: {node | parent's q << 16 (0xffff root), unused}
   uint32_t cb[NMAX];          // pair-count descriptor of the branch above node i: child (tip row | internal q) | parent q << 16 | tip << 31
   int ivars[IV_COUNT];
@@ -113,14 +115,70 @@ __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb,
   __syncthreads();
 }
 
-// One Felsenstein pass over every pattern of the element (linear space, fp64).  Thread = pattern.  Nodes are visited
-// in the element's pruning order; with USE_DIRTY only flagged nodes are recomputed (their clean children are read
-// from the current arena copy).  Every recomputed node is written to copy sel[s]^wflip.  Returns sum_p w_p log L_p.
-// The result of an op is forwarded in registers when the next op is its parent (descriptor bits 4..6), so the
-// shared-memory stack only holds results that have to wait for a sibling subtree.
+// Program of one pruning pass, built by warp 0: the nodes to recompute (all, or the dirty ones) in the element's pruning
+// order, with every operand resolved once instead of per thread and node.  Descriptor of a node:
+//   x = offset (doubles) of its partial in the arena copy it is written to; the scale count sits at x >> 2
+//   y = kind0 | kind1 << 3 | child0 << 6 | child1 << 16 | park << 26 (stack slot the result is parked in, 63 = none: the
+//       parent is the next node of the pass and takes it from registers)
+//   z, w = payload of child 0 / 1 by kind: 0 missing; 1 tip: byte offset of its row in the staged codes; 2 result of the
+//       previous node (registers); 3 stack: offset (doubles) of its slot; 4 arena: offset (doubles) of its current partial
 template <bool USE_DIRTY, class SM>
-__device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, int wflip, const Arena& A, int n_su, int n_rows,
-                                             int tid) {
+__device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppad, int wflip, int n_su, int lane) {
+  int n_act = 0;
+  for (int k0 = 0; k0 < n_su; k0 += 32) {
+    const int k = k0 + lane;
+    const bool inc = k < n_su && (!USE_DIRTY || S.dirty[S.ops[k].x & 0xffff]);
+    const unsigned bal = __ballot_sync(0xffffffffu, inc);
+    if (inc) S.actk[n_act + __popc(bal & ((1u << lane) - 1u))] = (int16_t)k;
+    n_act += __popc(bal);
+  }
+  __syncwarp();
+  for (int j = lane; j < n_act; j += 32) {
+    const uint4 op = S.ops[S.actk[j]];
+    const int s = op.x & 0xffff;
+    const uint32_t q = op.x >> 16;
+    const int prev_s = (j > 0) ? (int)(S.ops[S.actk[j - 1]].x & 0xffff) : -1;
+    const int next_s = (j + 1 < n_act) ? (int)(S.ops[S.actk[j + 1]].x & 0xffff) : -2;
+    uint4 d;
+    d.x = (uint32_t)(S.sel[s] ^ wflip) * A.part_stride + q * (uint32_t)Ppad * 4u;
+    const uint32_t park = (j + 1 == n_act || next_s == (int)S.parent[s]) ? 63u : ((op.z >> 8) & 0xffu);
+    uint32_t kinds[2], pay[2];
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+      const uint32_t kind = (op.z >> (2 * cc)) & 3u;
+      const uint32_t ch = cc ? (op.y >> 16) : (op.y & 0xffff);
+      const uint32_t xi = cc ? (op.w >> 16) : (op.w & 0xffff);
+      kinds[cc] = 0u;
+      pay[cc] = 0u;
+      if (kind == 1u) {
+        kinds[cc] = 1u;
+        pay[cc] = xi * kCodeRow;
+      } else if (kind == 2u) {
+        const bool dch = !USE_DIRTY || S.dirty[ch];
+        if (dch && (int)ch == prev_s) kinds[cc] = 2u;
+        else if (dch) {
+          kinds[cc] = 3u;
+          pay[cc] = ((op.z >> (16 + 8 * cc)) & 0xffu) * 4u * kBD;
+        } else {
+          kinds[cc] = 4u;
+          pay[cc] = (uint32_t)S.sel[ch] * A.part_stride + xi * (uint32_t)Ppad * 4u;
+        }
+      }
+    }
+    d.y = kinds[0] | (kinds[1] << 3) | ((op.y & 0xffffu) << 6) | ((op.y >> 16) << 16) | (park << 26);
+    d.z = pay[0];
+    d.w = pay[1];
+    S.act[j] = d;
+  }
+  return n_act;
+}
+
+// One Felsenstein pass over every pattern of the element (linear space, fp64) through the program in S.act.
+// Thread = pattern.  Every recomputed node is written to the arena copy its descriptor names; the result of a node is
+// forwarded in registers when the next node of the pass is its parent, so the shared-memory stack only holds results
+// that wait for a sibling subtree.  Returns sum_p w_p log L_p.
+template <class SM>
+__device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, const Arena& A, int n_act, int n_rows, int tid) {
   const int P = ev.h->P, Ppad = ev.h->Ppad;
   double acc = 0.0;
   for (int p0 = 0; p0 < Ppad; p0 += kTile) {
@@ -129,56 +187,45 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
     if (p < P) {
       const uint8_t* __restrict__ cp = S.codes + (tid >> 1);
       const int sh = (p & 1) * 4;
+      const double* __restrict__ gpart = A.part + (uint32_t)p * 4u;
+      const int16_t* __restrict__ gsc = A.sc + p;
       double o0 = 1.0, o1 = 1.0, o2 = 1.0, o3 = 1.0;
       int sc = 0;
-      uint4 nxt = S.ops[0];
-      for (int k = 0; k < n_su; k++) {
+      uint4 nxt = S.act[0];
+      for (int k = 0; k < n_act; k++) {
         const uint4 op = nxt;
-        if (k + 1 < n_su) nxt = S.ops[k + 1];  // next descriptor is in flight while this node is computed
-        const int s = op.x & 0xffff;
-        if (USE_DIRTY && !S.dirty[s]) continue;
-        const int k0 = op.z & 3, k1 = (op.z >> 2) & 3;
-        const int ch0 = op.y & 0xffff, ch1 = op.y >> 16;
-        const int x0 = op.w & 0xffff, x1 = op.w >> 16;
+        if (k + 1 < n_act) nxt = S.act[k + 1];  // next descriptor is in flight while this node is computed
+        const uint32_t k0 = op.y & 7u, k1 = (op.y >> 3) & 7u;
+        const uint32_t ch0 = (op.y >> 6) & 0x3ffu, ch1 = (op.y >> 16) & 0x3ffu;
         // ---- gather: partials of internal children (registers / stack / arena), codes of tip children
         double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0, b0 = 1.0, b1 = 1.0, b2 = 1.0, b3 = 1.0;
         int sc0 = 0, sc1 = 0;
         uint32_t code0 = 15u, code1 = 15u;
-        if (k0 == 2) {
-          const bool dch = !USE_DIRTY || S.dirty[ch0];
-          if (dch && (op.z & 16u)) { a0 = o0; a1 = o1; a2 = o2; a3 = o3; sc0 = sc; }
-          else if (dch) {
-            const int sl = (op.z >> 16) & 0xff;
-            const double* st = S.stack + sl * 4 * kBD + tid;
-            a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];
-            sc0 = S.stack_sc[sl * kBD + tid];
-          } else {
-            const uint32_t a = S.sel[ch0];
-            const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x0 * Ppad + p) * 4u));
-            const double2 u = g2[0], v = g2[1];
-            a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;
-            sc0 = A.sc[a * A.sc_stride + (uint32_t)x0 * Ppad + p];
-          }
-        } else if (k0 == 1) code0 = ((uint32_t)cp[x0 * kCodeRow] >> sh) & 15u;
-        if (k1 == 2) {
-          const bool dch = !USE_DIRTY || S.dirty[ch1];
-          if (dch && (op.z & 32u)) { b0 = o0; b1 = o1; b2 = o2; b3 = o3; sc1 = sc; }
-          else if (dch) {
-            const int sl = (op.z >> 24) & 0xff;
-            const double* st = S.stack + sl * 4 * kBD + tid;
-            b0 = st[0]; b1 = st[kBD]; b2 = st[2 * kBD]; b3 = st[3 * kBD];
-            sc1 = S.stack_sc[sl * kBD + tid];
-          } else {
-            const uint32_t a = S.sel[ch1];
-            const double2* g2 = reinterpret_cast<const double2*>(A.part + (a * A.part_stride + ((uint32_t)x1 * Ppad + p) * 4u));
-            const double2 u = g2[0], v = g2[1];
-            b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
-            sc1 = A.sc[a * A.sc_stride + (uint32_t)x1 * Ppad + p];
-          }
-        } else if (k1 == 1) code1 = ((uint32_t)cp[x1 * kCodeRow] >> sh) & 15u;
+        if (k0 == 2u) { a0 = o0; a1 = o1; a2 = o2; a3 = o3; sc0 = sc; }
+        else if (k0 == 3u) {
+          const double* st = S.stack + op.z + tid;
+          a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];
+          sc0 = S.stack_sc[(op.z >> 2) + tid];
+        } else if (k0 == 4u) {
+          const double2* g2 = reinterpret_cast<const double2*>(gpart + op.z);
+          const double2 u = g2[0], v = g2[1];
+          a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;
+          sc0 = gsc[op.z >> 2];
+        } else if (k0 == 1u) code0 = ((uint32_t)cp[op.z] >> sh) & 15u;
+        if (k1 == 2u) { b0 = o0; b1 = o1; b2 = o2; b3 = o3; sc1 = sc; }
+        else if (k1 == 3u) {
+          const double* st = S.stack + op.w + tid;
+          b0 = st[0]; b1 = st[kBD]; b2 = st[2 * kBD]; b3 = st[3 * kBD];
+          sc1 = S.stack_sc[(op.w >> 2) + tid];
+        } else if (k1 == 4u) {
+          const double2* g2 = reinterpret_cast<const double2*>(gpart + op.w);
+          const double2 u = g2[0], v = g2[1];
+          b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
+          sc1 = gsc[op.w >> 2];
+        } else if (k1 == 1u) code1 = ((uint32_t)cp[op.w] >> sh) & 15u;
         // ---- messages: m_j = sum_i P_child(j -> i) L_child(i); tips select / add columns; gaps and missing children give 1
         double m0 = 1.0, m1 = 1.0, m2 = 1.0, m3 = 1.0, n0 = 1.0, n1 = 1.0, n2 = 1.0, n3 = 1.0;
-        if (k0 == 2) {
+        if (k0 >= 2u) {
           const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch0 * 16);
           const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
           m0 = ((r00.x * a0 + r00.y * a1) + r01.x * a2) + r01.y * a3;
@@ -198,7 +245,7 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
             m3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];
           }
         }
-        if (k1 == 2) {
+        if (k1 >= 2u) {
           const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch1 * 16);
           const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
           n0 = ((r00.x * b0 + r00.y * b1) + r01.x * b2) + r01.y * b3;
@@ -227,18 +274,16 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
           o0 *= PA_SCALE_UP; o1 *= PA_SCALE_UP; o2 *= PA_SCALE_UP; o3 *= PA_SCALE_UP;
           sc += 1;
         }
-        if (!(op.z & 64u)) {  // the parent is not the next op: park the result on the stack
-          const int sl = (op.z >> 8) & 0xff;
-          double* st = S.stack + sl * 4 * kBD + tid;
+        const uint32_t park = op.y >> 26;
+        if (park != 63u) {  // the parent is not the next node of the pass: park the result on the stack
+          double* st = S.stack + park * 4 * kBD + tid;
           st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
-          S.stack_sc[sl * kBD + tid] = (int16_t)sc;
+          S.stack_sc[park * kBD + tid] = (int16_t)sc;
         }
-        const uint32_t q = op.x >> 16;
-        const uint32_t a = S.sel[s] ^ wflip;
-        double2* g2 = reinterpret_cast<double2*>(A.part + (a * A.part_stride + (q * Ppad + p) * 4u));
+        double2* g2 = reinterpret_cast<double2*>(const_cast<double*>(gpart) + op.x);
         g2[0] = make_double2(o0, o1);
         g2[1] = make_double2(o2, o3);
-        A.sc[a * A.sc_stride + q * Ppad + p] = (int16_t)sc;
+        const_cast<int16_t*>(gsc)[op.x >> 2] = (int16_t)sc;
       }
       // the last node of the program is the root (or nothing was computed: missing root -> likelihood 1)
       const double lik = ((S.pi[0] * o0 + S.pi[1] * o1) + S.pi[2] * o2) + S.pi[3] * o3;
@@ -246,6 +291,17 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
     }
   }
   return block_sum(acc, S.red, tid, kBD);
+}
+
+// build the program of a pass on warp 0 and publish its length (one barrier)
+template <bool USE_DIRTY, class SM>
+__device__ __forceinline__ int make_pass(SM& S, const Arena& A, int Ppad, int wflip, int n_su, int tid) {
+  if (tid < 32) {
+    const int n_act = build_pass_program<USE_DIRTY>(S, A, Ppad, wflip, n_su, tid);
+    if (tid == 0) S.ivars[IV_NACT] = n_act;
+  }
+  __syncthreads();
+  return S.ivars[IV_NACT];
 }
 
 // scalar helpers that run on a few lanes once per iteration: one out-of-line copy each keeps the iteration loop small
@@ -442,10 +498,11 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
     __syncthreads();
     // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in arena copy 0
     {
-      const double ll = prune_pass<false>(ev, S, S.Pcur, 0, A, n_su, n_rows, tid);
+      const int n_act = make_pass<false>(S, A, Ppad, 0, n_su, tid);
+      const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid);
       if (tid == 0) {
         S.scal[SC_LL] = ll;
-        w_npu += (unsigned long long)n_su * h->P;
+        w_npu += (unsigned long long)n_act * h->P;
         w_root += h->P;
       }
     }
@@ -723,16 +780,12 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       }
       __syncthreads();
       if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431 (recomputed partials overwrite the current copy in place)
-        const double ll = prune_pass<true>(ev, S, S.Pcur, 0, A, n_su, n_rows, tid);
-        if (warp == 0) {  // work counters: lane-parallel, not a serial loop on one thread
-          int cnt_nodes = 0;
-          for (int k = lane; k < n_su; k += 32) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
-          cnt_nodes = __reduce_add_sync(0xffffffffu, cnt_nodes);
-          if (lane == 0) {
-            S.scal[SC_LL] = ll;
-            w_npu += (unsigned long long)cnt_nodes * h->P;
-            w_root += h->P;
-          }
+        const int n_act = make_pass<true>(S, A, Ppad, 0, n_su, tid);
+        const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid);
+        if (tid == 0) {
+          S.scal[SC_LL] = ll;
+          w_npu += (unsigned long long)n_act * h->P;
+          w_root += h->P;
         }
         __syncthreads();
       }
@@ -751,7 +804,13 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
         if (has)
           for (int i = tid; i < n - 1; i += kBD)
             if (!(S.flags[i] & PA_F_MISSING) && S.Z[i] == cls) mark_ancestors(S.parent, S.dirty, i);
-        if (warp == 0) {
+        __syncthreads();
+        if (warp == 1) {  // the program of the proposal's pass is built next to warp 0's scalar work
+          if (has) {
+            const int n_act = build_pass_program<true>(S, A, Ppad, 1, n_su, lane);
+            if (lane == 0) S.ivars[IV_NACT] = n_act;
+          }
+        } else if (warp == 0) {
           // lane 0: proposal (or prior draw); lanes 0..3: the prior / Hastings terms of the MH ratio in parallel
           int valid = 0;
           double cur_r = old_rate, proposal = 0.0, r = 0.0;
@@ -821,13 +880,13 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
           }
           __syncthreads();
           const long long tp0 = clock64();
-          const double ll_new = prune_pass<true>(ev, S, S.Pprop, 1, A, n_su, n_rows, tid);  // log_f_Xz, into the non-current copy
+          const int n_act = S.ivars[IV_NACT];
+          const double ll_new = prune_pass(ev, S, S.Pprop, A, n_act, n_rows, tid);  // log_f_Xz, into the non-current copy
           if (tid == 0 && !neut) ph8 += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
           if (warp == 0) {
-            int cnt_nodes = 0, cnt_cls = 0;  // work counters: lane-parallel, not a serial loop on one thread
-            for (int k = lane; k < n_su; k += 32) cnt_nodes += S.dirty[S.ops[k].x & 0xffff];
+            const int cnt_nodes = n_act;
+            int cnt_cls = 0;  // work counter: lane-parallel, not a serial loop on one thread
             for (int i = lane; i < n - 1; i += 32) cnt_cls += (S.Z[i] == cls);
-            cnt_nodes = __reduce_add_sync(0xffffffffu, cnt_nodes);
             cnt_cls = __reduce_add_sync(0xffffffffu, cnt_cls);
             if (lane == 0) {
               const double MH = (ll_new - S.scal[SC_LL]) + S.scal[SC_MHPART];
