@@ -1,0 +1,182 @@
+"""Host side of the path (b): parsers, filters and the error behaviour of the drop-in binary on edge
+inputs.  No GPU needed: every check stops before (or never reaches) a CUDA call.
+
+Where the reference binary built from the unmodified sources is available (oracle/_ref/PhyloAcc-ST-ref, built by
+`make -C oracle ref`; it travels to the GPU box) the drop-in binary is compared with it directly: same exit code, same
+message.  Front-end results on edge inputs are compared with the oracle front-end (pinned bit-exact against the
+reference on the golden cases, which include trimming, PRUNE_TREE, MIN_LEN and GAP_PROP)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import phyloacc_b200 as pab
+from oracle import frontend as fe, probe
+from phyloacc_b200 import synth
+from tests._util import Case
+
+REF_BIN = probe.REF_BIN if os.path.exists(probe.REF_BIN) else None
+
+
+def _run(binary, *args):
+    r = subprocess.run([binary, *args], capture_output=True, text=True, timeout=300)
+    return r.returncode, r.stdout + r.stderr
+
+
+def _both(*args):
+    """(ours, reference or None)"""
+    ours = _run(pab.BIN_PATH, *args)
+    ref = _run(REF_BIN, *args) if REF_BIN else None
+    return ours, ref
+
+
+def test_no_argument_probe(native_lib):
+    # the driver's presence probe (phyloacc_lib/core.py:47-110) runs the binary with no arguments and wants exit code <= 1
+    (rc, out), ref = _both()
+    assert rc == 1 and "Please specify the path of the parameter file." in out
+    if ref:
+        assert ref[0] == rc and "Please specify the path of the parameter file." in ref[1]
+
+
+def test_unreadable_config(native_lib, tmp_path):
+    (rc, out), ref = _both(str(tmp_path / "nope.cfg"))
+    assert rc == 1 and "Cannot open the parameters file" in out
+    if ref:
+        assert ref[0] == 1 and "Cannot open the parameters file" in ref[1]
+
+
+def test_missing_result_folder(native_lib):
+    case = Case("tiny8")
+    shutil.rmtree(os.path.join(case.dir, "out"))
+    (rc, out), ref = _both(case.cfg)
+    assert rc == 1 and "output path doesn't exist or empty!" in out  # main.cpp:334-338, checked before any data is loaded
+    if ref:
+        assert ref[0] == 1 and "output path doesn't exist or empty!" in ref[1]
+    case.close()
+
+
+@pytest.mark.parametrize("which,msg", [("sim.fa", "Cannot open the phylogenetic profile input file"), ("sim.bed", "Cannot open the segment input file"),
+                                       ("sim.mod", "Cannot open the phylogenetic tree input file")])
+def test_missing_input_files(which, msg, native_lib):
+    case = Case("tiny8")
+    os.remove(os.path.join(case.dir, which))
+    (rc, out), ref = _both(case.cfg)
+    assert rc == 1 and msg in out, out[-500:]  # profile.cpp:26-29, 74-77; newick.cpp:438-442
+    if ref:
+        assert ref[0] == 1 and msg in ref[1]
+    # the C ABI reports the same condition as an error code + message, without exiting the host process
+    with pytest.raises(pab.PhyloAccError) as ei:
+        pab.Engine.from_config(case.cfg, device=-1)
+    assert ei.value.code in (-4, -1) and msg in str(ei.value)
+    case.close()
+
+
+def test_unlabeled_internal_node(native_lib):
+    case = Case("tiny8")
+    mod = os.path.join(case.dir, "sim.mod")
+    text = open(mod).read()
+    # drop the label of the last internal node before the root's closing parenthesis
+    import re
+    tree_line = [l for l in text.split("\n") if l.startswith("TREE:")][0]
+    broken = re.sub(r"\)([A-Za-z_][A-Za-z0-9_]*):", "):", tree_line, count=1)
+    assert broken != tree_line
+    open(mod, "w").write(text.replace(tree_line, broken))
+    (rc, out), ref = _both(case.cfg)
+    assert rc == 1 and "Some nodes in the tree aren't labeled" in out  # newick.cpp:416-419
+    if ref:
+        assert ref[0] == 1 and "Some nodes in the tree aren't labeled" in ref[1]
+    case.close()
+
+
+def test_config_quirks_unknown_keys_comments_blank_lines(native_lib):
+    case = Case("tiny8")
+    body = open(case.cfg).read()
+    open(case.cfg, "w").write("# a comment line\n\n" + body + "\nNOT_A_KEY 12\n\n")
+    eng = pab.Engine.from_config(case.cfg, device=-1)  # unknown keys are reported and skipped (main.cpp:280-283)
+    assert eng.num_elements == case.C
+    p = eng.params()
+    assert p.burnin == case.P.BURNIN and p.mcmc == case.P.MCMC and p.seed == case.P.SEED and p.hyper_lrate2_a == case.P.HYPER_LRATE2_A
+    eng.close()
+    case.close()
+
+
+def test_bed_stops_at_first_short_line(native_lib):
+    # profile.cpp:84: the element list ends at the first line with fewer than three tab-separated fields
+    case = Case("ratite43")
+    bed = os.path.join(case.dir, "sim.bed")
+    lines = open(bed).read().strip().split("\n")
+    keep = 4
+    open(bed, "w").write("\n".join(lines[:keep] + ["truncated"] + lines[keep:]) + "\n")
+    open(os.path.join(case.dir, "sim.id"), "w").write("\n".join(str(i) for i in range(keep)) + "\n")
+    eng = pab.Engine.from_config(case.cfg, device=-1)
+    names, pos = fe.load_bed(bed)
+    assert len(names) == keep and eng.num_elements == keep
+    eng.close()
+    case.close()
+
+
+def _front_end_case(tmp, **kw):
+    tree = synth.make_tree(S=12, seed=3, n_out=2, n_target=3)
+    batch = synth.simulate(tree, C=kw.pop("C", 6), length=kw.pop("length", 80), seed=kw.pop("seed", 5), **kw.pop("sim", {}))
+    cfg = synth.write_files(batch, tmp, prefix="edge", params=kw.pop("params", {}))
+    P = fe.load_params(cfg)
+    otree = fe.parse_mod(P.PHYTREE_FILE)
+    names, X = fe.load_fasta(P.ALIGN_FILE)
+    _, pos = fe.load_bed(P.SEG_FILE)
+    starts, lens = fe.element_layout(pos)
+    model = fe.build_model(otree, P)
+    return cfg, model, fe.reorder_alignment(otree, names, X), starts, lens
+
+
+def _check_frontend(cfg, model, X, starts, lens):
+    eng = pab.Engine.from_config(cfg, device=-1)
+    n_f = 0
+    for c in range(len(starts)):
+        o = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
+        i = eng.element_info(c)
+        assert i["filtered"] == o.filter, c
+        if o.filter:
+            n_f += 1
+            continue
+        pt = fe.compress_patterns(o.masks)
+        assert i["GG"] == o.GG and i["P"] == pt.P and i["root"] == o.root and i["nodes"] == o.nodes
+        assert (i["missing"] == o.missing).all() and (i["pattern_codes"] == pt.codes).all() and (i["pattern_weights"] == pt.weights).all()
+    eng.close()
+    return n_f
+
+
+def test_short_and_gappy_elements_are_filtered_like_the_reference(native_lib, tmp_path):
+    # MIN_LEN filter (bpp_c.hpp:158), column trimming (bpp_c.hpp:268-301), missing-species / conserved filter (bpp_c.hpp:331-373)
+    cfg, model, X, starts, lens = _front_end_case(str(tmp_path), length=70, sim=dict(gap_frac=0.25, missing_frac=0.3, ambig_frac=0.02),
+                                                  params=dict(MIN_LEN=60, TRIM_GAP_PERCENT=0.5, GAP_PROP=0.4, CONSERVE_PROP=0.3))
+    n_f = _check_frontend(cfg, model, X, starts, lens)
+    assert 0 < n_f  # the case really exercises the filters
+
+
+def test_prune_tree_and_gapchar(native_lib, tmp_path):
+    cfg, model, X, starts, lens = _front_end_case(str(tmp_path), length=90, sim=dict(gap_frac=0.1, missing_frac=0.25), params=dict(PRUNE_TREE=1, GAP_PROP=0.5))
+    _check_frontend(cfg, model, X, starts, lens)
+
+
+def test_element_past_the_alignment_end_is_clipped(native_lib, tmp_path):
+    # std::string::substr semantics (bpp_c.hpp:211): an element that runs past the alignment is shortened, not rejected
+    cfg, model, X, starts, lens = _front_end_case(str(tmp_path), C=3, length=100)
+    bed = fe.load_params(cfg).SEG_FILE
+    rows = [l.split("\t") for l in open(bed).read().strip().split("\n")]
+    rows[-1][2] = str(int(rows[-1][2]) + 40)  # the last element claims 40 more columns than the FASTA has
+    open(bed, "w").write("\n".join("\t".join(r) for r in rows) + "\n")
+    eng = pab.Engine.from_config(cfg, device=-1)
+    i = eng.element_info(2)
+    assert not i["filtered"] and i["GG"] == 100
+    eng.close()
+
+
+def test_empty_id_list_and_out_of_range_ids(native_lib, tmp_path):
+    case = Case("tiny8")
+    open(os.path.join(case.dir, "sim.id"), "w").write("")
+    eng = pab.Engine.from_config(case.cfg, device=-1)
+    assert len(eng.ids()) == 0
+    eng.close()
+    case.close()
