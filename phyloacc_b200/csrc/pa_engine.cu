@@ -108,6 +108,11 @@ void Engine::release_device() {
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
   fr((void*&)d_arena_w); fr((void*&)d_sel); fr((void*&)d_init_rates); fr((void*&)d_init_z);
   cap_init_rates = cap_init_z = 0;
+  if (h_trace_d) cudaFreeHost(h_trace_d);
+  if (h_trace_z) cudaFreeHost(h_trace_z);
+  h_trace_d = nullptr;
+  h_trace_z = nullptr;
+  cap_h_trace_d = cap_h_trace_z = 0;
   cap_chain_list = cap_sel = cap_trace_d = cap_trace_z = cap_arena = cap_arena_w = cap_counters = cap_queue = 0;
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
@@ -180,7 +185,12 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
   loaded = true;
   if (device < 0) return PA_OK;
   PA_CUDA(cudaSetDevice(device));
-  release_device();
+  // only the batch itself is replaced; the buffers of a run (arenas, traces, pinned host copies) persist and grow on demand
+  if (d_blobs) cudaFree(d_blobs);
+  if (d_blob_off) cudaFree(d_blob_off);
+  d_blobs = nullptr;
+  d_blob_off = nullptr;
+  sampled = collected = false;
   std::vector<uint8_t> all(total);
   for (int c = 0; c < C; c++)
     if (!plans[c].filtered) {

@@ -57,8 +57,9 @@ struct Engine {
   double* d_init_rates = nullptr;
   uint32_t* d_init_z = nullptr;
   size_t cap_init_rates = 0, cap_init_z = 0;
-  std::vector<double> h_trace_d;
-  std::vector<uint32_t> h_trace_z;
+  double* h_trace_d = nullptr;           // pinned host copies of the traces of the last run (grow-only)
+  uint32_t* h_trace_z = nullptr;
+  size_t cap_h_trace_d = 0, cap_h_trace_z = 0;
   bool sampled = false, collected = false;
   pa_counters counters{};
   unsigned long long phase_cycles[10] = {0};  // SM cycles spent per chain-kernel phase (thread 0 of every CTA, summed)

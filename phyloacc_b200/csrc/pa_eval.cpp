@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -35,6 +36,13 @@ static double gamma_pdf(double x, double a, double b) {  // gsl_ran_gamma_pdf
   if (x == 0) return (a == 1) ? 1 / b : 0;
   if (a == 1) return std::exp(-x / b) / b;
   return std::exp((a - 1) * std::log(x / b) - x / b - std::lgamma(a)) / b;
+}
+// the same density with lgamma(a) supplied by the caller (a is a constant of the run: one lgamma instead of one per iteration)
+static double gamma_pdf_lg(double x, double a, double b, double lga) {
+  if (x < 0) return 0;
+  if (x == 0) return (a == 1) ? 1 / b : 0;
+  if (a == 1) return std::exp(-x / b) / b;
+  return std::exp((a - 1) * std::log(x / b) - x / b - lga) / b;
 }
 static double lnbeta(double a, double b) { return std::lgamma(a) + std::lgamma(b) - std::lgamma(a + b); }
 
@@ -387,11 +395,22 @@ int Engine::fetch_traces() {
     return PA_OK;
   }
   PA_CUDA(cudaSetDevice(device));
-  h_trace_d.resize((size_t)6 * T * n_chains);
-  h_trace_z.resize((size_t)ZW * T * n_chains);
+  // pinned host buffers (grow-only): the trace download runs at PCIe speed instead of through a pageable staging copy
+  auto reserve_host = [&](void*& p, size_t& cap, size_t bytes) -> cudaError_t {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  };
+  const size_t bytes_d = sizeof(double) * 6 * (size_t)T * n_chains, bytes_z = sizeof(uint32_t) * (size_t)ZW * T * n_chains;
+  PA_CUDA(reserve_host((void*&)h_trace_d, cap_h_trace_d, bytes_d));
+  PA_CUDA(reserve_host((void*&)h_trace_z, cap_h_trace_z, bytes_z));
   unsigned long long hc[24];
-  PA_CUDA(cudaMemcpyAsync(h_trace_d.data(), d_trace_d, sizeof(double) * h_trace_d.size(), cudaMemcpyDeviceToHost, stream));
-  PA_CUDA(cudaMemcpyAsync(h_trace_z.data(), d_trace_z, sizeof(uint32_t) * h_trace_z.size(), cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaMemcpyAsync(h_trace_d, d_trace_d, bytes_d, cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaMemcpyAsync(h_trace_z, d_trace_z, bytes_z, cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaMemcpyAsync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaStreamSynchronize(stream));
   counters.node_pattern_updates = hc[0];
@@ -591,8 +610,11 @@ double eval2_fallback_finish(const Engine& eng, int mdl, const Eval2Work& w, con
 }  // namespace
 
 int Engine::collect(pa_results* out) {
+  const bool timing = getenv("PA_TIMING") != nullptr;
+  const double t_start = omp_get_wtime();
   int rc = fetch_traces();
   if (rc != PA_OK) return rc;
+  const double t_fetch = omp_get_wtime();
   const int n_ids = (int)run_ids.size();
   if (out->n < n_ids || out->N != model.tree.N) {
     set_error("pa_results too small for this run");
@@ -609,6 +631,7 @@ int Engine::collect(pa_results* out) {
     if (out->median_rates) for (int k = 0; k < 15; k++) out->median_rates[(size_t)i * 15 + k] = 0;
     if (out->post_Z) for (size_t k = 0; k < (size_t)3 * N * 4; k++) out->post_Z[(size_t)i * 3 * N * 4 + k] = 0;
   }
+  const double lg_ca = std::lgamma(P.conserve_prior_a), lg_na = std::lgamma(P.acce_prior_a);
   std::vector<Eval2Work> works(n_chains);
   std::vector<double> logml(n_chains, 0.0);
   int err = PA_OK;
@@ -629,8 +652,8 @@ int Engine::collect(pa_results* out) {
     int max_m = -1;
     for (int m = 0; m < T; m++) {
       full[m] = tr.loglik[m] + 0.0;
-      full[m] += std::log(gamma_pdf(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b));
-      if (mdl != PA_M0) full[m] += std::log(gamma_pdf(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b));
+      full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
+      if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
       if (m >= num_burn && full[m] > max_ll) {
         max_ll = full[m];
         max_m = m;
@@ -646,8 +669,8 @@ int Engine::collect(pa_results* out) {
     if (out->median_rates) {
       double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
       std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
-      for (int k = 0; k < 5; k++) {
-        std::sort(cols[k]->begin(), cols[k]->end());
+      for (int k = 0; k < 5; k++) {  // the element the reference reads after sorting the whole trace (bpp_c2.cpp:742-760)
+        std::nth_element(cols[k]->begin(), cols[k]->begin() + cols[k]->size() / 2, cols[k]->end());
         md[k] = (*cols[k])[cols[k]->size() / 2];
       }
     }
@@ -663,6 +686,7 @@ int Engine::collect(pa_results* out) {
     }
   }
   if (err != PA_OK) return err;
+  const double t_sum = omp_get_wtime();
   // Eval2 fallback (no configuration carries >= 2% weight with a finite log-det): exact log-likelihood of every
   // configuration at the posterior-mean rates, by the replay kernel, in one batch
   {
@@ -694,6 +718,9 @@ int Engine::collect(pa_results* out) {
   }
   if (out->loglik)
     for (int ch = 0; ch < n_chains; ch++) out->loglik[chain_elem_pos[ch] * 3 + chain_model[ch]] = logml[ch];
+  if (timing)
+    fprintf(stderr, "[pa timing] collect: wait + trace download %.3f s, MonitorChain/Eval2/summaries %.3f s (%d threads), Eval2 fallback %.3f s\n",
+            t_fetch - t_start, t_sum - t_fetch, nt, omp_get_wtime() - t_sum);
   return PA_OK;
 }
 

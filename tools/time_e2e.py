@@ -18,7 +18,7 @@ prm.burnin, prm.mcmc, prm.adapt_freq, prm.seed = bench.BURNIN, bench.MCMC, 500, 
 prm.num_thread = os.cpu_count() or 1
 eng = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup, conserve=tree.conserve, device=0)
 ids = np.arange(batch.C, dtype=np.int32)
-for rep in range(2):
+for rep in range(int(os.environ.get("PA_REPS", "4"))):
     t0 = time.time()
     eng.load_alignment(batch.X, batch.elem_start, batch.elem_len)
     t1 = time.time()
