@@ -76,16 +76,6 @@ struct Engine {
   int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);
 };
 
-// Eval2 + summaries (pa_eval.cpp)
-struct ChainSummary {
-  double logml = 0, loglik_max = 0;
-  std::vector<int8_t> max_Z;
-  double med[5] = {0, 0, 0, 0, 0};
-  std::vector<double> post_Z;  // [N][4]
-  int failure = 0;
-};
-int summarize_chain(Engine& eng, int elem, int mdl, const ChainTraceHost& tr, ChainSummary& out);
-
 }  // namespace pa
 
 // the opaque handle of the C ABI

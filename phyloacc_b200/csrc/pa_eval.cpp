@@ -724,6 +724,4 @@ int Engine::collect(pa_results* out) {
   return PA_OK;
 }
 
-int summarize_chain(Engine&, int, int, const ChainTraceHost&, ChainSummary&) { return PA_ERR_STATE; }
-
 }  // namespace pa
