@@ -37,7 +37,9 @@ constexpr int kTile = 256;       // patterns / sites per tile
 constexpr int kCodeRow = 132;    // staged bytes per tip row: 264 patterns
 constexpr int kXS = kBD + 4;     // bytes per row of sampled bases: 65 words, so that rows of different nodes fall into different banks
 
-enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R, SC_COUNT = 16 };
+enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R,
+       // scalars of the two MH steps, computed ahead of time by the last warp while the others sample histories
+       SC_PRE_R_N = 16, SC_PRE_PROP_N, SC_PRE_PRIOR_N, SC_PRE_MH_N, SC_PRE_R_C, SC_PRE_PROP_C, SC_PRE_PRIOR_C, SC_PRE_MH_C, SC_COUNT = 24 };
 enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_COUNT = 16 };
 
 template <int NMAX, int SLOTS>
@@ -535,6 +537,36 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
       const double cur_n = S.scal[SC_N], cur_c = S.scal[SC_C];
       __syncthreads();
       PA_PHASE(ph1)
+      if (warp == kNW - 1) {
+        // The random draws and the prior / Hastings terms of this iteration's two MH steps depend only on the rates and
+        // proposal scales at the start of the iteration, not on Z: the last warp (idle below 225 sites) evaluates them
+        // now -- same draw-schedule slots, same arithmetic as at the steps -- so that the steps only pick values.
+        const double old_n = S.scal[SC_N], old_c = S.scal[SC_C], pn = S.scal[SC_PROPN], pc = S.scal[SC_PROPC];
+        const double r_n = u01(philox4(cp.seed, key, 0u, 0u, (uint32_t)m, PA_ST_RATE).x);
+        const double r_c = u01(philox4(cp.seed, key, 1u, 0u, (uint32_t)m, PA_ST_RATE).x);
+        double v = 0.0;  // lane 0: n proposal; lane 1: n drawn from its prior; lane 2: c drawn from its prior (bpp_c.cpp:940-964,998)
+        if (resZ != 0 && lane < 3)
+          v = sched_gamma_ol(cp.seed, key, lane == 2 ? 1u : 0u, 1, (uint32_t)m, PA_ST_RATE, lane == 0 ? old_n / pn : (lane == 1 ? cp.nprior_a : cp.cprior_a),
+                             lane == 0 ? pn : (lane == 1 ? cp.nprior_b : cp.cprior_b));
+        const double prop_n = __shfl_sync(0xffffffffu, v, 0), prior_n = __shfl_sync(0xffffffffu, v, 1), prior_c = __shfl_sync(0xffffffffu, v, 2);
+        const double prop_c = old_c * (r_c * (pc - 1 / pc) + 1 / pc);  // bpp_c.cpp:1010-1011
+        double x = prop_n, a = cp.nprior_a, b = cp.nprior_b, sgn = 1.0;                    // lane 0: + log pdf(n proposal | prior)
+        if (lane == 1) { x = old_n; sgn = -1.0; }                                         // lane 1: - log pdf(n current  | prior)
+        if (lane == 2) { x = old_n; a = prop_n / pn; b = pn; }                             // lane 2: + log q(current | proposal)
+        if (lane == 3) { x = prop_n; a = old_n / pn; b = pn; sgn = -1.0; }                // lane 3: - log q(proposal | current)
+        if (lane == 4) { x = prop_c; a = cp.cprior_a; b = cp.cprior_b; }                   // lane 4: + log pdf(c proposal | prior)
+        if (lane == 5) { x = old_c; a = cp.cprior_a; b = cp.cprior_b; sgn = -1.0; }       // lane 5: - log pdf(c current  | prior)
+        double term = 0.0;
+        if (lane >= 4 ? lane < 6 : resZ != 0) term = sgn * log_gamma_pdf_ol(x, a, b);
+        if (lane == 6) term = log(old_c) - log(prop_c);
+        const double t0 = __shfl_sync(0xffffffffu, term, 0), t1 = __shfl_sync(0xffffffffu, term, 1), t2 = __shfl_sync(0xffffffffu, term, 2),
+                     t3 = __shfl_sync(0xffffffffu, term, 3), t4 = __shfl_sync(0xffffffffu, term, 4), t5 = __shfl_sync(0xffffffffu, term, 5),
+                     t6 = __shfl_sync(0xffffffffu, term, 6);
+        if (lane == 0) {
+          S.scal[SC_PRE_R_N] = r_n; S.scal[SC_PRE_PROP_N] = prop_n; S.scal[SC_PRE_PRIOR_N] = prior_n; S.scal[SC_PRE_MH_N] = ((t0 + t1) + t2) + t3;
+          S.scal[SC_PRE_R_C] = r_c; S.scal[SC_PRE_PROP_C] = prop_c; S.scal[SC_PRE_PRIOR_C] = prior_c; S.scal[SC_PRE_MH_C] = ((t4 + t5) + t6) + 0.0;
+        }
+      }
       for (int g0 = 0; g0 < GG; g0 += kTile) {
         const int pb = (int)ev.sitepat[g0] & ~7;  // sites are sorted by pattern: this tile spans < 264 patterns from pb
         ensure_staged(S, ev, pb, n_rows, tid);
@@ -811,13 +843,13 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
             if (lane == 0) S.ivars[IV_NACT] = n_act;
           }
         } else if (warp == 0) {
-          // lane 0: proposal (or prior draw); lanes 0..3: the prior / Hastings terms of the MH ratio in parallel
-          int valid = 0;
-          double cur_r = old_rate, proposal = 0.0, r = 0.0;
+          // the draws and the prior / Hastings terms were evaluated at the start of the iteration (history phase); pick them
           if (lane == 0) {
+            int valid = 0;
+            double cur_r = old_rate, proposal = 0.0, r = 0.0;
             if (!has) {  // no branch in this class: draw from the prior (bpp_c.cpp:940-964)
               if (resZ != 0) {
-                cur_r = sched_gamma_ol(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, prior_a, prior_b);
+                cur_r = neut ? S.scal[SC_PRE_PRIOR_N] : S.scal[SC_PRE_PRIOR_C];
                 if (neut) {
                   if (cp.ropt == 1 && cur_r < cp.nlb) cur_r = old_rate;
                   else if (cp.ropt == 2 && cur_r < S.scal[SC_C]) cur_r = old_rate;
@@ -827,37 +859,19 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
                 }
               }
             } else {
-              r = u01(philox4(cp.seed, key, which, 0u, (uint32_t)m, PA_ST_RATE).x);
+              r = neut ? S.scal[SC_PRE_R_N] : S.scal[SC_PRE_R_C];
               valid = 1;
+              proposal = neut ? S.scal[SC_PRE_PROP_N] : S.scal[SC_PRE_PROP_C];
               if (neut) {
-                proposal = sched_gamma_ol(cp.seed, key, which, 1, (uint32_t)m, PA_ST_RATE, old_rate / S.scal[SC_PROPN], S.scal[SC_PROPN]);
                 if (cp.ropt == 1 && proposal < cp.nlb) valid = 0;
                 else if (cp.ropt == 2 && proposal < S.scal[SC_C]) valid = 0;
               } else {
-                const double pc = S.scal[SC_PROPC];
-                const double u = r * (pc - 1 / pc) + 1 / pc;
-                proposal = old_rate * u;
                 if (cp.ropt == 1 && proposal > cp.cub) valid = 0;
                 else if (cp.ropt == 2 && proposal > S.scal[SC_N]) valid = 0;
               }
               if (proposal < 1e-12 || proposal > 1e8) valid = 0;
             }
-          }
-          valid = __shfl_sync(0xffffffffu, valid, 0);
-          proposal = __shfl_sync(0xffffffffu, proposal, 0);
-          double term = 0.0;
-          if (valid) {
-            const double pn = S.scal[SC_PROPN];
-            double x = proposal, a = prior_a, b = prior_b, sgn = 1.0;               // lane 0: + log pdf(proposal | prior)
-            if (lane == 1) { x = old_rate; sgn = -1.0; }                             // lane 1: - log pdf(current  | prior)
-            if (lane == 2) { x = old_rate; a = proposal / pn; b = pn; }               // lane 2: + log q(current | proposal)   (n only)
-            if (lane == 3) { x = proposal; a = old_rate / pn; b = pn; sgn = -1.0; }  // lane 3: - log q(proposal | current)  (n only)
-            if (lane < 2 || (neut && lane < 4)) term = sgn * log_gamma_pdf_ol(x, a, b);
-            else if (!neut && lane == 2) term = log(old_rate) - log(proposal);
-          }
-          const double t1 = __shfl_sync(0xffffffffu, term, 1), t2 = __shfl_sync(0xffffffffu, term, 2), t3 = __shfl_sync(0xffffffffu, term, 3);
-          if (lane == 0) {
-            S.scal[SC_MHPART] = ((term + t1) + t2) + t3;
+            S.scal[SC_MHPART] = valid ? (neut ? S.scal[SC_PRE_MH_N] : S.scal[SC_PRE_MH_C]) : 0.0;
             S.scal[SC_PROPOSAL] = valid ? proposal : cur_r;
             S.scal[SC_R] = r;
             S.ivars[IV_VALID] = valid;
