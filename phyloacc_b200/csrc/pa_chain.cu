@@ -28,23 +28,22 @@ namespace pa {
 
 namespace {
 
-#ifndef PA_CTAS_PER_SM
-#define PA_CTAS_PER_SM 3
-#endif
-constexpr int kBD = 256;
-constexpr int kNW = kBD / 32;
-constexpr int kTile = 256;       // patterns / sites per tile
-constexpr int kCodeRow = 132;    // staged bytes per tip row: 264 patterns
-constexpr int kXS = kBD + 4;     // bytes per row of sampled bases: 65 words, so that rows of different nodes fall into different banks
+// Per-layout constants (SmemT): BD threads per CTA; a tile is BD patterns / sites; CODEROW staged bytes per tip row
+// (BD + 8 patterns); XS bytes per row of sampled bases (BD / 4 + 1 words: rows of different nodes fall into different banks).
+#define PA_LAYOUT_CONSTANTS(SM) \
+  constexpr int kBD = SM::BD, kNW = SM::BD / 32, kTile = SM::BD, kCodeRow = SM::CODEROW, kXS = SM::XS; \
+  (void)kNW; (void)kTile; (void)kCodeRow; (void)kXS
 
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R,
        // scalars of the two MH steps, computed ahead of time by the last warp while the others sample histories
        SC_PRE_R_N = 16, SC_PRE_PROP_N, SC_PRE_PRIOR_N, SC_PRE_MH_N, SC_PRE_R_C, SC_PRE_PROP_C, SC_PRE_PRIOR_C, SC_PRE_MH_C, SC_COUNT = 24 };
 enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_COUNT = 16 };
 
-template <int NMAX, int SLOTS>
+template <int NMAX, int SLOTS_, int BD_>
 struct SmemT {
   static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
+  static constexpr int SLOTS = SLOTS_;     // temp-stack slots kept in shared memory; results parked deeper are re-read from the arena
+  static constexpr int BD = BD_, CODEROW = BD_ / 2 + 4, XS = BD_ + 4;
   alignas(16) double Pcur[NMAX * 16];
   union {  // buffers that are live in disjoint phases of an iteration share storage
     struct { alignas(16) double Pprop[NMAX * 16]; };  // rate steps: proposal P(t)
@@ -55,12 +54,12 @@ struct SmemT {
   };
   union {
     struct {  // pruning passes: per-thread temp stack [slot][base][thread] + scale counts
-      alignas(16) double stack[SLOTS * 4 * kBD];
-      int16_t stack_sc[SLOTS * kBD];
+      alignas(16) double stack[SLOTS * 4 * BD];
+      int16_t stack_sc[SLOTS * BD];
     };
     struct {  // history sampling: sampled bases [internal node][site] (4 = no draw), pattern offsets of the tile's sites
-      alignas(4) uint8_t xs8[NI * kXS];
-      uint16_t spat[kTile];
+      alignas(4) uint8_t xs8[NI * XS];
+      uint16_t spat[BD];
     };
   };
   double red[34];
@@ -78,7 +77,7 @@ struct SmemT {
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
-  alignas(4) uint8_t codes[NI * kCodeRow];
+  alignas(4) uint8_t codes[NI * CODEROW];
 };
 
 __device__ __forceinline__ double class_rate(int z, double n_rate, double c_rate) { return z == 2 ? n_rate : (z == 0 ? 1.0 : c_rate); }
@@ -103,6 +102,7 @@ struct Arena {
 // stage the packed tip codes of patterns [pb, pb + 264) (pb a multiple of 8) into shared memory
 template <class SM>
 __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb, int n_rows, int tid) {
+  PA_LAYOUT_CONSTANTS(SM);
   if (S.ivars[IV_STAGED] == pb) return;
   __syncthreads();
   const int half = ev.h->Ppad >> 1;
@@ -126,6 +126,7 @@ __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb,
 //       previous node (registers); 3 stack: offset (doubles) of its slot; 4 arena: offset (doubles) of its current partial
 template <bool USE_DIRTY, class SM>
 __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppad, int wflip, int n_su, int lane) {
+  PA_LAYOUT_CONSTANTS(SM);
   int n_act = 0;
   for (int k0 = 0; k0 < n_su; k0 += 32) {
     const int k = k0 + lane;
@@ -143,7 +144,10 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
     const int next_s = (j + 1 < n_act) ? (int)(S.ops[S.actk[j + 1]].x & 0xffff) : -2;
     uint4 d;
     d.x = (uint32_t)(S.sel[s] ^ wflip) * A.part_stride + q * (uint32_t)Ppad * 4u;
-    const uint32_t park = (j + 1 == n_act || next_s == (int)S.parent[s]) ? 63u : ((op.z >> 8) & 0xffu);
+    // a result that waits for a sibling subtree is parked in its stack slot if that slot is one of the SM::SLOTS kept in
+    // shared memory; deeper slots are not kept: the consumer re-reads the partial from the arena copy it was stored to
+    uint32_t park = (j + 1 == n_act || next_s == (int)S.parent[s]) ? 63u : ((op.z >> 8) & 0xffu);
+    if (park != 63u && park >= (uint32_t)SM::SLOTS) park = 63u;
     uint32_t kinds[2], pay[2];
 #pragma unroll
     for (int cc = 0; cc < 2; cc++) {
@@ -158,9 +162,12 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
       } else if (kind == 2u) {
         const bool dch = !USE_DIRTY || S.dirty[ch];
         if (dch && (int)ch == prev_s) kinds[cc] = 2u;
-        else if (dch) {
+        else if (dch && ((op.z >> (16 + 8 * cc)) & 0xffu) < (uint32_t)SM::SLOTS) {
           kinds[cc] = 3u;
           pay[cc] = ((op.z >> (16 + 8 * cc)) & 0xffu) * 4u * kBD;
+        } else if (dch) {  // parked beyond the shared-memory slots: read back what this pass stored
+          kinds[cc] = 4u;
+          pay[cc] = (uint32_t)(S.sel[ch] ^ wflip) * A.part_stride + xi * (uint32_t)Ppad * 4u;
         } else {
           kinds[cc] = 4u;
           pay[cc] = (uint32_t)S.sel[ch] * A.part_stride + xi * (uint32_t)Ppad * 4u;
@@ -181,6 +188,7 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
 // that wait for a sibling subtree.  Returns sum_p w_p log L_p.
 template <class SM>
 __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, const Arena& A, int n_act, int n_rows, int tid) {
+  PA_LAYOUT_CONSTANTS(SM);
   const int P = ev.h->P, Ppad = ev.h->Ppad;
   double acc = 0.0;
   for (int p0 = 0; p0 < Ppad; p0 += kTile) {
@@ -352,10 +360,11 @@ __device__ __noinline__ void z_update_logspace(SM& S, int n) {
   }
 }
 
-template <int NMAX, int SLOTS>
-__global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch L) {
+template <int NMAX, int SLOTS, int BD, int MINB>
+__global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef SmemT<NMAX, SLOTS> SM;
+  typedef SmemT<NMAX, SLOTS, BD> SM;
+  PA_LAYOUT_CONSTANTS(SM);
   SM& S = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ChainParams& cp = L.cp;
@@ -1017,29 +1026,32 @@ __global__ void __launch_bounds__(kBD, PA_CTAS_PER_SM) chain_kernel(ChainLaunch 
 }
 
 struct Variant {
-  int nmax, slots;
+  int nmax, slots, bd, ctas_per_sm;
   size_t smem;
   void (*kernel)(ChainLaunch);
 };
 
-template <int NMAX, int SLOTS>
+template <int NMAX, int SLOTS, int BD, int MINB>
 Variant make_variant() {
-  return Variant{NMAX, SLOTS, sizeof(SmemT<NMAX, SLOTS>) + 16, chain_kernel<NMAX, SLOTS>};
+  return Variant{NMAX, SLOTS, BD, MINB, sizeof(SmemT<NMAX, SLOTS, BD>) + 16, chain_kernel<NMAX, SLOTS, BD, MINB>};
 }
 
-// compiled shared-memory layouts: (max nodes of the tree incl. 2 * tip rows - 1, temp slots)
-const Variant* pick_variant(int n_max, int slots_max, int s_rows) {
-  static const Variant variants[] = {make_variant<32, 4>(), make_variant<96, 4>(), make_variant<96, 6>(), make_variant<160, 6>()};
+// compiled layouts: (max nodes of the tree incl. 2 * tip rows - 1, temp-stack slots in shared memory, threads per CTA,
+// resident CTAs per SM the register budget is compiled for).  Any tree with at most `nmax` nodes runs on any of them:
+// results parked deeper than the shared-memory slots are re-read from the arena.
+const Variant* pick_variant(int n_max, int s_rows, int bd) {
+  // (a 128-thread layout <96, 2, 128, 5> was measured: 5 CTAs per SM but two tiles for most elements -> 25 % slower)
+  static const Variant variants[] = {make_variant<32, 4, 256, 3>(), make_variant<96, 4, 256, 3>(), make_variant<160, 4, 256, 2>()};
   const int need = n_max > 2 * s_rows - 1 ? n_max : 2 * s_rows - 1;
   for (const Variant& v : variants)
-    if (need <= v.nmax && slots_max <= v.slots && s_rows <= v.nmax / 2 + 1) return &v;
+    if (v.bd == bd && need <= v.nmax && s_rows <= v.nmax / 2 + 1) return &v;
   return nullptr;
 }
 
 }  // namespace
 
-size_t chain_smem_bytes(int n_max, int slots_max, int s_rows) {
-  const Variant* v = pick_variant(n_max, slots_max, s_rows);
+size_t chain_smem_bytes(int n_max, int s_rows, int bd) {
+  const Variant* v = pick_variant(n_max, s_rows, bd);
   return v ? v->smem : (size_t)1 << 30;
 }
 
@@ -1048,12 +1060,13 @@ size_t chain_arena_bytes(int n_max, int P_max) {
   return (b + 255) & ~size_t(255);
 }
 
-int chain_block_dim() { return kBD; }
-int chain_ctas_per_sm() { return PA_CTAS_PER_SM; }
+int chain_ctas_per_sm(int n_max, int s_rows, int bd) {
+  const Variant* v = pick_variant(n_max, s_rows, bd);
+  return v ? v->ctas_per_sm : 1;
+}
 
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream) {
-  if (BD != kBD) return PA_ERR_ARG;
-  const Variant* v = pick_variant(L.n_max, L.slots_max, L.S_rows);
+  const Variant* v = pick_variant(L.n_max, L.S_rows, BD);
   if (!v) {
     set_error("tree too large for the compiled chain-kernel shared-memory layouts");
     return PA_ERR_LIMIT;
@@ -1063,7 +1076,7 @@ int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream) {
     set_error(std::string("chain kernel shared memory: ") + cudaGetErrorString(err));
     return PA_ERR_LIMIT;
   }
-  v->kernel<<<grid, kBD, v->smem, stream>>>(L);
+  v->kernel<<<grid, BD, v->smem, stream>>>(L);
   err = cudaGetLastError();
   if (err != cudaSuccess) {
     set_error(std::string("chain kernel launch: ") + cudaGetErrorString(err));

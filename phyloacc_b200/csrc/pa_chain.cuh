@@ -16,10 +16,10 @@ struct ChainLaunch {
   uint8_t* arena; size_t arena_stride;
   unsigned long long* counters; int* queue;
 };
-size_t chain_smem_bytes(int n_max, int slots_max, int s_rows);
+size_t chain_smem_bytes(int n_max, int s_rows, int bd);  // bd: threads per CTA of the layout (256 or 128)
+int chain_ctas_per_sm(int n_max, int s_rows, int bd);
 size_t chain_arena_bytes(int n_max, int P_max);
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
-int chain_block_dim();
 // one-warp-per-chain kernel (pa_chain_warp.cu)
 size_t chain_warp_smem_bytes(int n_max, int warps);
 int chain_warp_pst(int P_max);

@@ -19,8 +19,6 @@
 
 namespace pa {
 
-int chain_block_dim();
-int chain_ctas_per_sm();
 
 #define PA_CUDA(call)                                                                         \
   do {                                                                                        \
@@ -257,7 +255,8 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   if (const char* env = getenv("PA_WARPS_PER_CHAIN")) { const int w = atoi(env); warps_per_chain = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 2; }
   // trees too large for the 256-thread kernel's shared-memory layouts (temp stack, per-warp pair counters, staged tip
   // codes) go to the small-CTA kernel, which needs none of them: 8 warps per chain, one CTA per SM
-  const bool wide_fits = (int)chain_smem_bytes(n_max, slots_max, model.tree.S) <= smem_optin;
+  const int BD = 256;  // threads per CTA of the production kernel's layouts
+  const bool wide_fits = (int)chain_smem_bytes(n_max, model.tree.S, BD) <= smem_optin;
   if (!wide_fits) warps_per_chain = 8;
   const bool warp_fits = (int)chain_warp_smem_bytes(n_max, warps_per_chain) <= smem_optin;
   int warp_pmax = 384;
@@ -282,15 +281,14 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
 
   int grid_wide = 0, grid_warp = 0;
   size_t stride_wide = 0, stride_warp = 0;
-  const int BD = chain_block_dim();
   if (n_wide > 0) {
-    const size_t smem = chain_smem_bytes(n_max, slots_max, model.tree.S);
+    const size_t smem = chain_smem_bytes(n_max, model.tree.S, BD);
     if ((int)smem > smem_optin) {
       set_error("tree too large for the chain kernel's shared memory (" + std::to_string(smem) + " bytes needed)");
       return PA_ERR_LIMIT;
     }
     // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and by the kernel's launch bounds
-    int per_sm = std::max(1, std::min(chain_ctas_per_sm(), (int)(233472 / (smem + 1024))));
+    int per_sm = std::max(1, std::min(chain_ctas_per_sm(n_max, model.tree.S, BD), (int)(233472 / (smem + 1024))));
     if (const char* env = getenv("PA_CTAS_PER_SM_RUNTIME")) per_sm = std::max(1, std::min(per_sm, atoi(env)));  // tuning knob
     grid_wide = std::min(n_wide, num_sms * per_sm);
     stride_wide = chain_arena_bytes(n_max, (P_max_wide + 31) & ~31);
