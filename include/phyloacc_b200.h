@@ -107,6 +107,7 @@ typedef struct pa_element_info {
   int32_t* pattern_weights; /* [P] */
   int32_t* site_pattern;    /* [GG] pattern index of every kept column, original column order */
   uint8_t* fixZ;            /* [3][N]: 1 where fixZ == 1 for M0, M1, M2 (initMCMC bpp_c.cpp:155-161,240-289) */
+  int32_t n_slots;          /* out: temporaries the pruning traversal of this element's tree needs (no reference counterpart) */
 } pa_element_info;
 
 const char* pa_last_error(void);

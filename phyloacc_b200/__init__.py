@@ -66,7 +66,7 @@ class PaTrace(C.Structure):
 class PaElementInfo(C.Structure):
     _fields_ = [("filtered", C.c_int32), ("GG", C.c_int32), ("P", C.c_int32), ("root", C.c_int32), ("n_nodes", C.c_int32),
                 ("missing", _u8p), ("nodes", _i32p), ("children2", _i32p), ("parent2", _i32p), ("distances2", _f64p),
-                ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p)]
+                ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p), ("n_slots", C.c_int32)]
 
 
 class PaHyper(C.Structure):
@@ -291,7 +291,7 @@ class Engine:
         info.site_pattern = bufs["site_pattern"].ctypes.data_as(_i32p)
         info.fixZ = bufs["fixZ"].ctypes.data_as(_u8p)
         _check(self._lib.pa_engine_element_info(self._h, c, C.byref(info)))
-        out = dict(filtered=bool(info.filtered), GG=info.GG, P=info.P, root=info.root, n_nodes=info.n_nodes)
+        out = dict(filtered=bool(info.filtered), GG=info.GG, P=info.P, root=info.root, n_nodes=info.n_nodes, n_slots=info.n_slots)
         if not out["filtered"]:
             out.update(missing=bufs["missing"].astype(bool), nodes=bufs["nodes"][:info.n_nodes].tolist(), children2=bufs["children2"],
                        parent2=bufs["parent2"], distances2=bufs["distances2"], pattern_codes=bufs["pattern_codes"][:info.P],

@@ -84,6 +84,7 @@ int pa_engine_element_info(const pa_engine* e, int32_t elem, pa_element_info* ou
   out->P = p.P;
   out->root = p.root;
   out->n_nodes = (int32_t)p.nodes.size();
+  out->n_slots = p.n_slots;
   if (p.filtered) return PA_OK;
   if (out->missing) memcpy(out->missing, p.missing.data(), N);
   if (out->nodes) memcpy(out->nodes, p.nodes.data(), sizeof(int32_t) * p.nodes.size());

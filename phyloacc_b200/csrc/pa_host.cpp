@@ -848,6 +848,7 @@ void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, in
   memset(&h, 0, sizeof(h));
   h.n = n; h.ni = ni; h.S = S; h.P = Pn; h.Ppad = Ppad; h.GG = GG; h.W = W; h.n_slots = std::max(1, n_slots);
   h.n_up = n_up; h.n_down = n_down; h.elem_id = elem_id;
+  out.n_slots = std::max(1, n_slots);
   h.off_parent = put(blob, parent_l, n);
   h.off_child = put(blob, child_l, 2 * n);
   h.off_flags = put(blob, flags, n);

@@ -117,6 +117,7 @@ struct Alignment {  // PhyloProf
 struct ElemPlan {  // integer part of BPP_C::BPP_C for one element + pattern compression
   bool filtered = true;
   int GG = 0, P = 0, root = -1;
+  int n_slots = 0;                              // temp-partial slots the pruning traversal needs (Sethi-Ullman number)
   std::vector<uint8_t> missing;                 // [N]
   std::vector<int32_t> nodes;                   // post-order of the pruned tree (original ids)
   std::vector<int32_t> children2, parent2;      // [N][2], [N]

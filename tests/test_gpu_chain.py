@@ -158,3 +158,22 @@ def test_small_cta_kernel_matches_oracle(warps, native_lib, oracle_lib, tmp_path
     eng = pab.Engine.from_config(cfg, device=0)
     assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2, 3]) >= 6
     eng.close()
+
+
+def test_balanced_tree_parks_deeper_than_the_shared_memory_stack(native_lib, oracle_lib, tmp_path, monkeypatch):
+    """A perfectly balanced tree needs more temporaries than the four stack slots the 256-thread kernel keeps in shared
+    memory: the deeper parks are re-read from the arena (build_pass_program), with the same chains as the oracle."""
+    from phyloacc_b200 import synth
+
+    def balanced(rng, n_tips):
+        if n_tips == 1:
+            return ("tip",)
+        return (balanced(rng, n_tips // 2), balanced(rng, n_tips - n_tips // 2))
+
+    monkeypatch.setattr(synth, "_yule_topology", balanced)
+    cfg, P, otree, model, X, starts, lens = _synthetic_case(str(tmp_path), S=40, C=3, length=120, gap_frac=0.01, missing_frac=0.0,
+                                                            params=dict(BURNIN=6, MCMC=14, CHAIN=1, ADAPT_FREQ=5, SEED=9))
+    eng = pab.Engine.from_config(cfg, device=0)
+    assert max(eng.element_info(c)["n_slots"] for c in range(3)) > 4
+    assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2]) >= 6
+    eng.close()
