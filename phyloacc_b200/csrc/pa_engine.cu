@@ -174,6 +174,11 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
   n_max = 0; slots_max = 1; P_max = 0; GG_max = 0;
   for (int c = 0; c < C; c++) {
     if (plans[c].filtered) continue;
+    if (plans[c].GG > 65535) {  // pattern / site indices and pattern weights are 16-bit on the device
+      set_error("element " + std::to_string(c) + " has " + std::to_string(plans[c].GG) + " columns; the engine handles at most 65535 per element");
+      loaded = false;
+      return PA_ERR_LIMIT;
+    }
     blob_off[c] = (int64_t)total;
     total += plans[c].blob.size();
     const ElemHeader* h = reinterpret_cast<const ElemHeader*>(plans[c].blob.data());

@@ -180,3 +180,18 @@ def test_empty_id_list_and_out_of_range_ids(native_lib, tmp_path):
     assert len(eng.ids()) == 0
     eng.close()
     case.close()
+
+
+def test_element_longer_than_the_device_index_range_is_refused(native_lib):
+    # pattern / site indices are 16-bit on the device: a 70 kb "element" is an error (PA_ERR_LIMIT), not a silent wrap-around
+    tree = synth.make_tree(S=8, seed=5, n_out=2, n_target=2)
+    G = 70000
+    X = np.full((tree.S, G), ord("a"), dtype=np.uint8)
+    prm = pab.default_params()
+    eng = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup, conserve=tree.conserve, device=-1)
+    with pytest.raises(pab.PhyloAccError) as ei:
+        eng.load_alignment(X, np.array([0], dtype=np.int64), np.array([G], dtype=np.int32))
+    assert ei.value.code == -5 and "65535" in str(ei.value)
+    eng.load_alignment(X, np.array([0], dtype=np.int64), np.array([60000], dtype=np.int32))  # below the limit: accepted
+    assert not eng.element_info(0, gg_max=60000)["filtered"]
+    eng.close()
