@@ -39,8 +39,9 @@ enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL
        SC_PRE_R_N = 16, SC_PRE_PROP_N, SC_PRE_PRIOR_N, SC_PRE_MH_N, SC_PRE_R_C, SC_PRE_PROP_C, SC_PRE_PRIOR_C, SC_PRE_MH_C, SC_COUNT = 24 };
 enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_COUNT = 16 };
 
-template <int NMAX, int SLOTS_, int BD_>
+template <int NMAX, int SLOTS_, int BD_, bool STAGE_>
 struct SmemT {
+  static constexpr bool STAGE = STAGE_;    // tip codes of the current tile staged in shared memory (false: read from the blob; deep trees)
   static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
   static constexpr int SLOTS = SLOTS_;     // temp-stack slots kept in shared memory; results parked deeper are re-read from the arena
   static constexpr int BD = BD_, CODEROW = BD_ / 2 + 4, XS = BD_ + 4;
@@ -77,7 +78,7 @@ struct SmemT {
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
-  alignas(4) uint8_t codes[NI * CODEROW];
+  alignas(4) uint8_t codes[STAGE_ ? NI * CODEROW : 4];
 };
 
 __device__ __forceinline__ double class_rate(int z, double n_rate, double c_rate) { return z == 2 ? n_rate : (z == 0 ? 1.0 : c_rate); }
@@ -103,6 +104,7 @@ struct Arena {
 template <class SM>
 __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb, int n_rows, int tid) {
   PA_LAYOUT_CONSTANTS(SM);
+  if (!SM::STAGE) return;
   if (S.ivars[IV_STAGED] == pb) return;
   __syncthreads();
   const int half = ev.h->Ppad >> 1;
@@ -158,7 +160,7 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
       pay[cc] = 0u;
       if (kind == 1u) {
         kinds[cc] = 1u;
-        pay[cc] = xi * kCodeRow;
+        pay[cc] = xi * (SM::STAGE ? (uint32_t)kCodeRow : (uint32_t)(Ppad >> 1));  // byte offset of the tip's row of codes
       } else if (kind == 2u) {
         const bool dch = !USE_DIRTY || S.dirty[ch];
         if (dch && (int)ch == prev_s) kinds[cc] = 2u;
@@ -195,7 +197,7 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
     ensure_staged(S, ev, p0, n_rows, tid);
     const int p = p0 + tid;
     if (p < P) {
-      const uint8_t* __restrict__ cp = S.codes + (tid >> 1);
+      const uint8_t* __restrict__ cp = SM::STAGE ? (S.codes + (tid >> 1)) : (ev.codes + (p >> 1));
       const int sh = (p & 1) * 4;
       const double* __restrict__ gpart = A.part + (uint32_t)p * 4u;
       const int16_t* __restrict__ gsc = A.sc + p;
@@ -360,10 +362,10 @@ __device__ __noinline__ void z_update_logspace(SM& S, int n) {
   }
 }
 
-template <int NMAX, int SLOTS, int BD, int MINB>
+template <int NMAX, int SLOTS, int BD, int MINB, bool STAGE>
 __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef SmemT<NMAX, SLOTS, BD> SM;
+  typedef SmemT<NMAX, SLOTS, BD, STAGE> SM;
   PA_LAYOUT_CONSTANTS(SM);
   SM& S = *reinterpret_cast<SM*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -645,13 +647,15 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           const int nb = n - 1;
           const int K = max(1, kBD / nb);                               // site slices per branch
           const int sub = min(128, (((tile_sites + K - 1) / K) + 3) & ~3);  // sites per slice: multiple of 4, <= 128 (8-bit fields)
-          if (tid < nb * K) {
-            const int i = tid % nb, k = tid / nb;
+          for (int task = tid; task < nb * K; task += kBD) {  // more than kBD branches (deep trees): several per thread
+            const int i = task % nb, k = task / nb;
             const uint32_t d = S.cb[i];
             if (d != 0xffffffffu) {
               const uint8_t* __restrict__ prow = S.xs8 + ((d >> 16) & 0x7fffu) * kXS;
               const bool tip = (d >> 31) != 0;
-              const uint8_t* __restrict__ crow = tip ? (S.codes + (d & 0xffffu) * kCodeRow) : (S.xs8 + (d & 0xffffu) * kXS);
+              const uint8_t* __restrict__ crow =
+                  tip ? (SM::STAGE ? (S.codes + (d & 0xffffu) * kCodeRow) : (ev.codes + (size_t)(d & 0xffffu) * (Ppad >> 1) + (pb >> 1)))
+                      : (S.xs8 + (d & 0xffffu) * kXS);
               for (int s0 = k * sub; s0 < tile_sites; s0 += K * sub) {
                 const int s1 = min(s0 + sub, tile_sites);
                 uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
@@ -1031,9 +1035,9 @@ struct Variant {
   void (*kernel)(ChainLaunch);
 };
 
-template <int NMAX, int SLOTS, int BD, int MINB>
+template <int NMAX, int SLOTS, int BD, int MINB, bool STAGE>
 Variant make_variant() {
-  return Variant{NMAX, SLOTS, BD, MINB, sizeof(SmemT<NMAX, SLOTS, BD>) + 16, chain_kernel<NMAX, SLOTS, BD, MINB>};
+  return Variant{NMAX, SLOTS, BD, MINB, sizeof(SmemT<NMAX, SLOTS, BD, STAGE>) + 16, chain_kernel<NMAX, SLOTS, BD, MINB, STAGE>};
 }
 
 // compiled layouts: (max nodes of the tree incl. 2 * tip rows - 1, temp-stack slots in shared memory, threads per CTA,
@@ -1041,7 +1045,9 @@ Variant make_variant() {
 // results parked deeper than the shared-memory slots are re-read from the arena.
 const Variant* pick_variant(int n_max, int s_rows, int bd) {
   // (a 128-thread layout <96, 2, 128, 5> was measured: 5 CTAs per SM but two tiles for most elements -> 25 % slower)
-  static const Variant variants[] = {make_variant<32, 4, 256, 3>(), make_variant<96, 4, 256, 3>(), make_variant<160, 4, 256, 2>()};
+  // the last layout serves Zoonomia-scale trees (240 taxa, 479 nodes): one CTA per SM, tip codes read from the blob
+  static const Variant variants[] = {make_variant<32, 4, 256, 3, true>(), make_variant<96, 4, 256, 3, true>(), make_variant<160, 4, 256, 2, true>(),
+                                     make_variant<480, 4, 256, 1, false>()};
   const int need = n_max > 2 * s_rows - 1 ? n_max : 2 * s_rows - 1;
   for (const Variant& v : variants)
     if (v.bd == bd && need <= v.nmax && s_rows <= v.nmax / 2 + 1) return &v;

@@ -20,10 +20,5 @@ size_t chain_smem_bytes(int n_max, int s_rows, int bd);  // bd: threads per CTA 
 int chain_ctas_per_sm(int n_max, int s_rows, int bd);
 size_t chain_arena_bytes(int n_max, int P_max);
 int launch_chains(const ChainLaunch& L, int grid, int BD, cudaStream_t stream);
-// one-warp-per-chain kernel (pa_chain_warp.cu)
-size_t chain_warp_smem_bytes(int n_max, int warps);
-int chain_warp_pst(int P_max);
-size_t chain_warp_arena_bytes(int n_max, int P_max);
-int launch_chains_warp(const ChainLaunch& L, int grid, int warps, cudaStream_t stream);
 }  // namespace pa
 #endif

@@ -139,7 +139,6 @@ struct ElemView {
   const int16_t* down_nodes;
   const int16_t* down_off;
   const uint8_t* codes;
-  const uint8_t* codes2;
   const uint16_t* weights;
   const uint32_t* gap;
   const uint16_t* sitepat;
@@ -164,7 +163,6 @@ __device__ __forceinline__ ElemView make_view(const uint8_t* blob) {
   v.down_nodes = reinterpret_cast<const int16_t*>(blob + h->off_down_nodes);
   v.down_off = reinterpret_cast<const int16_t*>(blob + h->off_down_off);
   v.codes = blob + h->off_codes;
-  v.codes2 = blob + h->off_codes2;
   v.weights = reinterpret_cast<const uint16_t*>(blob + h->off_weights);
   v.gap = reinterpret_cast<const uint32_t*>(blob + h->off_gap);
   v.sitepat = reinterpret_cast<const uint16_t*>(blob + h->off_sitepat);

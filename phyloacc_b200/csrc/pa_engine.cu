@@ -106,19 +106,14 @@ void Engine::release_device() {
   auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
   fr((void*&)d_blobs); fr((void*&)d_blob_off);
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
-  fr((void*&)d_arena_w); fr((void*&)d_sel); fr((void*&)d_init_rates); fr((void*&)d_init_z);
+  fr((void*&)d_init_rates); fr((void*&)d_init_z);
   cap_init_rates = cap_init_z = 0;
   if (h_trace_d) cudaFreeHost(h_trace_d);
   if (h_trace_z) cudaFreeHost(h_trace_z);
   h_trace_d = nullptr;
   h_trace_z = nullptr;
   cap_h_trace_d = cap_h_trace_z = 0;
-  cap_chain_list = cap_sel = cap_trace_d = cap_trace_z = cap_arena = cap_arena_w = cap_counters = cap_queue = 0;
-  if (ev_fork) cudaEventDestroy(ev_fork);
-  if (ev_join) cudaEventDestroy(ev_join);
-  if (stream2) cudaStreamDestroy(stream2);
-  ev_fork = ev_join = nullptr;
-  stream2 = nullptr;
+  cap_chain_list = cap_trace_d = cap_trace_z = cap_arena = cap_counters = cap_queue = 0;
 }
 
 int Engine::init(const pa_tree* tree, const pa_subst* subst, const pa_params* params, int dev) {

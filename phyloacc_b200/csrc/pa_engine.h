@@ -41,12 +41,8 @@ struct Engine {
   int32_t* d_chain_list = nullptr;       // [n_chains][2] (element id, model) sorted by decreasing cost
   double* d_trace_d = nullptr;           // [n_chains][6][T]
   uint32_t* d_trace_z = nullptr;         // [n_chains][T][ZW] 2-bit packed Z by local node index
-  uint8_t* d_arena = nullptr;            // per-CTA scratch (partials, scale counts, log P tables) of the 256-thread kernel
-  uint8_t* d_arena_w = nullptr;          // per-CTA scratch of the one-warp-per-chain kernel
-  int32_t* d_sel = nullptr;              // chain indices: the 256-thread kernel's chains, then the warp kernel's
-  cudaStream_t stream2 = nullptr;        // side stream: the two chain kernels run concurrently
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  size_t cap_chain_list = 0, cap_sel = 0, cap_trace_d = 0, cap_trace_z = 0, cap_arena = 0, cap_arena_w = 0, cap_counters = 0, cap_queue = 0;
+  uint8_t* d_arena = nullptr;            // per-CTA scratch (partials, scale counts, log P tables)
+  size_t cap_chain_list = 0, cap_trace_d = 0, cap_trace_z = 0, cap_arena = 0, cap_counters = 0, cap_queue = 0;
   unsigned long long* d_counters = nullptr;
   int* d_queue = nullptr;
   // last state of every (element, model) chain that has run: the warm start of the next outer CHAIN iteration

@@ -245,73 +245,27 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     return e;
   };
 
-  // Two kernels can share the chain list: the 256-thread kernel (pa_chain.cu, the production path) and the
-  // small-CTA kernel (pa_chain_warp.cu: 1-8 warps per chain, two patterns per lane, no shared-memory stack), which is
-  // parity-tested but measured SLOWER on B200 (profiles/r1_v4_small_cta_experiment.txt) and therefore opt-in:
-  // PA_CHAIN_KERNEL=warp sends every chain to it, PA_CHAIN_KERNEL=split the chains of elements with at most
-  // PA_WARP_PMAX site patterns; PA_WARPS_PER_CHAIN = 1 | 2 | 4 | 8.
-  const char* force = getenv("PA_CHAIN_KERNEL");
-  int warps_per_chain = 2;
-  if (const char* env = getenv("PA_WARPS_PER_CHAIN")) { const int w = atoi(env); warps_per_chain = (w == 1 || w == 2 || w == 4 || w == 8) ? w : 2; }
-  // trees too large for the 256-thread kernel's shared-memory layouts (temp stack, per-warp pair counters, staged tip
-  // codes) go to the small-CTA kernel, which needs none of them: 8 warps per chain, one CTA per SM
-  const int BD = 256;  // threads per CTA of the production kernel's layouts
-  const bool wide_fits = (int)chain_smem_bytes(n_max, model.tree.S, BD) <= smem_optin;
-  if (!wide_fits) warps_per_chain = 8;
-  const bool warp_fits = (int)chain_warp_smem_bytes(n_max, warps_per_chain) <= smem_optin;
-  int warp_pmax = 384;
-  if (const char* env = getenv("PA_WARP_PMAX")) warp_pmax = atoi(env);
-  std::vector<int32_t> sel_wide, sel_warp;
-  int P_max_warp = 1, P_max_wide = 1;
-  for (int k = 0; k < n_chains; k++) {
-    const int Pk = plans[list[2 * k]].P;
-    bool to_warp = false;
-    if (force && !strcmp(force, "split")) to_warp = warp_fits && Pk <= warp_pmax;
-    if ((force && !strcmp(force, "warp")) || !wide_fits) to_warp = true;
-    if (to_warp && !warp_fits) {
-      set_error("tree too large for the chain kernels' shared memory (" + std::to_string(n_max) + " nodes)");
-      return PA_ERR_LIMIT;
-    }
-    if (to_warp) { sel_warp.push_back(k); P_max_warp = std::max(P_max_warp, Pk); }
-    else { sel_wide.push_back(k); P_max_wide = std::max(P_max_wide, Pk); }
+  // one persistent launch: CTAs pull chains (longest first) from an atomic queue
+  const int BD = 256;  // threads per CTA of the chain kernel's layouts
+  const size_t smem = chain_smem_bytes(n_max, model.tree.S, BD);
+  if ((int)smem > smem_optin) {
+    set_error("tree too large for the chain kernel's shared-memory layouts (" + std::to_string(n_max) + " nodes)");
+    return PA_ERR_LIMIT;
   }
-  const int n_wide = (int)sel_wide.size(), n_warp = (int)sel_warp.size();
-  std::vector<int32_t> sel_all(sel_wide);
-  sel_all.insert(sel_all.end(), sel_warp.begin(), sel_warp.end());
-
-  int grid_wide = 0, grid_warp = 0;
-  size_t stride_wide = 0, stride_warp = 0;
-  if (n_wide > 0) {
-    const size_t smem = chain_smem_bytes(n_max, model.tree.S, BD);
-    if ((int)smem > smem_optin) {
-      set_error("tree too large for the chain kernel's shared memory (" + std::to_string(smem) + " bytes needed)");
-      return PA_ERR_LIMIT;
-    }
-    // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and by the kernel's launch bounds
-    int per_sm = std::max(1, std::min(chain_ctas_per_sm(n_max, model.tree.S, BD), (int)(233472 / (smem + 1024))));
-    if (const char* env = getenv("PA_CTAS_PER_SM_RUNTIME")) per_sm = std::max(1, std::min(per_sm, atoi(env)));  // tuning knob
-    grid_wide = std::min(n_wide, num_sms * per_sm);
-    stride_wide = chain_arena_bytes(n_max, (P_max_wide + 31) & ~31);
-  }
-  if (n_warp > 0) {
-    const size_t smem = chain_warp_smem_bytes(n_max, warps_per_chain);
-    int per_sm = std::max(1, std::min(32, (int)(233472 / (smem + 1024))));
-    if (const char* env = getenv("PA_WARPS_PER_SM_RUNTIME")) per_sm = std::max(1, std::min(per_sm, atoi(env)));  // tuning knob
-    grid_warp = std::min(n_warp, num_sms * per_sm);
-    stride_warp = chain_warp_arena_bytes(n_max, P_max_warp);
-  }
+  // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and by the layout's launch bounds
+  int per_sm = std::max(1, std::min(chain_ctas_per_sm(n_max, model.tree.S, BD), (int)(233472 / (smem + 1024))));
+  if (const char* env = getenv("PA_CTAS_PER_SM_RUNTIME")) per_sm = std::max(1, std::min(per_sm, atoi(env)));  // tuning knob
+  const int grid = std::min(n_chains, num_sms * per_sm);
+  const size_t stride = chain_arena_bytes(n_max, P_max);
   PA_CUDA(reserve((void*&)d_chain_list, cap_chain_list, sizeof(int32_t) * 2 * n_chains));
-  PA_CUDA(reserve((void*&)d_sel, cap_sel, sizeof(int32_t) * n_chains));
   PA_CUDA(reserve((void*&)d_trace_d, cap_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
   PA_CUDA(reserve((void*&)d_trace_z, cap_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));
-  if (grid_wide) PA_CUDA(reserve((void*&)d_arena, cap_arena, stride_wide * grid_wide));
-  if (grid_warp) PA_CUDA(reserve((void*&)d_arena_w, cap_arena_w, stride_warp * grid_warp));
+  PA_CUDA(reserve((void*&)d_arena, cap_arena, stride * grid));
   PA_CUDA(reserve((void*&)d_counters, cap_counters, sizeof(unsigned long long) * 24));
-  PA_CUDA(reserve((void*&)d_queue, cap_queue, sizeof(int) * 2));
+  PA_CUDA(reserve((void*&)d_queue, cap_queue, sizeof(int)));
   PA_CUDA(cudaMemcpyAsync(d_chain_list, list.data(), sizeof(int32_t) * 2 * n_chains, cudaMemcpyHostToDevice, stream));
-  PA_CUDA(cudaMemcpyAsync(d_sel, sel_all.data(), sizeof(int32_t) * n_chains, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 24, stream));
-  PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int) * 2, stream));
+  PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int), stream));
   bool any_warm = false;
   if (warm_start && !cur_set.empty()) {
     std::vector<double> ir((size_t)n_chains * 8, 0.0);
@@ -354,32 +308,11 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   L.init_rates = any_warm ? d_init_rates : nullptr;
   L.init_z = any_warm ? d_init_z : nullptr;
   L.counters = d_counters;
-  counters.kernel_launches = 0;
-  // the long chains go first, on the side stream, so that both kernels share the SMs; `stream` joins at the end
-  if (!stream2) PA_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-  if (!ev_fork) PA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-  if (!ev_join) PA_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  if (grid_wide) {
-    L.sel = d_sel; L.n_sel = n_wide; L.P_max = (P_max_wide + 31) & ~31;
-    L.arena = d_arena; L.arena_stride = stride_wide; L.queue = d_queue;
-    cudaStream_t st = grid_warp ? stream2 : stream;
-    if (grid_warp) {
-      PA_CUDA(cudaEventRecord(ev_fork, stream));
-      PA_CUDA(cudaStreamWaitEvent(stream2, ev_fork, 0));
-    }
-    const int rc = launch_chains(L, grid_wide, BD, st);
-    if (rc != PA_OK) return rc;
-    if (grid_warp) PA_CUDA(cudaEventRecord(ev_join, stream2));
-    counters.kernel_launches++;
-  }
-  if (grid_warp) {
-    L.sel = d_sel + n_wide; L.n_sel = n_warp; L.P_max = chain_warp_pst(P_max_warp);
-    L.arena = d_arena_w; L.arena_stride = stride_warp; L.queue = d_queue + 1;
-    const int rc = launch_chains_warp(L, grid_warp, warps_per_chain, stream);
-    if (rc != PA_OK) return rc;
-    if (grid_wide) PA_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
-    counters.kernel_launches++;
-  }
+  L.sel = nullptr; L.n_sel = n_chains; L.P_max = P_max;
+  L.arena = d_arena; L.arena_stride = stride; L.queue = d_queue;
+  const int rc = launch_chains(L, grid, BD, stream);
+  if (rc != PA_OK) return rc;
+  counters.kernel_launches = 1;
   return PA_OK;
 }
 

@@ -814,14 +814,6 @@ void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, in
       const uint8_t c = out.pattern_codes[(size_t)p * S + s];
       b = (p & 1) ? (uint8_t)((b & 0x0F) | (c << 4)) : (uint8_t)((b & 0xF0) | c);
     }
-  const int n_tile64 = (Pn + 63) / 64;
-  std::vector<uint8_t> codes2((size_t)S * n_tile64 * 32, 0xFF);
-  for (int p = 0; p < Pn; p++)
-    for (int s = 0; s < S; s++) {
-      uint8_t& b = codes2[((size_t)s * n_tile64 + (p >> 6)) * 32 + (p & 31)];
-      const uint8_t c = out.pattern_codes[(size_t)p * S + s];
-      b = ((p >> 5) & 1) ? (uint8_t)((b & 0x0F) | (c << 4)) : (uint8_t)((b & 0xF0) | c);
-    }
   std::vector<uint16_t> weights(Ppad, 0);
   for (int p = 0; p < Pn; p++) weights[p] = (uint16_t)out.pattern_weights[p];
   // gap flags of internal nodes per pattern (bpp_c.hpp:417-428): both children "all-gap" (raw tip codes, regardless of `missing`)
@@ -871,8 +863,6 @@ void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, in
   h.off_weights = put(blob, weights, Ppad);
   h.off_gap = put(blob, gap, gap.size());
   h.off_sitepat = put(blob, sitepat, GGpad);
-  h.off_codes2 = put(blob, codes2, codes2.size());
-  h.n_tile64 = n_tile64;
   blob.resize((blob.size() + 255) & ~size_t(255), 0);
   h.blob_bytes = (int32_t)blob.size();
   memcpy(blob.data(), &h, sizeof(h));

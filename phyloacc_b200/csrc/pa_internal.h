@@ -60,8 +60,7 @@ struct ElemHeader {
   int32_t off_weights;     // uint16[Ppad]
   int32_t off_gap;         // uint32[W][Ppad]   bit q set <=> internal node q is "all-gap" at this pattern (bpp_c.hpp:417-428)
   int32_t off_sitepat;     // uint16[GGpad]     pattern of each site, sites sorted by (pattern, column)
-  int32_t off_codes2;      // uint8[S][n_tile64][32] tip masks for the warp kernel: byte (tile t, lane l) = pattern 64t+l | pattern 64t+32+l << 4
-  int32_t n_tile64;        // ceil(P / 64)
+  int32_t pad_[2];
 };
 
 // Substitution model on the device: P(t) = sum_m exp(eval[m] * t * r) * A[m]  with A[m][j][i] = V[j][m] * Vinv[m][i]

@@ -14,7 +14,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, obj, ksub, n_iter = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
 title = sys.argv[5] if len(sys.argv) > 5 else os.path.basename(rep)
-SRC = os.path.join(ROOT, "phyloacc_b200", "csrc", "pa_chain.cu" if "warp" not in obj else "pa_chain_warp.cu")
+SRC = os.path.join(ROOT, "phyloacc_b200", "csrc", "pa_chain.cu")
 
 
 def ncu_csv(page):

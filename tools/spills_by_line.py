@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """List the source lines that carry local-memory (spill / stack) instructions in a kernel of the built library.
-usage: spills_by_line.py <object-name-in-lib, e.g. pa_chain_warp> <kernel-substring, e.g. Li86> [top]"""
+usage: spills_by_line.py <object-name-in-lib, e.g. pa_chain.sm> <kernel-substring, e.g. Li96ELi4> [top]"""
 import collections
 import os
 import re
