@@ -1047,7 +1047,7 @@ const Variant* pick_variant(int n_max, int s_rows, int bd) {
   // (a 128-thread layout <96, 2, 128, 5> was measured: 5 CTAs per SM but two tiles for most elements -> 25 % slower)
   // the last layout serves Zoonomia-scale trees (240 taxa, 479 nodes): one CTA per SM, tip codes read from the blob
   static const Variant variants[] = {make_variant<32, 4, 256, 3, true>(), make_variant<96, 4, 256, 3, true>(), make_variant<160, 4, 256, 2, true>(),
-                                     make_variant<480, 4, 256, 1, false>()};
+                                     make_variant<240, 4, 256, 2, false>(), make_variant<480, 4, 256, 1, false>()};
   const int need = n_max > 2 * s_rows - 1 ? n_max : 2 * s_rows - 1;
   for (const Variant& v : variants)
     if (v.bd == bd && need <= v.nmax && s_rows <= v.nmax / 2 + 1) return &v;
