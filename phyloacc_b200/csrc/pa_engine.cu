@@ -105,8 +105,10 @@ void Engine::release_device() {
   cudaSetDevice(device);
   auto fr = [](void*& p) { if (p) cudaFree(p); p = nullptr; };
   fr((void*&)d_blobs); fr((void*&)d_blob_off);
+  cap_blobs = cap_blob_off = 0;
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
-  fr((void*&)d_init_rates); fr((void*&)d_init_z);
+  fr((void*&)d_init_rates); fr((void*&)d_init_z); fr((void*&)d_replay);
+  cap_replay = 0;
   cap_init_rates = cap_init_z = 0;
   if (h_trace_d) cudaFreeHost(h_trace_d);
   if (h_trace_z) cudaFreeHost(h_trace_z);
@@ -186,10 +188,6 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
   if (device < 0) return PA_OK;
   PA_CUDA(cudaSetDevice(device));
   // only the batch itself is replaced; the buffers of a run (arenas, traces, pinned host copies) persist and grow on demand
-  if (d_blobs) cudaFree(d_blobs);
-  if (d_blob_off) cudaFree(d_blob_off);
-  d_blobs = nullptr;
-  d_blob_off = nullptr;
   sampled = collected = false;
   std::vector<uint8_t> all(total);
   for (int c = 0; c < C; c++)
@@ -197,8 +195,23 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
       memcpy(all.data() + blob_off[c], plans[c].blob.data(), plans[c].blob.size());
       std::vector<uint8_t>().swap(plans[c].blob);  // the packed copy now lives in HBM
     }
-  PA_CUDA(cudaMalloc(&d_blobs, std::max<size_t>(total, 16)));
-  PA_CUDA(cudaMalloc(&d_blob_off, sizeof(int64_t) * std::max(C, 1)));
+  {
+    const size_t need_b = std::max<size_t>(total, 16), need_o = sizeof(int64_t) * (size_t)std::max(C, 1);
+    if (need_b > cap_blobs || !d_blobs) {
+      if (d_blobs) cudaFree(d_blobs);
+      d_blobs = nullptr;
+      cap_blobs = 0;
+      PA_CUDA(cudaMalloc(&d_blobs, need_b));
+      cap_blobs = need_b;
+    }
+    if (need_o > cap_blob_off || !d_blob_off) {
+      if (d_blob_off) cudaFree(d_blob_off);
+      d_blob_off = nullptr;
+      cap_blob_off = 0;
+      PA_CUDA(cudaMalloc(&d_blob_off, need_o));
+      cap_blob_off = need_o;
+    }
+  }
   PA_CUDA(cudaMemcpyAsync(d_blobs, all.data(), total, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemcpyAsync(d_blob_off, blob_off.data(), sizeof(int64_t) * C, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaStreamSynchronize(stream));
@@ -223,14 +236,22 @@ int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z
       return PA_ERR_ARG;
     }
   PA_CUDA(cudaSetDevice(device));
-  int32_t* d_elem = nullptr;
-  int8_t* d_Z = nullptr;
-  double *d_n = nullptr, *d_c = nullptr, *d_out = nullptr;
-  PA_CUDA(cudaMalloc(&d_elem, sizeof(int32_t) * n_states));
-  PA_CUDA(cudaMalloc(&d_Z, (size_t)n_states * N));
-  PA_CUDA(cudaMalloc(&d_n, sizeof(double) * n_states));
-  PA_CUDA(cudaMalloc(&d_c, sizeof(double) * n_states));
-  PA_CUDA(cudaMalloc(&d_out, sizeof(double) * n_states));
+  // one persistent scratch buffer (grow-only), carved into the five arrays of a replay batch
+  const size_t ns = (size_t)n_states;
+  const size_t off_n = 0, off_c = off_n + 8 * ns, off_out = off_c + 8 * ns, off_elem = off_out + 8 * ns, off_Z = off_elem + ((4 * ns + 15) & ~size_t(15));
+  const size_t need = off_Z + ns * N;
+  if (need > cap_replay || !d_replay) {
+    if (d_replay) cudaFree(d_replay);
+    d_replay = nullptr;
+    cap_replay = 0;
+    PA_CUDA(cudaMalloc(&d_replay, need));
+    cap_replay = need;
+  }
+  double* d_n = reinterpret_cast<double*>(d_replay + off_n);
+  double* d_c = reinterpret_cast<double*>(d_replay + off_c);
+  double* d_out = reinterpret_cast<double*>(d_replay + off_out);
+  int32_t* d_elem = reinterpret_cast<int32_t*>(d_replay + off_elem);
+  int8_t* d_Z = reinterpret_cast<int8_t*>(d_replay + off_Z);
   PA_CUDA(cudaMemcpyAsync(d_elem, elem, sizeof(int32_t) * n_states, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemcpyAsync(d_Z, Z, (size_t)n_states * N, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemcpyAsync(d_n, n_rate, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
@@ -246,7 +267,6 @@ int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_states, cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaStreamSynchronize(stream));
-  cudaFree(d_elem); cudaFree(d_Z); cudaFree(d_n); cudaFree(d_c); cudaFree(d_out);
   return PA_OK;
 }
 

@@ -31,6 +31,7 @@ struct Engine {
   // device-resident batch
   uint8_t* d_blobs = nullptr;
   int64_t* d_blob_off = nullptr;
+  size_t cap_blobs = 0, cap_blob_off = 0;
 
   // last sampling run
   std::vector<int32_t> run_ids;          // element ids passed to sample()
@@ -53,6 +54,8 @@ struct Engine {
   double* d_init_rates = nullptr;
   uint32_t* d_init_z = nullptr;
   size_t cap_init_rates = 0, cap_init_z = 0;
+  uint8_t* d_replay = nullptr;           // scratch of loglik_replay (grow-only)
+  size_t cap_replay = 0;
   double* h_trace_d = nullptr;           // pinned host copies of the traces of the last run (grow-only)
   uint32_t* h_trace_z = nullptr;
   size_t cap_h_trace_d = 0, cap_h_trace_z = 0;

@@ -393,8 +393,16 @@ int Engine::get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr) {
   tr.l2_rate.assign(d + 5 * T, d + 6 * T);
   tr.Z.assign((size_t)T * N, -1);
   const uint32_t* z = &h_trace_z[(size_t)ch * T * ZW];
-  for (int m = 0; m < T; m++)
-    for (int k = 0; k < n; k++) tr.Z[(size_t)m * N + pl.nodes[k]] = (int8_t)((z[(size_t)m * ZW + (k >> 4)] >> (2 * (k & 15))) & 3);
+  const int32_t* nodes = pl.nodes.data();
+  for (int m = 0; m < T; m++) {
+    int8_t* row = &tr.Z[(size_t)m * N];
+    const uint32_t* zw = z + (size_t)m * ZW;
+    for (int k0 = 0; k0 < n; k0 += 16) {  // one packed word = 16 nodes of the pruned tree, 2 bits each
+      uint32_t word = zw[k0 >> 4];
+      const int kn = std::min(16, n - k0);
+      for (int k = 0; k < kn; k++, word >>= 2) row[nodes[k0 + k]] = (int8_t)(word & 3u);
+    }
+  }
   return PA_OK;
 }
 
@@ -435,10 +443,14 @@ double eval2_main(const Engine& eng, const ElemPlan& pl, int mdl, const ChainTra
   const int N = eng.model.tree.N, num_burn = P.burnin, num_mcmc = P.mcmc, T = num_burn + num_mcmc;
   const bool null_model = (mdl == PA_M0);  // resZ == 0
   std::vector<int> uncertain;
-  for (int s = 0; s < N; s++) {
-    int cnt = 0;
-    for (int i = num_burn; i < T; i++) cnt += tr.Z[(size_t)i * N + s] == Max_Z[s];
-    if (cnt < num_mcmc) uncertain.push_back(s);
+  {
+    std::vector<uint8_t> differs(N, 0);  // a node is uncertain iff some post-burn-in row differs from Max_Z there
+    for (int i = num_burn; i < T; i++) {
+      const int8_t* row = &tr.Z[(size_t)i * N];
+      for (int s = 0; s < N; s++) differs[s] |= (uint8_t)(row[s] != Max_Z[s]);
+    }
+    for (int s = 0; s < N; s++)
+      if (differs[s]) uncertain.push_back(s);
   }
   std::vector<const int8_t*> configZ{Max_Z};
   std::vector<int> num{0};
@@ -581,11 +593,11 @@ int Engine::collect(pa_results* out) {
     std::vector<double> full(T);
     double max_ll = -INFINITY;
     int max_m = -1;
-    for (int m = 0; m < T; m++) {
+    for (int m = num_burn; m < T; m++) {  // only the post-burn-in rows are used (arg-max here, Eval2's averages below)
       full[m] = tr.loglik[m] + 0.0;
       full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
       if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
-      if (m >= num_burn && full[m] > max_ll) {
+      if (full[m] > max_ll) {
         max_ll = full[m];
         max_m = m;
       }
@@ -608,8 +620,24 @@ int Engine::collect(pa_results* out) {
     if (out->post_Z) {
       double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
       std::vector<int> cnt((size_t)N * 4, 0);
-      for (int m = num_burn; m < T; m++)
-        for (int s = 0; s < N; s++) cnt[s * 4 + tr.Z[(size_t)m * N + s] + 1]++;
+      {
+        // per-value passes over the row-major trace (vectorisable compare-and-add) instead of a scattered histogram
+        std::vector<int> c0(N, 0), c1(N, 0), c2(N, 0);
+        for (int m = num_burn; m < T; m++) {
+          const int8_t* row = &tr.Z[(size_t)m * N];
+          for (int s = 0; s < N; s++) {
+            c0[s] += row[s] == 0;
+            c1[s] += row[s] == 1;
+            c2[s] += row[s] == 2;
+          }
+        }
+        for (int s = 0; s < N; s++) {
+          cnt[s * 4 + 1] = c0[s];
+          cnt[s * 4 + 2] = c1[s];
+          cnt[s * 4 + 3] = c2[s];
+          cnt[s * 4] = num_mcmc - c0[s] - c1[s] - c2[s];  // Z == -1: the node is outside the element's pruned tree
+        }
+      }
       for (int s = 0; s < N; s++) {
         if (pl.missing[s]) cnt[s * 4] = num_mcmc;
         for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
