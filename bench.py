@@ -284,6 +284,10 @@ def main():
                 "algorithmic_fma_per_step": fma, "kernel": "chain_kernel",
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+        # BASELINE's second metric: full-tree-equivalent site likelihoods per second on UNCOMPRESSED columns
+        # (sum over upward passes of columns x recomputed internal nodes / (S - 1)), rank 0's share x ranks
+        site_liks = float(cnt["node_site_updates"]) / (tree.S - 1) / (ms_step * 1e-3) * world
+        compression = float(cnt["node_site_updates"]) / max(1.0, float(cnt["node_pattern_updates"]))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step_all, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
@@ -292,6 +296,7 @@ def main():
                            "parallelism": f"elements sharded over {world} GPU(s), no data-path collective, one all_gather of summaries"},
                 "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "pruned_site_liks": {"value": site_liks, "unit": "full-tree-equivalent site likelihoods/s", "columns_per_pattern": compression},
                 "gpu_launches": int(cnt["kernel_launches"]) * args.steps,
                 "clocks": _clock_summary(clocks),
                 "work": {k: int(v) for k, v in cnt.items()}, "accelerated_calls_rank0": n_acc}

@@ -169,6 +169,7 @@ int pa_engine_get_trace(pa_engine* e, int32_t i, int32_t model, pa_trace* out);
  * root evaluations, P(t) builds, history draws, kernel launches. */
 typedef struct pa_counters {
   uint64_t node_pattern_updates, root_evals, pt_builds, history_draws, chain_iterations, kernel_launches;
+  uint64_t node_site_updates; /* like node_pattern_updates, counted on UNCOMPRESSED columns (BASELINE metric "pruned site-liks/sec") */
 } pa_counters;
 int pa_engine_counters(pa_engine* e, pa_counters* out);
 /* SM cycles per phase of the chain kernel, summed over CTAs (thread 0 clock64 deltas): init, trace, history sampling,

@@ -79,7 +79,8 @@ class PaHyper(C.Structure):
 
 class PaCounters(C.Structure):
     _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
-                ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("node_site_updates", C.c_uint64)]
 
 
 EXPORTS = [

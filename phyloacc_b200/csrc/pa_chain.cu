@@ -75,6 +75,9 @@ struct SmemT {
   uint32_t cb[NMAX];          // pair-count descriptor of the branch above node i: child (tip row | internal q) | parent q << 16 | tip << 31
   int ivars[IV_COUNT];
   int nz[18];
+  // work counters and SM cycles per phase (thread 0 only; in shared memory so that they do not occupy registers of every thread)
+  unsigned long long work[6];  // node-pattern updates, root evaluations, P(t) builds, history draws, iterations, node-site updates
+  long long phase[10], t_last;
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
@@ -383,15 +386,21 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
   A.sc_stride = (uint32_t)L.n_max * L.P_max;
   const int n_rows = L.S_rows;
 
-  unsigned long long w_npu = 0, w_root = 0, w_pt = 0, w_hist = 0, w_iter = 0;  // work counters (thread 0)
-  long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, ph6 = 0, ph7 = 0, ph8 = 0, ph9 = 0;  // SM cycles per phase (thread 0)
-  long long t_last = clock64();
-#define PA_PHASE(var)                  \
-  if (tid == 0) {                      \
-    const long long t_now = clock64(); \
-    var += t_now - t_last;             \
-    t_last = t_now;                    \
+  if (tid < 6) S.work[tid] = 0ull;
+  if (tid < 10) S.phase[tid] = 0ll;
+  if (tid == 0) S.t_last = clock64();
+#define PA_PHASE(k)                     \
+  if (tid == 0) {                       \
+    const long long t_now = clock64();  \
+    S.phase[k] += t_now - S.t_last;     \
+    S.t_last = t_now;                   \
   }
+#define w_npu S.work[0]
+#define w_root S.work[1]
+#define w_pt S.work[2]
+#define w_hist S.work[3]
+#define w_iter S.work[4]
+#define w_nsu S.work[5]
 
   for (;;) {
     __syncthreads();
@@ -516,11 +525,12 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       if (tid == 0) {
         S.scal[SC_LL] = ll;
         w_npu += (unsigned long long)n_act * h->P;
+        w_nsu += (unsigned long long)n_act * GG;
         w_root += h->P;
       }
     }
     __syncthreads();
-    PA_PHASE(ph0)
+    PA_PHASE(0)
 
     double* tr_d = L.trace_d + (size_t)chain * 6 * T;
     uint32_t* tr_z = L.trace_z + (size_t)chain * T * L.ZW;
@@ -547,7 +557,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       for (int i = tid; i < n * 3; i += kBD) S.eamb[i] = 0.0;
       const double cur_n = S.scal[SC_N], cur_c = S.scal[SC_C];
       __syncthreads();
-      PA_PHASE(ph1)
+      PA_PHASE(1)
       if (warp == kNW - 1) {
         // The random draws and the prior / Hastings terms of this iteration's two MH steps depend only on the rates and
         // proposal scales at the start of the iteration, not on Z: the last warp (idle below 225 sites) evaluates them
@@ -708,7 +718,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         __syncthreads();
       }
       if (tid == 0) w_hist += (unsigned long long)GG * ni;
-      PA_PHASE(ph2)
+      PA_PHASE(2)
 
       // ---------------- getEmission (bpp_c2.cpp:355-390) fused with the start of Update_Z_subtree (bpp_c.cpp:1186-1200):
       // e_s(k) = sum_bins count * log P_k, then b_s(k) = exp(e_s(k) - max) with state 2 masked on fixZ nodes, and the Z uniforms
@@ -742,7 +752,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         if (!(mx > -CUDART_INF) || mx != mx) S.ivars[IV_ZFALLBACK] = 1;
       }
       __syncthreads();
-      PA_PHASE(ph3)
+      PA_PHASE(3)
 
       // ---------------- Update_Z_subtree (bpp_c.cpp:1204-1293): scaled linear messages by tree level, one warp
       if (warp == 0) {
@@ -800,7 +810,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         }
       }
       __syncthreads();
-      PA_PHASE(ph4)
+      PA_PHASE(4)
 
       // ---------------- changed Z: dirty ancestors, class switch of P(t), class presence
       for (int i = tid; i < n; i += kBD) {
@@ -830,13 +840,14 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         if (tid == 0) {
           S.scal[SC_LL] = ll;
           w_npu += (unsigned long long)n_act * h->P;
+          w_nsu += (unsigned long long)n_act * GG;
           w_root += h->P;
         }
         __syncthreads();
       }
       for (int i = tid; i < n; i += kBD) S.dirty[i] = 0;
       __syncthreads();
-      PA_PHASE(ph5)
+      PA_PHASE(5)
 
       // ---------------- sample_rate: accelerated rate n (cls 2), then conserved rate c (cls 1)  (bpp_c.cpp:930-1176)
       for (int step = 0; step < 2; step++) {
@@ -909,7 +920,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           const long long tp0 = clock64();
           const int n_act = S.ivars[IV_NACT];
           const double ll_new = prune_pass(ev, S, S.Pprop, A, n_act, n_rows, tid);  // log_f_Xz, into the non-current copy
-          if (tid == 0 && !neut) ph8 += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
+          if (tid == 0 && !neut) S.phase[8] += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
           if (warp == 0) {
             const int cnt_nodes = n_act;
             int cnt_cls = 0;  // work counter: lane-parallel, not a serial loop on one thread
@@ -923,6 +934,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
                 S.scal[SC_LL] = ll_new;
               }
               w_npu += (unsigned long long)cnt_nodes * h->P;
+              w_nsu += (unsigned long long)cnt_nodes * GG;
               w_root += h->P;
               w_pt += cnt_cls;
             }
@@ -976,7 +988,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           }
         }
         __syncthreads();
-        if (neut) { PA_PHASE(ph6) } else { PA_PHASE(ph7) }
+        if (neut) { PA_PHASE(6) } else { PA_PHASE(7) }
       }
 
       // ---------------- sample_transition (bpp_c.cpp:522-613): six gamma draws on six lanes
@@ -1014,19 +1026,22 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         Tx[0] = 1 - g; Tx[3] = g;
       }
       __syncthreads();
-      PA_PHASE(ph9)
+      PA_PHASE(9)
     }  // iterations
   }    // chains
 
-  if (tid == 0 && L.counters) {
-    atomicAdd(&L.counters[0], w_npu);
-    atomicAdd(&L.counters[1], w_root);
-    atomicAdd(&L.counters[2], w_pt);
-    atomicAdd(&L.counters[3], w_hist);
-    atomicAdd(&L.counters[4], w_iter);
-    const long long phs[10] = {ph0, ph1, ph2, ph3, ph4, ph5, ph6, ph7, ph8, ph9};
-    for (int k = 0; k < 10; k++) atomicAdd(&L.counters[8 + k], (unsigned long long)phs[k]);
+  __syncthreads();
+  if (L.counters) {
+    if (tid < 6) atomicAdd(&L.counters[tid], S.work[tid]);
+    if (tid < 10) atomicAdd(&L.counters[8 + tid], (unsigned long long)S.phase[tid]);
   }
+#undef PA_PHASE
+#undef w_npu
+#undef w_root
+#undef w_pt
+#undef w_hist
+#undef w_iter
+#undef w_nsu
 }
 
 struct Variant {

@@ -349,6 +349,7 @@ int Engine::fetch_traces() {
   counters.pt_builds = hc[2];
   counters.history_draws = hc[3];
   counters.chain_iterations = hc[4];
+  counters.node_site_updates = hc[5];
   for (int k = 0; k < 10; k++) phase_cycles[k] = hc[8 + k];
   // the last state of every chain becomes the warm start of its next run (Gibbs with UpHyper, bpp_c.cpp:474-485)
   {
