@@ -532,8 +532,6 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
     __syncthreads();
     PA_PHASE(0)
 
-    double* tr_d = L.trace_d + (size_t)chain * 6 * T;
-    uint32_t* tr_z = L.trace_z + (size_t)chain * T * L.ZW;
 
     for (int m = 0; m < T; m++) {
       // ---------------- MonitorChain: trace row m
@@ -543,11 +541,11 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           const int i = w * 16 + k;
           if (i < n) word |= (uint32_t)(S.Z[i] & 3) << (2 * k);
         }
-        tr_z[(size_t)m * L.ZW + w] = word;
+        L.trace_z[((size_t)chain * T + m) * L.ZW + w] = word;
       }
       if (tid < 6) {
         const int src = (tid == 0) ? SC_LL : (tid == 1 ? SC_N : (tid == 2 ? SC_C : (tid == 3 ? SC_G : (tid == 4 ? SC_L : SC_L2))));
-        tr_d[(size_t)tid * T + m] = S.scal[src];
+        L.trace_d[((size_t)chain * 6 + tid) * T + m] = S.scal[src];
       }
       if (m == T - 1) break;
       if (tid == 0) w_iter++;
@@ -555,7 +553,6 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       // ---------------- sample ancestral histories site by site + count parent->child base pairs per branch
       for (int i = tid; i < n * 16; i += kBD) S.cnt[i] = 0;
       for (int i = tid; i < n * 3; i += kBD) S.eamb[i] = 0.0;
-      const double cur_n = S.scal[SC_N], cur_c = S.scal[SC_C];
       __syncthreads();
       PA_PHASE(1)
       if (warp == kNW - 1) {
@@ -822,7 +819,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
             mark_ancestors(S.parent, S.dirty, i);
             S.ivars[IV_ANY_CHANGED] = 1;
             double P16[16];
-            build_P(sd, S.dist[i], class_rate(zn, cur_n, cur_c), true, P16);
+            build_P(sd, S.dist[i], class_rate(zn, S.scal[SC_N], S.scal[SC_C]), true, P16);  // the rates have not moved since the start of the iteration
 #pragma unroll
             for (int e = 0; e < 16; e++) S.Pcur[i * 16 + e] = P16[e];
           }
