@@ -42,10 +42,11 @@ enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_R
 template <int NMAX, int SLOTS_, int BD_, bool STAGE_>
 struct SmemT {
   static constexpr bool STAGE = STAGE_;    // tip codes of the current tile staged in shared memory (false: read from the blob; deep trees)
+  static constexpr bool XS8 = STAGE_;      // sampled bases also kept as a byte matrix (false: the parent's base is read back from the bit planes)
   static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
   static constexpr int SLOTS = SLOTS_;     // temp-stack slots kept in shared memory; results parked deeper are re-read from the arena
-  static constexpr int BD = BD_, CODEROW = BD_ / 2 + 4, XS = BD_ + 4;
-  alignas(16) double Pcur[NMAX * 16];
+  static constexpr int BD = BD_, CODEROW = BD_ / 2 + 4, XS = BD_ + 4, NWARP = BD_ / 32;
+  alignas(16) double Pcur[NMAX * 16];  // current P(t) of every branch; the root's slot holds pi in its first row (history sampling)
   union {  // buffers that are live in disjoint phases of an iteration share storage
     struct { alignas(16) double Pprop[NMAX * 16]; };  // rate steps: proposal P(t)
     struct {                                          // history sampling .. Z update
@@ -58,9 +59,10 @@ struct SmemT {
       alignas(16) double stack[SLOTS * 4 * BD];
       int16_t stack_sc[SLOTS * BD];
     };
-    struct {  // history sampling: sampled bases [internal node][site] (4 = no draw), pattern offsets of the tile's sites
-      alignas(4) uint8_t xs8[NI * XS];
-      uint16_t spat[BD];
+    struct {  // history sampling: bit planes of the sampled bases [internal node][warp = 32 sites]{A, C, G, T} and, on the small
+              // layouts, the same bases as bytes [internal node | one zero row][site] (4 = no draw)
+      alignas(16) uint4 planes[NI * NWARP];
+      alignas(4) uint8_t xs8[XS8 ? (NI + 1) * XS : 4];
     };
   };
   double red[34];
@@ -71,7 +73,9 @@ struct SmemT {
   alignas(16) uint4 ops[NI];  // pruning program, see init
   alignas(16) uint4 act[NI];  // program of the current pass: only the nodes to recompute, operands resolved (build_pass_program)
   int16_t actk[NI];           // their positions in ops
-  alignas(8) uint2 hs[NI];    // history descriptor of internal node q: {node | parent's q << 16 (0xffff root), unused}
+  // history descriptor of internal node q: {node | 0x8000 if not drawn (missing, padding) | row of the parent's sampled bases << 16 (NI = the
+  // zero row, for the root), offset (doubles) of the node's current partials in the arena}
+  alignas(8) uint2 hs[NI + 3];
   uint32_t cb[NMAX];          // pair-count descriptor of the branch above node i: child (tip row | internal q) | parent q << 16 | tip << 31
   int ivars[IV_COUNT];
   int nz[18];
@@ -79,6 +83,7 @@ struct SmemT {
   unsigned long long work[6];  // node-pattern updates, root evaluations, P(t) builds, history draws, iterations, node-site updates
   long long phase[10], t_last;
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
+  int16_t qof[NMAX];  // internal index of a node (-1 for tips)
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
   alignas(4) uint8_t codes[STAGE_ ? NI * CODEROW : 4];
@@ -365,8 +370,34 @@ __device__ __noinline__ void z_update_logspace(SM& S, int n) {
   }
 }
 
+// pair-count pass, rare path: the sites of 32-site word `word` of the current tile at which tip `row` carries an ambiguity code
+// (bits of `am`) contribute log sum_{b in code} P_k(x_parent -> b) to the branch's emissions (bpp_c2.cpp:372-378)
+template <class SM>
+__device__ __noinline__ void count_ambiguous(SM& S, const ElemView& ev, const double* __restrict__ logP, int n_max, int i, uint32_t row, uint32_t qp,
+                                             int site0, int word, uint32_t am) {
+  const int Ppad = ev.h->Ppad;
+  const uint4 pp = S.planes[qp * SM::NWARP + word];
+  while (am) {
+    const int bit = __ffs(am) - 1;
+    am &= am - 1u;
+    if (!(((pp.x | pp.y | pp.z | pp.w) >> bit) & 1u)) continue;  // no base drawn for the parent at this site
+    const uint32_t xp = ((pp.y >> bit) & 1u) + 2u * ((pp.z >> bit) & 1u) + 3u * ((pp.w >> bit) & 1u);
+    const int pat = ev.sitepat[site0 + bit];
+    const uint32_t code4 = ((uint32_t)ev.codes[(size_t)row * (Ppad >> 1) + (pat >> 1)] >> ((pat & 1) * 4)) & 15u;
+#pragma unroll 1
+    for (int kk = 0; kk < 3; kk++) {
+      const double* lp = logP + ((size_t)kk * n_max + i) * 16 + xp * 4;
+      double sum = 0;
+      for (int b = 0; b < 4; b++)
+        if ((code4 >> b) & 1u) sum += exp(lp[b]);
+      atomicAdd(&S.eamb[i * 3 + kk], log(sum));
+    }
+  }
+}
+
 template <int NMAX, int SLOTS, int BD, int MINB, bool STAGE>
 __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
+  static_assert(BD == 256, "the elements' tip planes are laid out for 256-site tiles");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef SmemT<NMAX, SLOTS, BD, STAGE> SM;
   PA_LAYOUT_CONSTANTS(SM);
@@ -439,6 +470,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       S.Z[i] = warm ? (int8_t)((L.init_z[(size_t)chain * L.ZW + (i >> 4)] >> (2 * (i & 15))) & 3u) : (int8_t)((i == root) ? 0 : 1);  // bpp_c.cpp:141-151
       S.dirty[i] = 0;
       S.sel[i] = 0;
+      S.qof[i] = ev.intidx[i];
     }
     // pair-count descriptors: the branch above node i joins the sampled base of its parent with the node's own sampled
     // base (internal node) or its data (tip)
@@ -474,11 +506,14 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         op.w = x_of(c0) | (x_of(c1) << 16);
       }
       S.ops[k] = op;
-      // history descriptors of internal node q = k (post-order): parent's q, and the node's non-missing tip children
+      // history descriptor of internal node q = k (post-order); the root's "parent" is the zero row (base 0 selects the row of
+      // pi kept in the root's slot of Pcur); every partial starts in arena copy 0
       const int sq = ev.intlist[k];
       const int par = ev.parent[sq];
-      S.hs[k] = make_uint2((uint32_t)sq | ((par >= 0 ? (uint32_t)ev.intidx[par] : 0xffffu) << 16), 0u);
+      S.hs[k] = make_uint2((uint32_t)sq | ((ev.flags[sq] & PA_F_MISSING) ? 0x8000u : 0u) | ((par >= 0 ? (uint32_t)ev.intidx[par] : (uint32_t)SM::NI) << 16),
+                           (uint32_t)k * (uint32_t)Ppad * 4u);
     }
+    if (tid < 3) S.hs[ni + tid] = make_uint2(0x8000u, 0u);  // the sampler walks the nodes in groups of four
     if (tid == 0) {
       int nsu = 0;
       while (nsu < ni && ev.su[nsu] >= 0) nsu++;
@@ -518,6 +553,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       }
     }
     __syncthreads();
+    if (tid < 4) S.Pcur[root * 16 + tid] = sd.pi[tid];  // the root has no branch: its first row serves the root draw of the history sampler
     // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in arena copy 0
     {
       const int n_act = make_pass<false>(S, A, Ppad, 0, n_su, tid);
@@ -586,128 +622,99 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         }
       }
       for (int g0 = 0; g0 < GG; g0 += kTile) {
-        const int pb = (int)ev.sitepat[g0] & ~7;  // sites are sorted by pattern: this tile spans < 264 patterns from pb
-        ensure_staged(S, ev, pb, n_rows, tid);
         const int g = g0 + tid;
         const bool valid = g < GG;
-        const int pat = valid ? ev.sitepat[g] : pb;
-        uint32_t gw0 = 0, gw1 = 0;
-        if (h->W >= 1) gw0 = ev.gap[pat];
-        if (h->W >= 2) gw1 = ev.gap[Ppad + pat];
-        const double* gp = A.part + (uint32_t)pat * 4u;
-        S.spat[tid] = (uint16_t)(pat - pb);
+        const int pat = valid ? (int)ev.sitepat[g] : 0;
+        const double* __restrict__ gp = A.part + (uint32_t)pat * 4u;
         uint8_t* xs = S.xs8 + tid;
-        for (int G = (ni - 1) >> 2; G >= 0; G--) {
+        if (SM::XS8) xs[SM::NI * kXS] = 0;
+        const int rootq = ni - 1, Gtop = (ni - 1) >> 2;
+        uint32_t gw = 0;
+        for (int G = Gtop; G >= 0; G--) {
+          if (G == Gtop || (G & 7) == 7) {  // "all-gap" flags of internal nodes 32 * (G >> 3) .. + 31 at this site's pattern (bpp_c.cpp:686-690)
+            const int wi = G >> 3;
+            gw = ev.gap[(size_t)wi * Ppad + pat];
+            if (wi == (rootq >> 5)) gw &= ~(1u << (rootq & 31));  // the root is always drawn (bpp_c.cpp:676-682)
+            if (!valid) gw = 0xffffffffu;                         // lanes beyond the element draw nothing
+          }
           // the partials of the group's nodes do not depend on the draws: fetch them first (one L2 round trip per 4 nodes)
           double2 pa[4], pc[4];
 #pragma unroll
           for (int j = 3; j >= 0; j--) {
-            const int q = 4 * G + j;
-            pa[j] = make_double2(0.0, 0.0);
-            pc[j] = make_double2(0.0, 0.0);
-            if (q < ni && valid) {
-              const int s = S.hs[q].x & 0xffff;
-              const double2* g2 = reinterpret_cast<const double2*>(gp + ((uint32_t)S.sel[s] * A.part_stride + (uint32_t)q * Ppad * 4u));
-              pa[j] = g2[0];
-              pc[j] = g2[1];
-            }
+            const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * G + j].y);
+            pa[j] = g2[0];
+            pc[j] = g2[1];
           }
           const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
 #pragma unroll
           for (int j = 3; j >= 0; j--) {
             const int q = 4 * G + j;
-            if (q >= ni) continue;
             const uint32_t d = S.hs[q].x;
-            const int s = d & 0xffff;
-            if (S.flags[s] & PA_F_MISSING) continue;
-            const uint32_t qp = d >> 16;
-            const bool isroot = (qp == 0xffffu);
-            bool gapbit;
-            if (q < 32) gapbit = (gw0 >> q) & 1u;
-            else if (q < 64) gapbit = (gw1 >> (q - 32)) & 1u;
-            else gapbit = (ev.gap[(size_t)(q >> 5) * Ppad + pat] >> (q & 31)) & 1u;
-            const bool active = valid && (isroot || !gapbit);
-            int x = 4;  // no draw: the node is "all-gap" at this site (bpp_c.cpp:686-690), or the lane has no site
-            if (active) {
-              const int xp = isroot ? 0 : (int)xs[qp * kXS];
-              const double u = u01(j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w)));
-              double p0, p1, p2, p3;
-              if (isroot) {
-                p0 = pa[j].x * S.pi[0]; p1 = pa[j].y * S.pi[1]; p2 = pc[j].x * S.pi[2]; p3 = pc[j].y * S.pi[3];
-              } else {
-                const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
-                const double2 r0 = Pr[0], r1 = Pr[1];
-                p0 = r0.x * pa[j].x; p1 = r0.y * pa[j].y; p2 = r1.x * pc[j].x; p3 = r1.y * pc[j].y;
+            if (d & 0x8000u) continue;  // missing node / padding: uniform over the CTA
+            const uint32_t s = d & 0x7fffu, qp = d >> 16;
+            int x = 4;  // no draw: the node is "all-gap" at this site, or the lane has no site
+            if (!((gw >> (q & 31)) & 1u)) {
+              uint32_t xp;
+              if (SM::XS8) xp = xs[qp * kXS];
+              else if (qp == (uint32_t)SM::NI) xp = 0u;
+              else {
+                const uint4 pp = S.planes[qp * kNW + warp];
+                xp = ((pp.y >> lane) & 1u) + 2u * ((pp.z >> lane) & 1u) + 3u * ((pp.w >> lane) & 1u);
               }
+              const double u = u01(j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w)));
+              const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
+              const double2 r0 = Pr[0], r1 = Pr[1];
+              const double p0 = r0.x * pa[j].x, p1 = r0.y * pa[j].y, p2 = r1.x * pc[j].x, p3 = r1.y * pc[j].y;
               // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
               const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
               x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
             }
-            xs[q * kXS] = (uint8_t)x;
+            if (SM::XS8) xs[q * kXS] = (uint8_t)x;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, x == 0), b1 = __ballot_sync(0xffffffffu, x == 1), b2 = __ballot_sync(0xffffffffu, x == 2),
+                           b3 = __ballot_sync(0xffffffffu, x == 3);
+            if (lane == 0) S.planes[q * kNW + warp] = make_uint4(b0, b1, b2, b3);
+            if (!SM::XS8) __syncwarp();  // the children of q read the planes back
           }
         }
         __syncthreads();
         // ---- parent->child base pairs of every branch over the tile's sites (getEmission's sufficient statistic,
-        // bpp_c2.cpp:355-390): thread = (branch, slice of the sites); 16 bins in 8-bit fields of four registers
+        // bpp_c2.cpp:355-390): thread = (branch, slice of the tile's 32-site words); a bin is the population count of
+        // (parent's plane of base x) & (child's plane of base y); the tips' planes come precomputed with the element
         {
-          const int tile_sites = min(kTile, GG - g0);
+          const int nw = (min(kTile, GG - g0) + 31) >> 5;
           const int nb = n - 1;
-          const int K = max(1, kBD / nb);                               // site slices per branch
-          const int sub = min(128, (((tile_sites + K - 1) / K) + 3) & ~3);  // sites per slice: multiple of 4, <= 128 (8-bit fields)
+          const int K = min(nw, max(1, kBD / nb));  // word slices per branch
+          const size_t tile_row0 = (size_t)(g0 / kTile) * (size_t)h->S;
           for (int task = tid; task < nb * K; task += kBD) {  // more than kBD branches (deep trees): several per thread
-            const int i = task % nb, k = task / nb;
+            const int k = task / nb, i = task - k * nb;
             const uint32_t d = S.cb[i];
-            if (d != 0xffffffffu) {
-              const uint8_t* __restrict__ prow = S.xs8 + ((d >> 16) & 0x7fffu) * kXS;
-              const bool tip = (d >> 31) != 0;
-              const uint8_t* __restrict__ crow =
-                  tip ? (SM::STAGE ? (S.codes + (d & 0xffffu) * kCodeRow) : (ev.codes + (size_t)(d & 0xffffu) * (Ppad >> 1) + (pb >> 1)))
-                      : (S.xs8 + (d & 0xffffu) * kXS);
-              for (int s0 = k * sub; s0 < tile_sites; s0 += K * sub) {
-                const int s1 = min(s0 + sub, tile_sites);
-                uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
-                for (int t = s0; t < s1; t += 4) {
-                  const uint32_t pw = *reinterpret_cast<const uint32_t*>(prow + t);
-                  uint32_t cw = 0u;
-                  if (!tip) cw = *reinterpret_cast<const uint32_t*>(crow + t);
+            if (d == 0xffffffffu) continue;
+            const uint32_t qp = (d >> 16) & 0x7fffu, cx = d & 0xffffu;
+            const bool tip = (d >> 31) != 0;
+            const uint4* __restrict__ prow = S.planes + qp * kNW;
+            const uint4* __restrict__ crow = S.planes + cx * kNW;
+            const size_t tcell = (tile_row0 + cx) * 8;
+            for (int w0 = k; w0 < nw; w0 += 4 * K) {  // at most 4 words (128 sites) per flush: 8-bit fields
+              uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+              const int w1 = min(nw, w0 + 4 * K);
+              for (int w = w0; w < w1; w += K) {
+                const uint4 a = prow[w];
+                uint4 c;
+                if (tip) {
+                  c = __ldg(ev.tipplanes + tcell + w);
+                  const uint32_t am = __ldg(ev.tipamb + tcell + w);
+                  if (am) count_ambiguous(S, ev, logP, L.n_max, i, cx, qp, g0 + 32 * w, w, am);
+                } else c = crow[w];
+                c0 += (uint32_t)__popc(a.x & c.x) + ((uint32_t)__popc(a.x & c.y) << 8) + ((uint32_t)__popc(a.x & c.z) << 16) + ((uint32_t)__popc(a.x & c.w) << 24);
+                c1 += (uint32_t)__popc(a.y & c.x) + ((uint32_t)__popc(a.y & c.y) << 8) + ((uint32_t)__popc(a.y & c.z) << 16) + ((uint32_t)__popc(a.y & c.w) << 24);
+                c2 += (uint32_t)__popc(a.z & c.x) + ((uint32_t)__popc(a.z & c.y) << 8) + ((uint32_t)__popc(a.z & c.z) << 16) + ((uint32_t)__popc(a.z & c.w) << 24);
+                c3 += (uint32_t)__popc(a.w & c.x) + ((uint32_t)__popc(a.w & c.y) << 8) + ((uint32_t)__popc(a.w & c.z) << 16) + ((uint32_t)__popc(a.w & c.w) << 24);
+              }
 #pragma unroll
-                  for (int e = 0; e < 4; e++) {
-                    if (t + e >= s1) break;
-                    const uint32_t xp = (pw >> (8 * e)) & 0xffu;
-                    uint32_t xc;
-                    if (tip) {
-                      const uint32_t po = S.spat[t + e];
-                      const uint32_t code4 = ((uint32_t)crow[po >> 1] >> ((po & 1u) * 4u)) & 15u;
-                      if (code4 == 15u) continue;
-                      if (code4 & (code4 - 1u)) {  // ambiguity code (rare): log sum_{b in code} P_k(x -> b) (bpp_c2.cpp:372-378)
-#pragma unroll 1
-                        for (int kk = 0; kk < 3; kk++) {
-                          const double* lp = logP + ((size_t)kk * L.n_max + i) * 16 + xp * 4;
-                          double sum = 0;
-                          for (int b = 0; b < 4; b++)
-                            if ((code4 >> b) & 1u) sum += exp(lp[b]);
-                          atomicAdd(&S.eamb[i * 3 + kk], log(sum));
-                        }
-                        continue;
-                      }
-                      xc = (uint32_t)__ffs(code4) - 1u;
-                    } else {
-                      xc = (cw >> (8 * e)) & 0xffu;
-                      if (xc >= 4u) continue;
-                    }
-                    const uint32_t bin = xp * 4u + xc, inc = 1u << (8u * (bin & 3u)), w = bin >> 2;
-                    c0 += (w == 0u) ? inc : 0u;
-                    c1 += (w == 1u) ? inc : 0u;
-                    c2 += (w == 2u) ? inc : 0u;
-                    c3 += (w == 3u) ? inc : 0u;
-                  }
-                }
-#pragma unroll
-                for (int b = 0; b < 16; b++) {
-                  const uint32_t cw4 = (b < 4) ? c0 : ((b < 8) ? c1 : ((b < 12) ? c2 : c3));
-                  const uint32_t c = (cw4 >> (8 * (b & 3))) & 0xffu;
-                  if (c) atomicAdd(&S.cnt[i * 16 + b], c);
-                }
+              for (int b = 0; b < 16; b++) {
+                const uint32_t cw4 = (b < 4) ? c0 : ((b < 8) ? c1 : ((b < 12) ? c2 : c3));
+                const uint32_t c = (cw4 >> (8 * (b & 3))) & 0xffu;
+                if (c) atomicAdd(&S.cnt[i * 16 + b], c);
               }
             }
           }
@@ -955,7 +962,11 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           }
         }
         for (int i = tid; i < n; i += kBD) {
-          if (accepted && S.dirty[i]) S.sel[i] ^= 1;  // the proposal's partials become the current ones
+          if (accepted && S.dirty[i]) {  // the proposal's partials become the current ones
+            const uint32_t sl = S.sel[i] ^ 1u, q = (uint32_t)S.qof[i];
+            S.sel[i] = (uint8_t)sl;
+            S.hs[q].y = sl * A.part_stride + q * (uint32_t)Ppad * 4u;
+          }
           S.dirty[i] = 0;
         }
         if (tid == 0) {

@@ -142,6 +142,8 @@ struct ElemView {
   const uint16_t* weights;
   const uint32_t* gap;
   const uint16_t* sitepat;
+  const uint4* tipplanes;
+  const uint32_t* tipamb;
 };
 
 __device__ __forceinline__ ElemView make_view(const uint8_t* blob) {
@@ -166,6 +168,8 @@ __device__ __forceinline__ ElemView make_view(const uint8_t* blob) {
   v.weights = reinterpret_cast<const uint16_t*>(blob + h->off_weights);
   v.gap = reinterpret_cast<const uint32_t*>(blob + h->off_gap);
   v.sitepat = reinterpret_cast<const uint16_t*>(blob + h->off_sitepat);
+  v.tipplanes = reinterpret_cast<const uint4*>(blob + h->off_tipplanes);
+  v.tipamb = reinterpret_cast<const uint32_t*>(blob + h->off_tipamb);
   return v;
 }
 

@@ -833,6 +833,21 @@ void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, in
   const int GGpad = (GG + 31) & ~31;
   std::vector<uint16_t> sitepat(GGpad, 0);
   for (int k = 0; k < GG; k++) sitepat[k] = (uint16_t)sorted_site_pat[k];
+  // the tips' data as bit planes over the sites of each 256-site tile (canonical site order): the pair-count pass of the
+  // chain kernel intersects them with the ballots of the sampled ancestral bases (getEmission's sufficient statistic)
+  const int n_tiles = (GG + 255) / 256;
+  std::vector<uint32_t> tipplanes((size_t)n_tiles * S * 32, 0), tipamb((size_t)n_tiles * S * 8, 0);
+  for (int k = 0; k < GG; k++) {
+    const int tile = k >> 8, w = (k >> 5) & 7, bit = k & 31;
+    const uint8_t* col = &out.pattern_codes[(size_t)sorted_site_pat[k] * S];
+    for (int s = 0; s < S; s++) {
+      const uint8_t c = col[s];
+      if (c == 15) continue;
+      const size_t cell = ((size_t)tile * S + s) * 8 + w;
+      if (c == 1 || c == 2 || c == 4 || c == 8) tipplanes[cell * 4 + (c == 1 ? 0 : (c == 2 ? 1 : (c == 4 ? 2 : 3)))] |= 1u << bit;
+      else tipamb[cell] |= 1u << bit;
+    }
+  }
 
   std::vector<uint8_t>& blob = out.blob;
   blob.assign(sizeof(ElemHeader), 0);
@@ -863,6 +878,8 @@ void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, in
   h.off_weights = put(blob, weights, Ppad);
   h.off_gap = put(blob, gap, gap.size());
   h.off_sitepat = put(blob, sitepat, GGpad);
+  h.off_tipplanes = put(blob, tipplanes, tipplanes.size());
+  h.off_tipamb = put(blob, tipamb, tipamb.size());
   blob.resize((blob.size() + 255) & ~size_t(255), 0);
   h.blob_bytes = (int32_t)blob.size();
   memcpy(blob.data(), &h, sizeof(h));

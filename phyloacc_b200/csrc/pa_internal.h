@@ -60,7 +60,9 @@ struct ElemHeader {
   int32_t off_weights;     // uint16[Ppad]
   int32_t off_gap;         // uint32[W][Ppad]   bit q set <=> internal node q is "all-gap" at this pattern (bpp_c.hpp:417-428)
   int32_t off_sitepat;     // uint16[GGpad]     pattern of each site, sites sorted by (pattern, column)
-  int32_t pad_[2];
+  int32_t off_tipplanes;   // uint32[T][S][8][4] bit planes of the tips' bases per 256-site tile (T = ceil(GG/256)): bit t of word w of
+                           //                    plane b <=> the species' code at site 256*tile + 32*w + t is exactly base b
+  int32_t off_tipamb;      // uint32[T][S][8]    bit set <=> the code there is an ambiguity code (neither one base nor a gap/N)
 };
 
 // Substitution model on the device: P(t) = sum_m exp(eval[m] * t * r) * A[m]  with A[m][j][i] = V[j][m] * Vinv[m][i]
