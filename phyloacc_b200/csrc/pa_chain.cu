@@ -196,6 +196,52 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
 // Thread = pattern.  Every recomputed node is written to the arena copy its descriptor names; the result of a node is
 // forwarded in registers when the next node of the pass is its parent, so the shared-memory stack only holds results
 // that wait for a sibling subtree.  Returns sum_p w_p log L_p.
+// message of one child to its parent: m_j = sum_i P_child(j -> i) L_child(i).  kind 0 missing (1), 1 tip (the code selects / adds
+// columns of P; a gap gives 1), 2 the previous node of the pass (registers), 3 parked on the shared-memory stack, 4 arena
+#define PA_CHILD_MSG(KIND, CH, PAY, M0, M1, M2, M3, SCC)                                                                      \
+  {                                                                                                                            \
+    const double* __restrict__ Pd = Pm + (CH) * 16;                                                                            \
+    if ((KIND) >= 2u) {                                                                                                        \
+      double a0, a1, a2, a3;                                                                                                   \
+      if ((KIND) == 2u) { a0 = o0; a1 = o1; a2 = o2; a3 = o3; SCC = sc; }                                                      \
+      else if ((KIND) == 3u) {                                                                                                 \
+        const double* st = S.stack + (PAY) + tid;                                                                              \
+        a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];                                                          \
+        SCC = S.stack_sc[((PAY) >> 2) + tid];                                                                                  \
+      } else {                                                                                                                 \
+        const double2* g2 = reinterpret_cast<const double2*>(gpart + (PAY));                                                   \
+        const double2 u = g2[0], v = g2[1];                                                                                    \
+        a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;                                                                                \
+        SCC = gsc[(PAY) >> 2];                                                                                                 \
+      }                                                                                                                        \
+      const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pd);                                                   \
+      const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];     \
+      M0 = ((r00.x * a0 + r00.y * a1) + r01.x * a2) + r01.y * a3;                                                              \
+      M1 = ((r10.x * a0 + r10.y * a1) + r11.x * a2) + r11.y * a3;                                                              \
+      M2 = ((r20.x * a0 + r20.y * a1) + r21.x * a2) + r21.y * a3;                                                              \
+      M3 = ((r30.x * a0 + r30.y * a1) + r31.x * a2) + r31.y * a3;                                                              \
+    } else {                                                                                                                   \
+      SCC = 0;                                                                                                                 \
+      const uint32_t code = ((KIND) == 1u) ? (((uint32_t)cp[(PAY)] >> sh) & 15u) : 15u;                                        \
+      if ((code & (code - 1u)) == 0u) {                                                                                        \
+        const int bb = __ffs(code) - 1;                                                                                        \
+        M0 = Pd[bb]; M1 = Pd[4 + bb]; M2 = Pd[8 + bb]; M3 = Pd[12 + bb];                                                       \
+      } else if (code == 15u) {                                                                                                \
+        M0 = 1.0; M1 = 1.0; M2 = 1.0; M3 = 1.0;                                                                                \
+      } else {                                                                                                                 \
+        const double e0 = (code & 1u) ? 1.0 : 0.0, e1 = (code & 2u) ? 1.0 : 0.0, e2 = (code & 4u) ? 1.0 : 0.0, e3 = (code & 8u) ? 1.0 : 0.0; \
+        M0 = ((e0 * Pd[0] + e1 * Pd[1]) + e2 * Pd[2]) + e3 * Pd[3];                                                            \
+        M1 = ((e0 * Pd[4] + e1 * Pd[5]) + e2 * Pd[6]) + e3 * Pd[7];                                                            \
+        M2 = ((e0 * Pd[8] + e1 * Pd[9]) + e2 * Pd[10]) + e3 * Pd[11];                                                          \
+        M3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];                                                        \
+      }                                                                                                                        \
+    }                                                                                                                          \
+  }
+
+// One Felsenstein pass over every pattern of the element (linear space, fp64) through the program in S.act.
+// Thread = pattern.  Every recomputed node is written to the arena copy its descriptor names; the result of a node is
+// forwarded in registers when the next node of the pass is its parent, so the shared-memory stack only holds results
+// that wait for a sibling subtree.  Returns sum_p w_p log L_p.
 template <class SM>
 __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, const Arena& A, int n_act, int n_rows, int tid) {
   PA_LAYOUT_CONSTANTS(SM);
@@ -207,86 +253,20 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
     if (p < P) {
       const uint8_t* __restrict__ cp = SM::STAGE ? (S.codes + (tid >> 1)) : (ev.codes + (p >> 1));
       const int sh = (p & 1) * 4;
-      const double* __restrict__ gpart = A.part + (uint32_t)p * 4u;
-      const int16_t* __restrict__ gsc = A.sc + p;
+      double* __restrict__ gpart = A.part + (uint32_t)p * 4u;
+      int16_t* __restrict__ gsc = A.sc + p;
       double o0 = 1.0, o1 = 1.0, o2 = 1.0, o3 = 1.0;
       int sc = 0;
       uint4 nxt = S.act[0];
       for (int k = 0; k < n_act; k++) {
         const uint4 op = nxt;
         if (k + 1 < n_act) nxt = S.act[k + 1];  // next descriptor is in flight while this node is computed
-        const uint32_t k0 = op.y & 7u, k1 = (op.y >> 3) & 7u;
-        const uint32_t ch0 = (op.y >> 6) & 0x3ffu, ch1 = (op.y >> 16) & 0x3ffu;
-        // ---- gather: partials of internal children (registers / stack / arena), codes of tip children
-        double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0, b0 = 1.0, b1 = 1.0, b2 = 1.0, b3 = 1.0;
-        int sc0 = 0, sc1 = 0;
-        uint32_t code0 = 15u, code1 = 15u;
-        if (k0 == 2u) { a0 = o0; a1 = o1; a2 = o2; a3 = o3; sc0 = sc; }
-        else if (k0 == 3u) {
-          const double* st = S.stack + op.z + tid;
-          a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];
-          sc0 = S.stack_sc[(op.z >> 2) + tid];
-        } else if (k0 == 4u) {
-          const double2* g2 = reinterpret_cast<const double2*>(gpart + op.z);
-          const double2 u = g2[0], v = g2[1];
-          a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;
-          sc0 = gsc[op.z >> 2];
-        } else if (k0 == 1u) code0 = ((uint32_t)cp[op.z] >> sh) & 15u;
-        if (k1 == 2u) { b0 = o0; b1 = o1; b2 = o2; b3 = o3; sc1 = sc; }
-        else if (k1 == 3u) {
-          const double* st = S.stack + op.w + tid;
-          b0 = st[0]; b1 = st[kBD]; b2 = st[2 * kBD]; b3 = st[3 * kBD];
-          sc1 = S.stack_sc[(op.w >> 2) + tid];
-        } else if (k1 == 4u) {
-          const double2* g2 = reinterpret_cast<const double2*>(gpart + op.w);
-          const double2 u = g2[0], v = g2[1];
-          b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y;
-          sc1 = gsc[op.w >> 2];
-        } else if (k1 == 1u) code1 = ((uint32_t)cp[op.w] >> sh) & 15u;
-        // ---- messages: m_j = sum_i P_child(j -> i) L_child(i); tips select / add columns; gaps and missing children give 1
-        double m0 = 1.0, m1 = 1.0, m2 = 1.0, m3 = 1.0, n0 = 1.0, n1 = 1.0, n2 = 1.0, n3 = 1.0;
-        if (k0 >= 2u) {
-          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch0 * 16);
-          const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
-          m0 = ((r00.x * a0 + r00.y * a1) + r01.x * a2) + r01.y * a3;
-          m1 = ((r10.x * a0 + r10.y * a1) + r11.x * a2) + r11.y * a3;
-          m2 = ((r20.x * a0 + r20.y * a1) + r21.x * a2) + r21.y * a3;
-          m3 = ((r30.x * a0 + r30.y * a1) + r31.x * a2) + r31.y * a3;
-        } else if (code0 != 15u) {
-          const double* Pd = Pm + ch0 * 16;
-          if ((code0 & (code0 - 1)) == 0) {
-            const int b = __ffs(code0) - 1;
-            m0 = Pd[b]; m1 = Pd[4 + b]; m2 = Pd[8 + b]; m3 = Pd[12 + b];
-          } else {
-            const double e0 = (code0 & 1u) ? 1.0 : 0.0, e1 = (code0 & 2u) ? 1.0 : 0.0, e2 = (code0 & 4u) ? 1.0 : 0.0, e3 = (code0 & 8u) ? 1.0 : 0.0;
-            m0 = ((e0 * Pd[0] + e1 * Pd[1]) + e2 * Pd[2]) + e3 * Pd[3];
-            m1 = ((e0 * Pd[4] + e1 * Pd[5]) + e2 * Pd[6]) + e3 * Pd[7];
-            m2 = ((e0 * Pd[8] + e1 * Pd[9]) + e2 * Pd[10]) + e3 * Pd[11];
-            m3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];
-          }
-        }
-        if (k1 >= 2u) {
-          const double2* __restrict__ Pc = reinterpret_cast<const double2*>(Pm + ch1 * 16);
-          const double2 r00 = Pc[0], r01 = Pc[1], r10 = Pc[2], r11 = Pc[3], r20 = Pc[4], r21 = Pc[5], r30 = Pc[6], r31 = Pc[7];
-          n0 = ((r00.x * b0 + r00.y * b1) + r01.x * b2) + r01.y * b3;
-          n1 = ((r10.x * b0 + r10.y * b1) + r11.x * b2) + r11.y * b3;
-          n2 = ((r20.x * b0 + r20.y * b1) + r21.x * b2) + r21.y * b3;
-          n3 = ((r30.x * b0 + r30.y * b1) + r31.x * b2) + r31.y * b3;
-        } else if (code1 != 15u) {
-          const double* Pd = Pm + ch1 * 16;
-          if ((code1 & (code1 - 1)) == 0) {
-            const int b = __ffs(code1) - 1;
-            n0 = Pd[b]; n1 = Pd[4 + b]; n2 = Pd[8 + b]; n3 = Pd[12 + b];
-          } else {
-            const double e0 = (code1 & 1u) ? 1.0 : 0.0, e1 = (code1 & 2u) ? 1.0 : 0.0, e2 = (code1 & 4u) ? 1.0 : 0.0, e3 = (code1 & 8u) ? 1.0 : 0.0;
-            n0 = ((e0 * Pd[0] + e1 * Pd[1]) + e2 * Pd[2]) + e3 * Pd[3];
-            n1 = ((e0 * Pd[4] + e1 * Pd[5]) + e2 * Pd[6]) + e3 * Pd[7];
-            n2 = ((e0 * Pd[8] + e1 * Pd[9]) + e2 * Pd[10]) + e3 * Pd[11];
-            n3 = ((e0 * Pd[12] + e1 * Pd[13]) + e2 * Pd[14]) + e3 * Pd[15];
-          }
-        }
+        double m0, m1, m2, m3, n0, n1, n2, n3;
+        int sc0, sc1;
+        PA_CHILD_MSG(op.y & 7u, (op.y >> 6) & 0x3ffu, op.z, m0, m1, m2, m3, sc0)
+        PA_CHILD_MSG((op.y >> 3) & 7u, (op.y >> 16) & 0x3ffu, op.w, n0, n1, n2, n3, sc1)
         // child 0's factor is applied first, then child 1's (same order as the reference's accumulation)
-        o0 = (1.0 * m0) * n0; o1 = (1.0 * m1) * n1; o2 = (1.0 * m2) * n2; o3 = (1.0 * m3) * n3;
+        o0 = m0 * n0; o1 = m1 * n1; o2 = m2 * n2; o3 = m3 * n3;
         sc = sc0 + sc1;
         // rescale by 2^256 when every entry dropped below 2^-256 (compare high words: all values are >= 0)
         const int hm = max(max(__double2hiint(o0), __double2hiint(o1)), max(__double2hiint(o2), __double2hiint(o3)));
@@ -300,10 +280,10 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
           st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
           S.stack_sc[park * kBD + tid] = (int16_t)sc;
         }
-        double2* g2 = reinterpret_cast<double2*>(const_cast<double*>(gpart) + op.x);
+        double2* g2 = reinterpret_cast<double2*>(gpart + op.x);
         g2[0] = make_double2(o0, o1);
         g2[1] = make_double2(o2, o3);
-        const_cast<int16_t*>(gsc)[op.x >> 2] = (int16_t)sc;
+        gsc[op.x >> 2] = (int16_t)sc;
       }
       // the last node of the program is the root (or nothing was computed: missing root -> likelihood 1)
       const double lik = ((S.pi[0] * o0 + S.pi[1] * o1) + S.pi[2] * o2) + S.pi[3] * o3;
@@ -312,6 +292,7 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
   }
   return block_sum(acc, S.red, tid, kBD);
 }
+#undef PA_CHILD_MSG
 
 // build the program of a pass on warp 0 and publish its length (one barrier)
 template <bool USE_DIRTY, class SM>
