@@ -37,7 +37,7 @@ namespace {
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R,
        // scalars of the two MH steps, computed ahead of time by the last warp while the others sample histories
        SC_PRE_R_N = 16, SC_PRE_PROP_N, SC_PRE_PRIOR_N, SC_PRE_MH_N, SC_PRE_R_C, SC_PRE_PROP_C, SC_PRE_PRIOR_C, SC_PRE_MH_C, SC_COUNT = 24 };
-enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_COUNT = 16 };
+enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_KSLICE, IV_COUNT = 16 };
 
 template <int NMAX, int SLOTS_, int BD_, bool STAGE_>
 struct SmemT {
@@ -84,6 +84,7 @@ struct SmemT {
   long long phase[10], t_last;
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   int16_t qof[NMAX];  // internal index of a node (-1 for tips)
+  uint16_t tk[BD_];   // pair-count pass: thread -> branch | word slice << 8 (trees with at most 128 branches)
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
   alignas(4) uint8_t codes[STAGE_ ? NI * CODEROW : 4];
@@ -495,6 +496,11 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
                            (uint32_t)k * (uint32_t)Ppad * 4u);
     }
     if (tid < 3) S.hs[ni + tid] = make_uint2(0x8000u, 0u);  // the sampler walks the nodes in groups of four
+    {  // pair-count pass: word slices per branch and the thread -> (branch, slice) map (no divisions in the iteration loop)
+      const int nb = n - 1, K = max(1, kBD / nb);
+      S.tk[tid] = (uint16_t)((K > 1 && tid < nb * K) ? ((tid % nb) | ((tid / nb) << 8)) : 0xffff);
+      if (tid == 0) S.ivars[IV_KSLICE] = K;
+    }
     if (tid == 0) {
       int nsu = 0;
       while (nsu < ni && ev.su[nsu] >= 0) nsu++;
@@ -610,51 +616,69 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         uint8_t* xs = S.xs8 + tid;
         if (SM::XS8) xs[SM::NI * kXS] = 0;
         const int rootq = ni - 1, Gtop = (ni - 1) >> 2;
-        uint32_t gw = 0;
-        for (int G = Gtop; G >= 0; G--) {
-          if (G == Gtop || (G & 7) == 7) {  // "all-gap" flags of internal nodes 32 * (G >> 3) .. + 31 at this site's pattern (bpp_c.cpp:686-690)
-            const int wi = G >> 3;
-            gw = ev.gap[(size_t)wi * Ppad + pat];
-            if (wi == (rootq >> 5)) gw &= ~(1u << (rootq & 31));  // the root is always drawn (bpp_c.cpp:676-682)
-            if (!valid) gw = 0xffffffffu;                         // lanes beyond the element draw nothing
-          }
-          // the partials of the group's nodes do not depend on the draws: fetch them first (one L2 round trip per 4 nodes)
-          double2 pa[4], pc[4];
+        // warps beyond the element's last site have nothing to draw (their words of the planes are never read)
+        if (g0 + (tid & ~31) < GG) {
+          uint32_t gw = 0;
+          for (int G = Gtop; G >= 0; G--) {
+            if (G == Gtop || (G & 7) == 7) {  // "all-gap" flags of internal nodes 32 * (G >> 3) .. + 31 at this site's pattern (bpp_c.cpp:686-690)
+              const int wi = G >> 3;
+              gw = ev.gap[(size_t)wi * Ppad + pat];
+              if (wi == (rootq >> 5)) gw &= ~(1u << (rootq & 31));  // the root is always drawn (bpp_c.cpp:676-682)
+              if (!valid) gw = 0xffffffffu;                         // lanes beyond the element draw nothing
+            }
+            // everything the group's four nodes read is fetched before anything is stored: their partials (one L2 round trip), their
+            // descriptors and the sampled bases of parents outside the group; a parent inside the group is forwarded in registers
+            uint2 d[4];
+            double2 pa[4], pc[4];
+            uint32_t xpar[4];
 #pragma unroll
-          for (int j = 3; j >= 0; j--) {
-            const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * G + j].y);
-            pa[j] = g2[0];
-            pc[j] = g2[1];
-          }
-          const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
+            for (int j = 3; j >= 0; j--) {
+              d[j] = S.hs[4 * G + j];
+              const double2* g2 = reinterpret_cast<const double2*>(gp + d[j].y);
+              pa[j] = g2[0];
+              pc[j] = g2[1];
+            }
 #pragma unroll
-          for (int j = 3; j >= 0; j--) {
-            const int q = 4 * G + j;
-            const uint32_t d = S.hs[q].x;
-            if (d & 0x8000u) continue;  // missing node / padding: uniform over the CTA
-            const uint32_t s = d & 0x7fffu, qp = d >> 16;
-            int x = 4;  // no draw: the node is "all-gap" at this site, or the lane has no site
-            if (!((gw >> (q & 31)) & 1u)) {
-              uint32_t xp;
-              if (SM::XS8) xp = xs[qp * kXS];
-              else if (qp == (uint32_t)SM::NI) xp = 0u;
+            for (int j = 3; j >= 0; j--) {
+              const uint32_t qp = d[j].x >> 16;
+              if (SM::XS8) xpar[j] = xs[qp * kXS];
+              else if (qp >= (uint32_t)SM::NI || (int)(qp >> 2) == G) xpar[j] = 0u;
               else {
                 const uint4 pp = S.planes[qp * kNW + warp];
-                xp = ((pp.y >> lane) & 1u) + 2u * ((pp.z >> lane) & 1u) + 3u * ((pp.w >> lane) & 1u);
+                xpar[j] = ((pp.y >> lane) & 1u) + 2u * ((pp.z >> lane) & 1u) + 3u * ((pp.w >> lane) & 1u);
               }
+            }
+            const uint4 rnd = philox4(cp.seed, key, (uint32_t)g, (uint32_t)G, (uint32_t)m, PA_ST_HIST);
+            const uint32_t gbits = gw >> ((4 * G) & 31);
+            int x[4];
+#pragma unroll
+            for (int j = 3; j >= 0; j--) {
+              const uint32_t s = d[j].x & 0x7fffu, qp = d[j].x >> 16;
+              uint32_t xp = xpar[j];
+#pragma unroll
+              for (int jj = 3; jj > j; jj--)
+                if (qp == (uint32_t)(4 * G + jj)) xp = (uint32_t)x[jj];
+              // branch-free, so that the four draws overlap: a node that is not drawn (missing / padding, "all-gap" at this site, lane
+              // without a site) evaluates the same expressions on whatever it fetched and discards the result
               const double u = u01(j == 0 ? rnd.x : (j == 1 ? rnd.y : (j == 2 ? rnd.z : rnd.w)));
-              const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + xp * 4);
+              const double2* Pr = reinterpret_cast<const double2*>(S.Pcur + s * 16 + (xp & 3u) * 4);
               const double2 r0 = Pr[0], r1 = Pr[1];
               const double p0 = r0.x * pa[j].x, p1 = r0.y * pa[j].y, p2 = r1.x * pc[j].x, p3 = r1.y * pc[j].y;
               // first k with u*tot < cumsum_k == number of cumulative sums not exceeding u*tot
               const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
-              x = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
+              const int xd = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
+              x[j] = ((d[j].x & 0x8000u) || ((gbits >> j) & 1u)) ? 4 : xd;  // 4 = no draw
             }
-            if (SM::XS8) xs[q * kXS] = (uint8_t)x;
-            const uint32_t b0 = __ballot_sync(0xffffffffu, x == 0), b1 = __ballot_sync(0xffffffffu, x == 1), b2 = __ballot_sync(0xffffffffu, x == 2),
-                           b3 = __ballot_sync(0xffffffffu, x == 3);
-            if (lane == 0) S.planes[q * kNW + warp] = make_uint4(b0, b1, b2, b3);
-            if (!SM::XS8) __syncwarp();  // the children of q read the planes back
+#pragma unroll
+            for (int j = 3; j >= 0; j--) {
+              const int q = 4 * G + j;
+              if (d[j].x & 0x8000u) continue;  // uniform over the CTA
+              if (SM::XS8) xs[q * kXS] = (uint8_t)x[j];
+              const uint32_t b0 = __ballot_sync(0xffffffffu, x[j] == 0), b1 = __ballot_sync(0xffffffffu, x[j] == 1),
+                             b2 = __ballot_sync(0xffffffffu, x[j] == 2), b3 = __ballot_sync(0xffffffffu, x[j] == 3);
+              if (lane == 0) S.planes[q * kNW + warp] = make_uint4(b0, b1, b2, b3);
+            }
+            if (!SM::XS8) __syncwarp();  // the nodes' children read the planes back
           }
         }
         __syncthreads();
@@ -664,10 +688,15 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         {
           const int nw = (min(kTile, GG - g0) + 31) >> 5;
           const int nb = n - 1;
-          const int K = min(nw, max(1, kBD / nb));  // word slices per branch
+          const int K = S.ivars[IV_KSLICE];  // word slices per branch
           const size_t tile_row0 = (size_t)(g0 / kTile) * (size_t)h->S;
-          for (int task = tid; task < nb * K; task += kBD) {  // more than kBD branches (deep trees): several per thread
-            const int k = task / nb, i = task - k * nb;
+          for (int task = tid; task < nb * K; task += kBD) {  // more than kBD / 2 branches (deep trees): one slice, several branches per thread
+            int k = 0, i = task;
+            if (K > 1) {
+              const uint32_t t = S.tk[tid];
+              k = t >> 8;
+              i = t & 0xffu;
+            }
             const uint32_t d = S.cb[i];
             if (d == 0xffffffffu) continue;
             const uint32_t qp = (d >> 16) & 0x7fffu, cx = d & 0xffffu;
@@ -933,7 +962,10 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           for (int task = tid; task < 4 * (n - 1); task += kBD) {
             const int i = task >> 2, j = task & 3;
             double r0, r1, r2, r3;
-            build_P_row(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
+            if (accepted && S.Z[i] == cls) {  // the accepted proposal's rows are still in Pprop (same arithmetic, same values)
+              const double* pp = S.Pprop + i * 16 + j * 4;
+              r0 = pp[0]; r1 = pp[1]; r2 = pp[2]; r3 = pp[3];
+            } else build_P_row(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
             double* lp = logP + ((size_t)cls * L.n_max + i) * 16 + j * 4;
             lp[0] = log(r0); lp[1] = log(r1); lp[2] = log(r2); lp[3] = log(r3);
             if (S.Z[i] == cls) {
