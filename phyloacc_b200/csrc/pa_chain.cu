@@ -864,7 +864,8 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       PA_PHASE(5)
 
       // ---------------- sample_rate: accelerated rate n (cls 2), then conserved rate c (cls 1)  (bpp_c.cpp:930-1176)
-      for (int step = 0; step < 2; step++) {
+      // (under M0 no branch can be accelerated and n is not drawn from its prior, bpp_c.cpp:940-964: the n step is a no-op)
+      for (int step = (resZ == 0) ? 1 : 0; step < 2; step++) {
         const bool neut = (step == 0);
         const int cls = neut ? 2 : 1;
         const uint32_t which = neut ? 0u : 1u;
@@ -924,13 +925,52 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
             const int i = task >> 2, j = task & 3;
             double* pp = S.Pprop + i * 16 + j * 4;
             if (S.Z[i] == cls) {
-              build_P_row(sd, S.dist[i], proposal, j, pp[0], pp[1], pp[2], pp[3]);
+              build_P_row_quad(sd, S.dist[i], proposal, j, pp[0], pp[1], pp[2], pp[3]);  // task & 3 == lane & 3
             } else {
               const double* pc = S.Pcur + i * 16 + j * 4;
               pp[0] = pc[0]; pp[1] = pc[1]; pp[2] = pc[2]; pp[3] = pc[3];
             }
           }
           __syncthreads();
+        }
+        {
+          // ---------------- sample_transition (bpp_c.cpp:522-613).  g, l, l2 depend on Z only and nothing reads them before the next
+          // iteration: the last warp (no patterns below 225) draws them while the others run the c-rate pruning pass
+          if (!neut && warp == kNW - 1) {
+            int c10 = 0, c20 = 0, c00 = 0, f21 = 0, f11 = 0, f12 = 0, f22 = 0;  // nZ(child, parent); f*: rows with fixZ != 1 only (bpp_c.cpp:541-552)
+            for (int i = lane; i < n - 1; i += 32) {
+              const int k = S.Z[i] * 3 + S.Z[S.parent[i]];
+              const bool fr = !S.fix[i];
+              c10 += (k == 3); c20 += (k == 6); c00 += (k == 0);
+              f21 += (fr && k == 7); f11 += (fr && k == 4); f12 += (fr && k == 5); f22 += (fr && k == 8);
+            }
+            c10 = __reduce_add_sync(0xffffffffu, c10); c20 = __reduce_add_sync(0xffffffffu, c20); c00 = __reduce_add_sync(0xffffffffu, c00);
+            f21 = __reduce_add_sync(0xffffffffu, f21); f11 = __reduce_add_sync(0xffffffffu, f11); f12 = __reduce_add_sync(0xffffffffu, f12);
+            f22 = __reduce_add_sync(0xffffffffu, f22);
+            const int whichb = lane >> 1;  // 0: g, 1: l, 2: l2; six gamma draws on six lanes
+            double a = 1.0, b = 1.0;
+            if (whichb == 0) { a = cp.prior_g_a + c10 + c20; b = cp.prior_g_b + c00; }
+            else if (whichb == 1) { a = cp.prior_l_a + f21; b = cp.prior_l_b + f11; }
+            else if (whichb == 2) { a = cp.prior_l2_a + f12; b = cp.prior_l2_b + f22; }
+            double x = 0.0;
+            if (lane < 6 && !(whichb == 2 && cp.prior_l2_a == 0))
+              x = sched_gamma_ol(cp.seed, key, (uint32_t)whichb, (lane & 1) ? 4096u : 0u, (uint32_t)m, PA_ST_TRANS, (lane & 1) ? b : a, 1.0);
+            const double y = __shfl_down_sync(0xffffffffu, x, 1);
+            const double beta = x / (x + y);
+            const double g = __shfl_sync(0xffffffffu, beta, 0), l = __shfl_sync(0xffffffffu, beta, 2);
+            const double l2 = (cp.prior_l2_a == 0) ? 0.0 : __shfl_sync(0xffffffffu, beta, 4);
+            if (lane == 0) {
+              S.scal[SC_G] = g; S.scal[SC_L] = l; S.scal[SC_L2] = l2;
+              double* Tf = S.T;
+              double* Tx = S.T + 9;
+              const double yy = 1 - l;
+              Tf[0] = 1 - g; Tf[3] = g; Tf[4] = yy; Tf[7] = 1 - yy; Tf[5] = l2; Tf[8] = 1 - l2;
+              Tx[0] = 1 - g; Tx[3] = g;
+            }
+          }
+        }
+        if (S.ivars[IV_VALID]) {
+          const double proposal = S.scal[SC_PROPOSAL];
           const long long tp0 = clock64();
           const int n_act = S.ivars[IV_NACT];
           const double ll_new = prune_pass(ev, S, S.Pprop, A, n_act, n_rows, tid);  // log_f_Xz, into the non-current copy
@@ -965,7 +1005,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
             if (accepted && S.Z[i] == cls) {  // the accepted proposal's rows are still in Pprop (same arithmetic, same values)
               const double* pp = S.Pprop + i * 16 + j * 4;
               r0 = pp[0]; r1 = pp[1]; r2 = pp[2]; r3 = pp[3];
-            } else build_P_row(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
+            } else build_P_row_quad(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
             double* lp = logP + ((size_t)cls * L.n_max + i) * 16 + j * 4;
             lp[0] = log(r0); lp[1] = log(r1); lp[2] = log(r2); lp[3] = log(r3);
             if (S.Z[i] == cls) {
@@ -1012,41 +1052,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         if (neut) { PA_PHASE(6) } else { PA_PHASE(7) }
       }
 
-      // ---------------- sample_transition (bpp_c.cpp:522-613): six gamma draws on six lanes
-      if (tid < 18) S.nz[tid] = 0;
-      __syncthreads();
-      for (int i = tid; i < n - 1; i += kBD) {
-        const int k = S.Z[i] * 3 + S.Z[S.parent[i]];
-        atomicAdd(&S.nz[k], 1);
-        if (!S.fix[i]) atomicAdd(&S.nz[9 + k], 1);
-      }
-      __syncthreads();
-      if (warp == 0) {
-        const int* nZ = S.nz;
-        const int* nF = S.nz + 9;
-        const int whichb = lane >> 1;  // 0: g, 1: l, 2: l2
-        double a = 1.0, b = 1.0;
-        if (whichb == 0) { a = cp.prior_g_a + nZ[1 * 3 + 0] + nZ[2 * 3 + 0]; b = cp.prior_g_b + nZ[0]; }
-        else if (whichb == 1) { a = cp.prior_l_a + nF[2 * 3 + 1]; b = cp.prior_l_b + nF[1 * 3 + 1]; }
-        else if (whichb == 2) { a = cp.prior_l2_a + nF[1 * 3 + 2]; b = cp.prior_l2_b + nF[2 * 3 + 2]; }
-        double x = 0.0;
-        if (lane < 6 && !(whichb == 2 && cp.prior_l2_a == 0))
-          x = sched_gamma_ol(cp.seed, key, (uint32_t)whichb, (lane & 1) ? 4096u : 0u, (uint32_t)m, PA_ST_TRANS, (lane & 1) ? b : a, 1.0);
-        const double y = __shfl_down_sync(0xffffffffu, x, 1);
-        if (lane == 0) S.scal[SC_G] = x / (x + y);
-        if (lane == 2) S.scal[SC_L] = x / (x + y);
-        if (lane == 4) S.scal[SC_L2] = (cp.prior_l2_a == 0) ? 0.0 : x / (x + y);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        const double g = S.scal[SC_G], l = S.scal[SC_L], l2 = S.scal[SC_L2];
-        double* Tf = S.T;
-        double* Tx = S.T + 9;
-        const double y = 1 - l;
-        Tf[0] = 1 - g; Tf[3] = g; Tf[4] = y; Tf[7] = 1 - y; Tf[5] = l2; Tf[8] = 1 - l2;
-        Tx[0] = 1 - g; Tx[3] = g;
-      }
-      __syncthreads();
+      // (sample_transition ran on the last warp next to the rate steps, see above)
       PA_PHASE(9)
     }  // iterations
   }    // chains

@@ -121,6 +121,24 @@ __device__ __forceinline__ void build_P_row(const SubstDev& sd, double t, double
   r3 = ((e0 * sd.A[0][k + 3] + e1 * sd.A[1][k + 3]) + e2 * sd.A[2][k + 3]) + e3 * sd.A[3][k + 3];
 }
 
+// build_P_row for four adjacent lanes that hold rows 0..3 of the same branch (lane & 3 == j, all four converged): each lane
+// evaluates one of the four exponentials and the quad exchanges them -- same expressions, same values as build_P_row
+__device__ __forceinline__ void build_P_row_quad(const SubstDev& sd, double t, double rate, int j, double& r0, double& r1, double& r2, double& r3) {
+  if (!(t > 1e-10)) {
+    r0 = (j == 0) ? 1.0 : 0.0; r1 = (j == 1) ? 1.0 : 0.0; r2 = (j == 2) ? 1.0 : 0.0; r3 = (j == 3) ? 1.0 : 0.0;
+    return;
+  }
+  const unsigned mask = __activemask();
+  const double ej = exp(sd.eval[j] * t * rate);
+  const int base = (int)(threadIdx.x & 28u);
+  const double e0 = __shfl_sync(mask, ej, base), e1 = __shfl_sync(mask, ej, base + 1), e2 = __shfl_sync(mask, ej, base + 2), e3 = __shfl_sync(mask, ej, base + 3);
+  const int k = j * 4;
+  r0 = ((e0 * sd.A[0][k] + e1 * sd.A[1][k]) + e2 * sd.A[2][k]) + e3 * sd.A[3][k];
+  r1 = ((e0 * sd.A[0][k + 1] + e1 * sd.A[1][k + 1]) + e2 * sd.A[2][k + 1]) + e3 * sd.A[3][k + 1];
+  r2 = ((e0 * sd.A[0][k + 2] + e1 * sd.A[1][k + 2]) + e2 * sd.A[2][k + 2]) + e3 * sd.A[3][k + 2];
+  r3 = ((e0 * sd.A[0][k + 3] + e1 * sd.A[1][k + 3]) + e2 * sd.A[2][k + 3]) + e3 * sd.A[3][k + 3];
+}
+
 // ---------------------------------------------------------------- element view (pointers into the blob)
 struct ElemView {
   const ElemHeader* h;
