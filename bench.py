@@ -270,16 +270,22 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_bytes = float(eng_blob_bytes(eng, ids)) + d2h  # alignment streamed once + trace write-back
-        # DRAM traffic of the chain kernel per launch: measured once under ncu (profiles/r1_v8_traffic.json, bytes per
+        # DRAM traffic of the chain kernel per launch: measured once under ncu (newest profiles/r*_v*_traffic.json, bytes per
         # chain-iteration of this workload) and scaled to this launch's chain-iterations; null when the file is absent
-        traffic = None
+        traffic, traffic_file = None, None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_v8_traffic.json")) as f:
+            import glob
+            import re
+
+            cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_v*_traffic.json")),
+                           key=lambda q: [int(x) for x in re.findall(r"\d+", os.path.basename(q))])
+            traffic_file = os.path.basename(cands[-1])
+            with open(cands[-1]) as f:
                 traffic = float(json.load(f)["dram_bytes_per_chain_iteration"]) * float(cnt["chain_iterations"])
         except Exception:
             pass
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write of one bench-size chain_kernel launch (profiles/r1_v8_traffic.json)",
+                "traffic": traffic, "traffic_source": f"ncu dram__bytes_read+write of one bench-size chain_kernel launch (profiles/{traffic_file})",
                 "peak_source": "measured live: register-resident DFMA micro-benchmark (pa_device_fp64_peak)",
                 "algorithmic_fma_per_step": fma, "kernel": "chain_kernel",
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
