@@ -65,6 +65,7 @@ struct SmemT {
       alignas(4) uint8_t xs8[XS8 ? (NI + 1) * XS : 4];
     };
   };
+  ElemView ev;  // pointers into the element's blob
   double red[34];
   double dist[NMAX], uz[NMAX];
   double scal[SC_COUNT];
@@ -428,7 +429,10 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
     const int elem = L.chain_list[2 * chain], mdl = L.chain_list[2 * chain + 1];
     const int resZ = (mdl == PA_M0) ? 0 : (mdl == PA_M1 ? 2 : 1);
     const uint32_t key = (uint32_t)elem * 4u + (uint32_t)mdl;
-    const ElemView ev = make_view(L.blobs + L.blob_off[elem]);
+    // the element's array pointers live in shared memory: in registers they spill, and local memory misses the (small) L1 here
+    if (tid == 0) S.ev = make_view(L.blobs + L.blob_off[elem]);
+    __syncthreads();
+    const ElemView& ev = S.ev;
     const ElemHeader* h = ev.h;
     const int n = h->n, ni = h->ni, GG = h->GG, Ppad = h->Ppad, root = n - 1;
     const int T = L.T;
@@ -619,6 +623,15 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
         // warps beyond the element's last site have nothing to draw (their words of the planes are never read)
         if (g0 + (tid & ~31) < GG) {
           uint32_t gw = 0;
+          // the partials of a group's four nodes do not depend on the draws: they are requested while the previous group's results
+          // are being stored and this group's random numbers are generated (one L2 / HBM round trip per 4 nodes)
+          double2 pa[4], pc[4];
+#pragma unroll
+          for (int j = 3; j >= 0; j--) {
+            const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * Gtop + j].y);
+            pa[j] = g2[0];
+            pc[j] = g2[1];
+          }
           for (int G = Gtop; G >= 0; G--) {
             if (G == Gtop || (G & 7) == 7) {  // "all-gap" flags of internal nodes 32 * (G >> 3) .. + 31 at this site's pattern (bpp_c.cpp:686-690)
               const int wi = G >> 3;
@@ -626,18 +639,12 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
               if (wi == (rootq >> 5)) gw &= ~(1u << (rootq & 31));  // the root is always drawn (bpp_c.cpp:676-682)
               if (!valid) gw = 0xffffffffu;                         // lanes beyond the element draw nothing
             }
-            // everything the group's four nodes read is fetched before anything is stored: their partials (one L2 round trip), their
-            // descriptors and the sampled bases of parents outside the group; a parent inside the group is forwarded in registers
+            // everything the group's four nodes read is fetched before anything is stored: their descriptors and the sampled bases of
+            // parents outside the group; a parent inside the group is forwarded in registers
             uint2 d[4];
-            double2 pa[4], pc[4];
             uint32_t xpar[4];
 #pragma unroll
-            for (int j = 3; j >= 0; j--) {
-              d[j] = S.hs[4 * G + j];
-              const double2* g2 = reinterpret_cast<const double2*>(gp + d[j].y);
-              pa[j] = g2[0];
-              pc[j] = g2[1];
-            }
+            for (int j = 3; j >= 0; j--) d[j] = S.hs[4 * G + j];
 #pragma unroll
             for (int j = 3; j >= 0; j--) {
               const uint32_t qp = d[j].x >> 16;
@@ -668,6 +675,14 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
               const double c1 = p0, c2 = c1 + p1, c3 = c2 + p2, xu = u * (c3 + p3);
               const int xd = (int)(xu >= c1) + (int)(xu >= c2) + (int)(xu >= c3);
               x[j] = ((d[j].x & 0x8000u) || ((gbits >> j) & 1u)) ? 4 : xd;  // 4 = no draw
+            }
+            if (G > 0) {
+#pragma unroll
+              for (int j = 3; j >= 0; j--) {
+                const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * (G - 1) + j].y);
+                pa[j] = g2[0];
+                pc[j] = g2[1];
+              }
             }
 #pragma unroll
             for (int j = 3; j >= 0; j--) {
@@ -744,11 +759,20 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           if (S.flags[i] & PA_F_MISSING) e = (k == 1) ? cp.log_constomis : 0.0;
           else {
             e = S.eamb[task];
-            const double* lp = logP + ((size_t)k * L.n_max + i) * 16;
-#pragma unroll 4
-            for (int b = 0; b < 16; b++) {
-              const uint32_t c = S.cnt[i * 16 + b];
-              if (c) e += (double)c * lp[b];
+            // the 16 log P entries come in one round trip (the table lives in the arena); a bin with no pairs adds nothing (its
+            // log P may be -inf: identity P(t) of a zero-length branch)
+            const double2* lp2 = reinterpret_cast<const double2*>(logP + ((size_t)k * L.n_max + i) * 16);
+            double2 lp[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) lp[b] = lp2[b];
+            const uint4* c4 = reinterpret_cast<const uint4*>(&S.cnt[i * 16]);
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+              const uint4 cw = c4[w];
+              if (cw.x) e += (double)cw.x * lp[2 * w].x;
+              if (cw.y) e += (double)cw.y * lp[2 * w].y;
+              if (cw.z) e += (double)cw.z * lp[2 * w + 1].x;
+              if (cw.w) e += (double)cw.w * lp[2 * w + 1].y;
             }
           }
         }

@@ -164,3 +164,26 @@ def test_balanced_tree_parks_deeper_than_the_shared_memory_stack(native_lib, ora
     assert max(eng.element_info(c)["n_slots"] for c in range(3)) > 4
     assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2]) >= 6
     eng.close()
+
+
+@pytest.mark.parametrize("S", [14, 110, 130])
+def test_ambiguity_codes_and_several_site_tiles_match_oracle(native_lib, oracle_lib, tmp_path, S):
+    """Elements longer than one 256-site tile with ambiguity-coded tips (r, y, k, m, s, w): the pair-count pass takes the tips from
+    the per-tile bit planes of the element blob, ambiguous sites through the out-of-line path (bpp_c2.cpp:372-378); S = 130 runs on
+    a deep-tree layout, where the sampled bases exist only as bit planes."""
+    from phyloacc_b200 import synth
+
+    tree = synth.make_tree(S=S, seed=11, n_out=max(2, S // 6), n_target=max(2, S // 5))
+    batch = synth.simulate(tree, C=3, length=100, seed=8, lengths=[300, 521, 64], gap_frac=0.03, missing_frac=0.02, ambig_frac=0.02)
+    cfg = synth.write_files(batch, str(tmp_path), prefix="amb", params=dict(BURNIN=3, MCMC=6, CHAIN=1, ADAPT_FREQ=4, SEED=12))
+    P = fe.load_params(cfg)
+    otree = fe.parse_mod(P.PHYTREE_FILE)
+    names, X = fe.load_fasta(P.ALIGN_FILE)
+    _, pos = fe.load_bed(P.SEG_FILE)
+    starts, lens = fe.element_layout(pos)
+    model = fe.build_model(otree, P)
+    X = fe.reorder_alignment(otree, names, X)
+    assert np.isin(X, np.frombuffer(b"rykmsw", dtype=np.uint8)).sum() > 50
+    eng = pab.Engine.from_config(cfg, device=0)
+    assert _compare_with_oracle(eng, P, model, X, starts, lens, [0, 1, 2]) >= 6
+    eng.close()
