@@ -150,7 +150,12 @@ int pa_engine_collect(pa_engine* e, pa_results* out);
  * selects the random streams of this outer iteration.  The state of a run is captured by pa_engine_collect.
  * pa_engine_sample_hyper is BPP::sample_hyperparam (bpp.cpp:324-477): one independence-MH sweep over the five
  * hyper-parameter pairs given the current rates of the full-model chains of `ids`; the accepted values take effect
- * for the next pa_engine_sample(_ex) and are returned in `out`. */
+ * for the next pa_engine_sample(_ex) and are returned in `out`.
+ * With the elements sharded over ranks (one engine per GPU) the sweep needs one exchange: pa_engine_hyper_sums returns this rank's
+ * PA_HYPER_NSUMS partial sums over its own `ids` (sum n, sum log n, sum c, sum log c, sum log l, sum log(1-l), sum log l2,
+ * sum log(1-l2), sum log g, sum log(1-g), count -- the sufficient statistics of bpp.cpp:340-349,403-452), the caller adds them over
+ * ranks (one all-reduce of 11 doubles) and every rank calls pa_engine_sample_hyper_sums with the totals: same draws, same result. */
+#define PA_HYPER_NSUMS 11
 typedef struct pa_hyper {
   double nprior_a, nprior_b, cprior_a, cprior_b;          /* ACCE_PRIOR_A/B, CONSERVE_PRIOR_A/B */
   double prior_l_a, prior_l_b, prior_g_a, prior_g_b;      /* HYPER_LRATE_A/B, HYPER_GRATE_A/B */
@@ -160,6 +165,8 @@ int pa_engine_sample_ex(pa_engine* e, const int32_t* ids, int32_t n_ids, int32_t
 int pa_engine_get_hyper(const pa_engine* e, pa_hyper* out);
 int pa_engine_set_hyper(pa_engine* e, const pa_hyper* in);
 int pa_engine_sample_hyper(pa_engine* e, int32_t iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
+int pa_engine_hyper_sums(pa_engine* e, const int32_t* ids, int32_t n_ids, double* sums /* [PA_HYPER_NSUMS] */);
+int pa_engine_sample_hyper_sums(pa_engine* e, int32_t iter, const double* sums /* [PA_HYPER_NSUMS] */, pa_hyper* out);
 int pa_engine_run(pa_engine* e, const int32_t* ids, int32_t n_ids, pa_results* out);
 
 /* Trace of one chain of the last pa_engine_sample (i = position in ids, model = PA_M0..PA_M2). */

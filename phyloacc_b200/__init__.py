@@ -69,6 +69,9 @@ class PaElementInfo(C.Structure):
                 ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p), ("n_slots", C.c_int32)]
 
 
+HYPER_NSUMS = 11  # PA_HYPER_NSUMS
+
+
 class PaHyper(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("nprior_a", "nprior_b", "cprior_a", "cprior_b", "prior_l_a", "prior_l_b", "prior_g_a", "prior_g_b",
                                           "prior_l2_a", "prior_l2_b")]
@@ -89,7 +92,8 @@ EXPORTS = [
     "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters", "pa_engine_phase_cycles",
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
-    "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper",
+    "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
+    "pa_engine_sample_hyper_sums",
 ]
 
 _lib = None
@@ -130,6 +134,8 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_hyper.argtypes = [C.c_void_p, C.POINTER(PaHyper)]
     lib.pa_engine_set_hyper.argtypes = [C.c_void_p, C.POINTER(PaHyper)]
     lib.pa_engine_sample_hyper.argtypes = [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.POINTER(PaHyper)]
+    lib.pa_engine_hyper_sums.argtypes = [C.c_void_p, _i32p, C.c_int32, _f64p]
+    lib.pa_engine_sample_hyper_sums.argtypes = [C.c_void_p, C.c_int32, _f64p, C.POINTER(PaHyper)]
     lib.pa_engine_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PaTrace)]
     lib.pa_engine_counters.argtypes = [C.c_void_p, C.POINTER(PaCounters)]
     lib.pa_engine_phase_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -338,6 +344,21 @@ class Engine:
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         h = PaHyper()
         _check(self._lib.pa_engine_sample_hyper(self._h, it, ids.ctypes.data_as(_i32p), len(ids), C.byref(h)))
+        return h.as_dict()
+
+    def hyper_sums(self, ids) -> np.ndarray:
+        """This rank's partial sums of the hyper-parameter sweep over its own `ids` (pa_engine_hyper_sums)."""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        sums = np.zeros(HYPER_NSUMS, dtype=np.float64)
+        _check(self._lib.pa_engine_hyper_sums(self._h, ids.ctypes.data_as(_i32p), len(ids), sums.ctypes.data_as(_f64p)))
+        return sums
+
+    def sample_hyper_from_sums(self, it: int, sums) -> dict:
+        """The sweep of sample_hyper from sums added over all ranks (pa_engine_sample_hyper_sums)."""
+        sums = np.ascontiguousarray(sums, dtype=np.float64)
+        assert sums.shape == (HYPER_NSUMS,)
+        h = PaHyper()
+        _check(self._lib.pa_engine_sample_hyper_sums(self._h, it, sums.ctypes.data_as(_f64p), C.byref(h)))
         return h.as_dict()
 
     def collect(self) -> Results:

@@ -155,6 +155,22 @@ int pa_engine_sample_hyper(pa_engine* e, int32_t iter, const int32_t* ids, int32
   return guarded([&]() { return e->eng.sample_hyper(iter, ids, n_ids, out); });
 }
 
+int pa_engine_hyper_sums(pa_engine* e, const int32_t* ids, int32_t n_ids, double* sums) {
+  if (!e || !sums || (n_ids > 0 && !ids)) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.hyper_sums(ids, n_ids, sums); });
+}
+
+int pa_engine_sample_hyper_sums(pa_engine* e, int32_t iter, const double* sums, pa_hyper* out) {
+  if (!e || !sums) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.sample_hyper_from_sums(iter, sums, out); });
+}
+
 int pa_engine_collect(pa_engine* e, pa_results* out) {
   if (!e || !out) {
     g_last = "null argument";

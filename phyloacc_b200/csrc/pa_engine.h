@@ -70,6 +70,8 @@ struct Engine {
   int loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out);
   int sample(const int32_t* ids, int32_t n_ids, int model_mask = 7, bool warm_start = false, int chain_iter = 0);
   int sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
+  int hyper_sums(const int32_t* ids, int32_t n_ids, double* sums /* [PA_HYPER_NSUMS] */);
+  int sample_hyper_from_sums(int iter, const double* sums, pa_hyper* out);
   int fetch_traces();
   int collect(pa_results* out);
   int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);

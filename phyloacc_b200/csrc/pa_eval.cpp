@@ -91,10 +91,13 @@ double gamma_host(uint32_t seed, uint32_t key, uint32_t idx, uint32_t sub0, uint
 // uniform MH on the Beta priors of l, l2, g, from the CURRENT states of the full-model chains (bpp.cur_*; elements
 // whose chain never ran keep the INIT_* values, as in the reference).  Draws come from the Philox schedule (stream
 // PA_ST_HYPER) in the reference's order of consumption.
-int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out) {
-  pa_params& P = model.prm;
+// The sweep depends on the elements only through ten sums and their count (PA_HYPER_NSUMS): sum n, sum log n, sum c, sum log c,
+// sum log l, sum log(1-l), sum log l2, sum log(1-l2), sum log g, sum log(1-g), count.  With the elements sharded over ranks each
+// rank contributes the sums of its own ids, one all-reduce adds them, and every rank runs the same sweep (same Philox draws).
+int Engine::hyper_sums(const int32_t* ids, int32_t n_ids, double* sums) {
+  const pa_params& P = model.prm;
   const size_t C = plans.size();
-  std::vector<double> rn(n_ids), rc(n_ids), rl(n_ids), rl2(n_ids), rg(n_ids);
+  for (int k = 0; k < PA_HYPER_NSUMS; k++) sums[k] = 0.0;
   for (int i = 0; i < n_ids; i++) {
     const int c = ids[i];
     if (c < 0 || (size_t)c >= C) {
@@ -103,31 +106,41 @@ int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* 
     }
     const size_t slot = (size_t)c * 3 + PA_M2;
     const bool have = cur_set.size() == C * 3 && cur_set[slot];
-    rn[i] = have ? cur_rates[slot * 5 + 0] : P.init_acce_rate;
-    rc[i] = have ? cur_rates[slot * 5 + 1] : P.init_conserve_rate;
-    rg[i] = have ? cur_rates[slot * 5 + 2] : P.init_grate;
-    rl[i] = have ? cur_rates[slot * 5 + 3] : P.init_lrate;
-    rl2[i] = have ? cur_rates[slot * 5 + 4] : P.init_lrate2;
+    const double rn = have ? cur_rates[slot * 5 + 0] : P.init_acce_rate, rc = have ? cur_rates[slot * 5 + 1] : P.init_conserve_rate;
+    const double rg = have ? cur_rates[slot * 5 + 2] : P.init_grate, rl = have ? cur_rates[slot * 5 + 3] : P.init_lrate;
+    const double rl2 = have ? cur_rates[slot * 5 + 4] : P.init_lrate2;
+    sums[0] += rn; sums[1] += std::log(rn);
+    sums[2] += rc; sums[3] += std::log(rc);
+    sums[4] += std::log(rl); sums[5] += std::log(1 - rl);
+    sums[6] += std::log(rl2); sums[7] += std::log(1 - rl2);
+    sums[8] += std::log(rg); sums[9] += std::log(1 - rg);
   }
+  sums[10] = (double)n_ids;
+  return PA_OK;
+}
+
+int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out) {
+  double sums[PA_HYPER_NSUMS];
+  const int rc = hyper_sums(ids, n_ids, sums);
+  return rc != PA_OK ? rc : sample_hyper_from_sums(iter, sums, out);
+}
+
+int Engine::sample_hyper_from_sums(int iter, const double* sums, pa_hyper* out) {
+  pa_params& P = model.prm;
   const uint32_t seed = (uint32_t)P.seed, it = (uint32_t)iter;
   uint32_t n_draw = 0;
   auto gam = [&](double a, double b) { return gamma_host(seed, PA_KEY_HYPER, n_draw++, 0u, it, PA_ST_HYPER, a, b); };
   auto uni = [&]() { return u01_host(philox4_host(seed, PA_KEY_HYPER, n_draw++, 0u, it, PA_ST_HYPER).x); };
   const double p = 1, r = 1, q = 0.1, sc = 0.1;  // hyper-priors of the Gamma shapes / scales (bpp.cpp:328-329)
   const double vna = 100, vnb = 100, vca = 100, vcb = 100;
-  const double n_ids_d = (double)n_ids;
+  const double n_ids_d = sums[10];
   double& nprior_a = P.acce_prior_a; double& nprior_b = P.acce_prior_b;
   double& cprior_a = P.conserve_prior_a; double& cprior_b = P.conserve_prior_b;
   const double nprior_a_prop = gam(vna, nprior_a / vna);
   const double cprior_a_prop = gam(vca, cprior_a / vca);
   const double nprior_b_prop = gam(vnb, nprior_b / vnb);
   const double cprior_b_prop = gam(vcb, cprior_b / vcb);
-  auto rate_step = [&](const std::vector<double>& rates, double& a, double& b, double a_prop, double b_prop, double va, double vb) {
-    double sum_r = 0, log_prod_r = 0;
-    for (double x : rates) {
-      sum_r += x;
-      log_prod_r += std::log(x);
-    }
+  auto rate_step = [&](double sum_r, double log_prod_r, double& a, double& b, double a_prop, double b_prop, double va, double vb) {
     double M = (a_prop - 1) * (std::log(p) + log_prod_r) - (q + sum_r) / b_prop - (n_ids_d + r) * std::lgamma(a_prop) - std::log(b_prop) * a_prop * (sc + n_ids_d);
     M -= (a - 1) * (std::log(p) + log_prod_r) - (q + sum_r) / b - (n_ids_d + r) * std::lgamma(a) - std::log(b) * a * (sc + n_ids_d);
     const double H = std::log(gamma_pdf(a, va, a_prop / va)) - std::log(gamma_pdf(a_prop, va, a / va)) + std::log(gamma_pdf(b, vb, b_prop / vb)) -
@@ -137,16 +150,11 @@ int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* 
       b = b_prop;
     }
   };
-  rate_step(rn, nprior_a, nprior_b, nprior_a_prop, nprior_b_prop, vna, vnb);
-  rate_step(rc, cprior_a, cprior_b, cprior_a_prop, cprior_b_prop, vca, vcb);
-  auto beta_step = [&](const std::vector<double>& rates, double& a, double& b) {
+  rate_step(sums[0], sums[1], nprior_a, nprior_b, nprior_a_prop, nprior_b_prop, vna, vnb);
+  rate_step(sums[2], sums[3], cprior_a, cprior_b, cprior_a_prop, cprior_b_prop, vca, vcb);
+  auto beta_step = [&](double log_p, double log_pc, double& a, double& b) {
     const double a_prop = a * (uni() * (1.3 - 0.7) + 0.7);
     const double b_prop = b * (uni() * (1.3 - 0.7) + 0.7);
-    double log_p = 0, log_pc = 0;
-    for (double x : rates) {
-      log_p += std::log(x);
-      log_pc += std::log(1 - x);
-    }
     double M = (a_prop - a) * (log_p - 1) + (b_prop - b) * (log_pc - 1);
     M += n_ids_d * (lnbeta(a, b) - lnbeta(a_prop, b_prop));
     const double H = std::log(a) - std::log(a_prop) + std::log(b) - std::log(b_prop);
@@ -155,9 +163,9 @@ int Engine::sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* 
       b = b_prop;
     }
   };
-  beta_step(rl, P.hyper_lrate_a, P.hyper_lrate_b);
-  beta_step(rl2, P.hyper_lrate2_a, P.hyper_lrate2_b);
-  beta_step(rg, P.hyper_grate_a, P.hyper_grate_b);
+  beta_step(sums[4], sums[5], P.hyper_lrate_a, P.hyper_lrate_b);
+  beta_step(sums[6], sums[7], P.hyper_lrate2_a, P.hyper_lrate2_b);
+  beta_step(sums[8], sums[9], P.hyper_grate_a, P.hyper_grate_b);
   if (out) {
     out->nprior_a = nprior_a; out->nprior_b = nprior_b; out->cprior_a = cprior_a; out->cprior_b = cprior_b;
     out->prior_l_a = P.hyper_lrate_a; out->prior_l_b = P.hyper_lrate_b; out->prior_g_a = P.hyper_grate_a; out->prior_g_b = P.hyper_grate_b;

@@ -43,3 +43,20 @@ def gather_summaries(local: np.ndarray, counts: Sequence[int], rank: int, world:
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return np.concatenate([out[r][: counts[r]].cpu().numpy() for r in range(world)], axis=0)
+
+
+def sample_hyper_sharded(engine, it: int, local_ids, world: int, device=None) -> dict:
+    """BPP::sample_hyperparam (bpp.cpp:324-477) with the elements sharded over ranks: the sweep depends on the elements only
+    through 11 sums (`Engine.hyper_sums`), so each rank adds up its own ids, ONE all-reduce adds the ranks, and every rank runs
+    the same sweep on the totals (same Philox draws -> same accepted values everywhere).  SURVEY.md §8e."""
+    import torch
+    import torch.distributed as dist
+
+    sums = engine.hyper_sums(local_ids)
+    if world > 1:
+        t = torch.from_numpy(sums.copy())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sums = t.cpu().numpy()
+    return engine.sample_hyper_from_sums(it, sums)
