@@ -10,7 +10,8 @@ A "step" is one pass of the hot path over one resident batch of synthetic elemen
 [50, 2000] bp): every element runs its M0, M1 and M2 chains for BURNIN+MCMC = 1500 iterations on the device.
 value   = elements x 3 x 1500 / device time of the chain kernel, inputs resident in HBM (CUDA events);
 e2e     = the same count / time of the public C-ABI call sequence with HOST buffers: pa_engine_load_alignment
-          (integer front-end + H2D) + pa_engine_run (chains + D2H of traces + Eval2 / summaries on the host);
+          (integer front-end + H2D) + pa_engine_run (chains + D2H of traces + Eval2 / summaries on the host, finished chains
+          summarised while later ones are still being sampled);
 roofline: FP64 FMA (north_star) -- algorithmic FMA per SURVEY.md §8d from the engine's work counters over the measured
           FP64 FMA peak of this GPU (micro-benchmark, MEASURED_PEAKS.json has no FP64 entry);
 cpu_baseline / --impl reference: the UNMODIFIED reference sources built against the compat shim

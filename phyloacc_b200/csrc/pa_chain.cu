@@ -416,9 +416,17 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
 #define w_iter S.work[4]
 #define w_nsu S.work[5]
 
+  if (tid == 0) S.ivars[IV_CHAIN] = -1;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
+      // the previous chain of this CTA is complete: every thread's trace writes precede the barrier above; publish it to the host,
+      // which downloads and summarises finished chains while the kernel is still running (pa_eval.cpp: fetch_range)
+      const int prev = S.ivars[IV_CHAIN];
+      if (prev >= 0 && L.done) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int*>(L.done + prev) = 1;
+      }
       S.ivars[IV_CHAIN] = atomicAdd(L.queue, 1);
       S.ivars[IV_STAGED] = -1;
     }

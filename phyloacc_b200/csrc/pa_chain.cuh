@@ -15,6 +15,7 @@ struct ChainLaunch {
   const uint32_t* init_z;     // [n_chains][ZW] packed Z of a warm start
   uint8_t* arena; size_t arena_stride;
   unsigned long long* counters; int* queue;
+  int* done;  // [n_sel] set to 1 (system scope) when the chain of queue slot k has written its last trace row; may be nullptr
 };
 size_t chain_smem_bytes(int n_max, int s_rows, int bd);  // bd: threads per CTA of the layout (256 or 128)
 int chain_ctas_per_sm(int n_max, int s_rows, int bd);

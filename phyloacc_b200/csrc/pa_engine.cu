@@ -112,6 +112,11 @@ void Engine::release_device() {
   cap_init_rates = cap_init_z = 0;
   if (h_trace_d) cudaFreeHost(h_trace_d);
   if (h_trace_z) cudaFreeHost(h_trace_z);
+  if (h_done) cudaFreeHost(h_done);
+  h_done = nullptr;
+  cap_h_done = 0;
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  copy_stream = nullptr;
   h_trace_d = nullptr;
   h_trace_z = nullptr;
   cap_h_trace_d = cap_h_trace_z = 0;

@@ -60,6 +60,12 @@ struct Engine {
   uint32_t* h_trace_z = nullptr;
   size_t cap_h_trace_d = 0, cap_h_trace_z = 0;
   bool sampled = false, collected = false;
+  // completion flags of the running launch, written by the kernel into mapped pinned memory (one per chain, device order), and the
+  // stream the finished chains' traces are downloaded on while the kernel is still running
+  int* h_done = nullptr;
+  size_t cap_h_done = 0;
+  int done_prefix = 0, fetched_prefix = 0;
+  cudaStream_t copy_stream = nullptr;
   pa_counters counters{};
   unsigned long long phase_cycles[10] = {0};  // SM cycles spent per chain-kernel phase (thread 0 of every CTA, summed)
 
@@ -73,6 +79,9 @@ struct Engine {
   int hyper_sums(const int32_t* ids, int32_t n_ids, double* sums /* [PA_HYPER_NSUMS] */);
   int sample_hyper_from_sums(int iter, const double* sums, pa_hyper* out);
   int fetch_traces();
+  int fetch_range(int lo, int hi);  // wait for chains [fetched_prefix, hi) of the running launch and download their traces
+  int fetch_finish();               // end of the launch: counters, warm-start states
+  int unpack_trace(int ch, ChainTraceHost& tr) const;
   int collect(pa_results* out);
   int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);
 };

@@ -2,6 +2,7 @@
 // reference computes after Gibbs: MaxLoglik / Max_Z (MonitorChain, bpp_c.cpp:768-814), Eval2 (bpp_c2.cpp:14-353) and
 // Output_init's medians / posterior Z frequencies (bpp_c2.cpp:739-785).
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -211,8 +212,13 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     }
   }
   n_chains = (int)chain_elem_pos.size();
+  if (sampled && !collected && device >= 0) {  // a launch that was never collected may still be writing its completion flags
+    cudaSetDevice(device);
+    cudaStreamSynchronize(stream);
+  }
   sampled = true;
   collected = false;
+  done_prefix = fetched_prefix = 0;
   counters = pa_counters{};
   if (n_chains == 0) return PA_OK;
   ZW = (n_max + 15) / 16;
@@ -274,6 +280,31 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   PA_CUDA(cudaMemcpyAsync(d_chain_list, list.data(), sizeof(int32_t) * 2 * n_chains, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 24, stream));
   PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int), stream));
+  // completion flags in mapped pinned memory (grow-only), the trace buffers on the host and the download stream
+  if (sizeof(int) * (size_t)n_chains > cap_h_done || !h_done) {
+    if (h_done) cudaFreeHost(h_done);
+    h_done = nullptr;
+    cap_h_done = 0;
+    PA_CUDA(cudaHostAlloc((void**)&h_done, sizeof(int) * (size_t)n_chains, cudaHostAllocMapped));
+    cap_h_done = sizeof(int) * (size_t)n_chains;
+  }
+  memset(h_done, 0, sizeof(int) * (size_t)n_chains);
+  int* d_done = nullptr;
+  PA_CUDA(cudaHostGetDevicePointer((void**)&d_done, h_done, 0));
+  if (!copy_stream) PA_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  {
+    auto reserve_host = [&](void*& p, size_t& cap, size_t bytes) -> cudaError_t {
+      if (bytes <= cap && p) return cudaSuccess;
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+      if (e == cudaSuccess) cap = bytes;
+      return e;
+    };
+    PA_CUDA(reserve_host((void*&)h_trace_d, cap_h_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
+    PA_CUDA(reserve_host((void*&)h_trace_z, cap_h_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));
+  }
   bool any_warm = false;
   if (warm_start && !cur_set.empty()) {
     std::vector<double> ir((size_t)n_chains * 8, 0.0);
@@ -318,38 +349,60 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   L.counters = d_counters;
   L.sel = nullptr; L.n_sel = n_chains; L.P_max = P_max;
   L.arena = d_arena; L.arena_stride = stride; L.queue = d_queue;
+  L.done = d_done;
   const int rc = launch_chains(L, grid, BD, stream);
   if (rc != PA_OK) return rc;
   counters.kernel_launches = 1;
   return PA_OK;
 }
 
-int Engine::fetch_traces() {
+// Download the traces of chains [fetched_prefix, hi) (device order = queue order: the kernel finishes them roughly in that
+// order and flags each one in mapped pinned memory).  Called while the kernel is still running: the copies go over a second
+// stream, so the host summaries of finished chains overlap the chains that are still being sampled.
+int Engine::fetch_range(int lo, int hi) {
+  (void)lo;
   if (!sampled) {
     set_error("nothing sampled yet");
     return PA_ERR_STATE;
   }
+  hi = std::min(hi, n_chains);
+  if (collected || hi <= fetched_prefix) return PA_OK;
+  PA_CUDA(cudaSetDevice(device));
+  volatile int* done = h_done;
+  bool finished = false;
+  while (done_prefix < hi) {
+    while (done_prefix < n_chains && done[done_prefix]) done_prefix++;
+    if (done_prefix >= hi) break;
+    if (finished) {  // the launch is over and a flag is missing: the kernel did not run through
+      set_error("chain kernel ended without completing every chain");
+      return PA_ERR_CUDA;
+    }
+    const cudaError_t q = cudaStreamQuery(stream);
+    if (q == cudaSuccess) finished = true;  // everything is flagged by now; scan once more
+    else if (q != cudaErrorNotReady) {
+      set_error(std::string("chain kernel: ") + cudaGetErrorString(q));
+      return PA_ERR_CUDA;
+    } else {
+      struct timespec ts = {0, 100000};  // 0.1 ms
+      nanosleep(&ts, nullptr);
+    }
+  }
+  const int a = fetched_prefix, b = std::min(n_chains, std::max(hi, done_prefix));
+  const size_t per_d = (size_t)6 * T, per_z = (size_t)ZW * T;
+  PA_CUDA(cudaMemcpyAsync(h_trace_d + a * per_d, d_trace_d + a * per_d, sizeof(double) * per_d * (b - a), cudaMemcpyDeviceToHost, copy_stream));
+  PA_CUDA(cudaMemcpyAsync(h_trace_z + a * per_z, d_trace_z + a * per_z, sizeof(uint32_t) * per_z * (b - a), cudaMemcpyDeviceToHost, copy_stream));
+  PA_CUDA(cudaStreamSynchronize(copy_stream));
+  fetched_prefix = b;
+  return PA_OK;
+}
+
+int Engine::fetch_finish() {
   if (collected || n_chains == 0) {
     collected = true;
     return PA_OK;
   }
   PA_CUDA(cudaSetDevice(device));
-  // pinned host buffers (grow-only): the trace download runs at PCIe speed instead of through a pageable staging copy
-  auto reserve_host = [&](void*& p, size_t& cap, size_t bytes) -> cudaError_t {
-    if (bytes <= cap && p) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = bytes;
-    return e;
-  };
-  const size_t bytes_d = sizeof(double) * 6 * (size_t)T * n_chains, bytes_z = sizeof(uint32_t) * (size_t)ZW * T * n_chains;
-  PA_CUDA(reserve_host((void*&)h_trace_d, cap_h_trace_d, bytes_d));
-  PA_CUDA(reserve_host((void*&)h_trace_z, cap_h_trace_z, bytes_z));
   unsigned long long hc[24];
-  PA_CUDA(cudaMemcpyAsync(h_trace_d, d_trace_d, bytes_d, cudaMemcpyDeviceToHost, stream));
-  PA_CUDA(cudaMemcpyAsync(h_trace_z, d_trace_z, bytes_z, cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaMemcpyAsync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaStreamSynchronize(stream));
   counters.node_pattern_updates = hc[0];
@@ -379,6 +432,19 @@ int Engine::fetch_traces() {
   return PA_OK;
 }
 
+int Engine::fetch_traces() {
+  if (!sampled) {
+    set_error("nothing sampled yet");
+    return PA_ERR_STATE;
+  }
+  if (collected || n_chains == 0) {
+    collected = true;
+    return PA_OK;
+  }
+  const int rc = fetch_range(0, n_chains);
+  return rc != PA_OK ? rc : fetch_finish();
+}
+
 int Engine::get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr) {
   int rc = fetch_traces();
   if (rc != PA_OK) return rc;
@@ -391,7 +457,12 @@ int Engine::get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr) {
     set_error("element was filtered; it has no chain");
     return PA_ERR_ARG;
   }
-  const ElemPlan& pl = plans[run_ids[i]];
+  return unpack_trace(ch, tr);
+}
+
+// host copy of chain `ch` (device order) from the downloaded trace buffers
+int Engine::unpack_trace(int ch, ChainTraceHost& tr) const {
+  const ElemPlan& pl = plans[run_ids[chain_elem_pos[ch]]];
   const int N = model.tree.N, n = (int)pl.nodes.size();
   const double* d = &h_trace_d[(size_t)ch * 6 * T];
   tr.loglik.assign(d, d + T);
@@ -564,9 +635,12 @@ double eval2_fallback_finish(const Engine& eng, int mdl, const Eval2Work& w, con
 int Engine::collect(pa_results* out) {
   const bool timing = getenv("PA_TIMING") != nullptr;
   const double t_start = omp_get_wtime();
-  int rc = fetch_traces();
-  if (rc != PA_OK) return rc;
-  const double t_fetch = omp_get_wtime();
+  if (!sampled) {
+    set_error("nothing sampled yet");
+    return PA_ERR_STATE;
+  }
+  int rc = PA_OK;
+  double t_wait = 0.0;
   const int n_ids = (int)run_ids.size();
   if (out->n < n_ids || out->N != model.tree.N) {
     set_error("pa_results too small for this run");
@@ -588,12 +662,25 @@ int Engine::collect(pa_results* out) {
   std::vector<double> logml(n_chains, 0.0);
   int err = PA_OK;
   const int nt = std::max(1, P.num_thread);
+  // Chains are summarised in the order the kernel finishes them (device order), chunk by chunk, while later chains are still being
+  // sampled: wait for a chunk's completion flags, download its traces on the copy stream, summarise it on the host threads.
+  const bool streaming = !collected && n_chains > 0;
+  const int chunk = streaming ? 192 : std::max(1, n_chains);
+  for (int lo = 0, hi = 0; lo < n_chains; lo = hi) {
+    hi = std::min(n_chains, lo + chunk);
+    if (streaming) {
+      const double t0 = omp_get_wtime();
+      rc = fetch_range(lo, hi);
+      if (rc != PA_OK) return rc;
+      hi = std::max(hi, fetched_prefix);
+      t_wait += omp_get_wtime() - t0;
+    }
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
-  for (int ch = 0; ch < n_chains; ch++) {
+  for (int ch = lo; ch < hi; ch++) {
     const int i = chain_elem_pos[ch], mdl = chain_model[ch];
     const ElemPlan& pl = plans[run_ids[i]];
     ChainTraceHost tr;
-    if (get_trace(i, mdl, tr) != PA_OK) {
+    if (unpack_trace(ch, tr) != PA_OK) {
 #pragma omp critical
       err = PA_ERR_STATE;
       continue;
@@ -653,7 +740,10 @@ int Engine::collect(pa_results* out) {
       }
     }
   }
+  }  // chunks
   if (err != PA_OK) return err;
+  rc = fetch_finish();
+  if (rc != PA_OK) return rc;
   const double t_sum = omp_get_wtime();
   // Eval2 fallback (no configuration carries >= 2% weight with a finite log-det): exact log-likelihood of every
   // configuration at the posterior-mean rates, by the replay kernel, in one batch
@@ -687,8 +777,8 @@ int Engine::collect(pa_results* out) {
   if (out->loglik)
     for (int ch = 0; ch < n_chains; ch++) out->loglik[chain_elem_pos[ch] * 3 + chain_model[ch]] = logml[ch];
   if (timing)
-    fprintf(stderr, "[pa timing] collect: wait + trace download %.3f s, MonitorChain/Eval2/summaries %.3f s (%d threads), Eval2 fallback %.3f s\n",
-            t_fetch - t_start, t_sum - t_fetch, nt, omp_get_wtime() - t_sum);
+    fprintf(stderr, "[pa timing] collect: waiting for chains + trace download %.3f s, MonitorChain/Eval2/summaries %.3f s (%d threads, overlapped with the kernel), Eval2 fallback %.3f s\n",
+            t_wait, t_sum - t_start - t_wait, nt, omp_get_wtime() - t_sum);
   return PA_OK;
 }
 
