@@ -290,7 +290,12 @@ def main():
                 "peak_source": "measured live: register-resident DFMA micro-benchmark (pa_device_fp64_peak)",
                 "algorithmic_fma_per_step": fma, "kernel": "chain_kernel",
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
+                        "note": "algorithmic bytes (alignment read once + trace rows written); the kernel's measured DRAM traffic is below"},
+                # measured DRAM traffic of the launch (arena spills out of L2) over this run's kernel time: how far the kernel is from
+                # being bandwidth-bound
+                "dram_measured": ({"achieved": traffic / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": traffic / (ms_step * 1e-3) / 1e9 / hbm_peak} if traffic else None)}
         # BASELINE's second metric: full-tree-equivalent site likelihoods per second on UNCOMPRESSED columns
         # (sum over upward passes of columns x recomputed internal nodes / (S - 1)), rank 0's share x ranks
         site_liks = float(cnt["node_site_updates"]) / (tree.S - 1) / (ms_step * 1e-3) * world
