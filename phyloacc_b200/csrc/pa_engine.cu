@@ -113,6 +113,9 @@ void Engine::release_device() {
   if (h_trace_d) cudaFreeHost(h_trace_d);
   if (h_trace_z) cudaFreeHost(h_trace_z);
   if (h_done) cudaFreeHost(h_done);
+  if (h_blobs) cudaFreeHost(h_blobs);
+  h_blobs = nullptr;
+  cap_h_blobs = 0;
   h_done = nullptr;
   cap_h_done = 0;
   if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -194,10 +197,18 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
   PA_CUDA(cudaSetDevice(device));
   // only the batch itself is replaced; the buffers of a run (arenas, traces, pinned host copies) persist and grow on demand
   sampled = collected = false;
-  std::vector<uint8_t> all(total);
+  // the blobs are gathered into a pinned staging buffer (grow-only, never cleared) by all host threads and go up in one copy
+  if (total > cap_h_blobs || !h_blobs) {
+    if (h_blobs) cudaFreeHost(h_blobs);
+    h_blobs = nullptr;
+    cap_h_blobs = 0;
+    PA_CUDA(cudaHostAlloc((void**)&h_blobs, std::max<size_t>(total, 16), cudaHostAllocDefault));
+    cap_h_blobs = std::max<size_t>(total, 16);
+  }
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (int c = 0; c < C; c++)
     if (!plans[c].filtered) {
-      memcpy(all.data() + blob_off[c], plans[c].blob.data(), plans[c].blob.size());
+      memcpy(h_blobs + blob_off[c], plans[c].blob.data(), plans[c].blob.size());
       std::vector<uint8_t>().swap(plans[c].blob);  // the packed copy now lives in HBM
     }
   {
@@ -217,7 +228,7 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
       cap_blob_off = need_o;
     }
   }
-  PA_CUDA(cudaMemcpyAsync(d_blobs, all.data(), total, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_blobs, h_blobs, total, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemcpyAsync(d_blob_off, blob_off.data(), sizeof(int64_t) * C, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaStreamSynchronize(stream));
   h2d_bytes = total + sizeof(int64_t) * C;

@@ -32,6 +32,8 @@ struct Engine {
   uint8_t* d_blobs = nullptr;
   int64_t* d_blob_off = nullptr;
   size_t cap_blobs = 0, cap_blob_off = 0;
+  uint8_t* h_blobs = nullptr;  // pinned staging copy of the blobs (grow-only)
+  size_t cap_h_blobs = 0;
 
   // last sampling run
   std::vector<int32_t> run_ids;          // element ids passed to sample()
