@@ -802,6 +802,10 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
 
       // ---------------- Update_Z_subtree (bpp_c.cpp:1204-1293): scaled linear messages by tree level, one warp
       if (warp == 0) {
+        // The two transition matrices have six distinct non-trivial entries (bpp_c.cpp:301-332): free [1-g 0 0; g y l2; 0 1-y 1-l2]
+        // (rows = child state, columns = parent state), fixZ == 1 [1-g 0 1; g 1 1; 0 0 1]; they stay in registers and the zero / one
+        // entries are not multiplied (x + 0 * v and 1 * v are exact, so the messages are the ones of the full 3 x 3 products)
+        const double t00 = S.T[0], t10 = S.T[3], t11 = S.T[4], t21 = S.T[7], t12 = S.T[5], t22 = S.T[8];
         for (int lv = 1; lv < h->n_up; lv++) {
           for (int idx = S.up_off[lv] + lane; idx < S.up_off[lv + 1]; idx += 32) {
             const int i = S.up_nodes[idx];
@@ -809,11 +813,14 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
 #pragma unroll
             for (int cc = 0; cc < 2; cc++) {
               const int ch = S.child[2 * i + cc];
-              const double* Tm = S.T + (S.fix[ch] ? 9 : 0);
+              const bool fx = S.fix[ch] != 0;
               const double v0 = S.back[ch * 3], v1 = S.back[ch * 3 + 1], v2 = S.back[ch * 3 + 2];
-              b0 *= (Tm[0] * v0 + Tm[3] * v1) + Tm[6] * v2;
-              b1 *= (Tm[1] * v0 + Tm[4] * v1) + Tm[7] * v2;
-              b2 *= (Tm[2] * v0 + Tm[5] * v1) + Tm[8] * v2;
+              const double f0 = t00 * v0 + t10 * v1;
+              const double f1 = fx ? v1 : __fma_rn(t21, v2, __dmul_rn(t11, v1));
+              const double f2 = fx ? ((v0 + v1) + v2) : __fma_rn(t22, v2, __dmul_rn(t12, v1));
+              b0 *= f0;
+              b1 *= f1;
+              b2 *= f2;
             }
             const double mx = fmax(b0, fmax(b1, b2));
             if (!(mx > 0.0) || mx != mx) S.ivars[IV_ZFALLBACK] = 1;

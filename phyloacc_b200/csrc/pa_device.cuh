@@ -303,20 +303,17 @@ __device__ __forceinline__ double prune_pattern(const ElemHeader* h, const TreeS
   return log(lik) - root_sc * PA_LOG_SCALE;
 }
 
-// deterministic block-wide sum (warp shuffles, then warp 0 adds the warp partials in order)
+// deterministic block-wide sum (warp shuffles, then the warp partials added in order; the leading barrier protects `red` from
+// the readers of a previous call)
 __device__ __forceinline__ double block_sum(double v, double* red /* >= 33 doubles */, int tid, int BD) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   __syncthreads();
   if ((tid & 31) == 0) red[tid >> 5] = v;
   __syncthreads();
-  if (tid == 0) {
-    double s = 0;
-    for (int w = 0; w < (BD >> 5); w++) s += red[w];
-    red[32] = s;
-  }
-  __syncthreads();
-  return red[32];
+  double s = 0;  // every thread adds the warp partials in the same order: one value, no third barrier
+  for (int w = 0; w < (BD >> 5); w++) s += red[w];
+  return s;
 }
 
 }  // namespace pa
