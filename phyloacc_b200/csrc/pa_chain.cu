@@ -3,7 +3,7 @@
 //
 //   MonitorChain  -> trace row (Z packed 2 bit/node, loglik, n, c, g, l, l2)                 bpp_c.cpp:741-834
 //   Update_Tg(.,.,true) for every site: ancestral bases, top-down, from per-PATTERN partials  bpp_c.cpp:672-733
-//   getEmission: parent->child base counts per branch  x  log P_k                           bpp_c2.cpp:355-390
+//   getEmission: parent->child base counts per branch (popc over bit planes)  x  log P_k    bpp_c2.cpp:355-390
 //   Update_Z_subtree: 3-state upward messages + top-down sampling of Z                       bpp_c.cpp:1182-1293
 //   getUpdateNode + Update_Tg(.,.,false): re-prune ancestors of changed Z                    bpp_c.cpp:620-671
 //   sample_rate (n, then c): MH with the histories integrated out (log_f_Xz)                 bpp_c.cpp:860-1176
@@ -15,7 +15,10 @@
 // which copy is current.  A pruning pass keeps the partials it recomputes in a per-thread shared-memory stack (for
 // its own parents) and streams them to the non-current copy; accepting a proposal flips the selectors of the
 // recomputed nodes, rejecting leaves everything untouched.  The shared-memory layout is a compile-time struct
-// (SmemT<NMAX, SLOTS>) so that every address is an immediate.
+// (SmemT<NMAX, SLOTS>) so that every address is an immediate.  The sampled ancestral bases of a 256-site tile are kept as
+// bit planes (four ballots per warp and node) next to a byte matrix for the parent look-ups; the tips' bases come as
+// precomputed bit planes with the element (ElemHeader::off_tipplanes), so the pair counts are AND + POPC per 32-site word.
+// Every finished chain is flagged in mapped pinned memory (ChainLaunch::done): the host summarises it while the kernel runs.
 // Random numbers: Philox4x32-10 indexed by (chain, iteration, purpose, site/node), see oracle/oracle.h.
 #include <cuda_runtime.h>
 
@@ -29,7 +32,8 @@ namespace pa {
 namespace {
 
 // Per-layout constants (SmemT): BD threads per CTA; a tile is BD patterns / sites; CODEROW staged bytes per tip row
-// (BD + 8 patterns); XS bytes per row of sampled bases (BD / 4 + 1 words: rows of different nodes fall into different banks).
+// (BD + 8 patterns); XS bytes per row of the byte matrix of sampled bases (BD / 4 + 1 words: rows of different nodes fall into
+// different banks).
 #define PA_LAYOUT_CONSTANTS(SM) \
   constexpr int kBD = SM::BD, kNW = SM::BD / 32, kTile = SM::BD, kCodeRow = SM::CODEROW, kXS = SM::XS; \
   (void)kNW; (void)kTile; (void)kCodeRow; (void)kXS
