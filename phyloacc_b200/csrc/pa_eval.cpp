@@ -676,70 +676,70 @@ int Engine::collect(pa_results* out) {
       t_wait += omp_get_wtime() - t0;
     }
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nt)
-  for (int ch = lo; ch < hi; ch++) {
-    const int i = chain_elem_pos[ch], mdl = chain_model[ch];
-    const ElemPlan& pl = plans[run_ids[i]];
-    ChainTraceHost tr;
-    if (unpack_trace(ch, tr) != PA_OK) {
+    for (int ch = lo; ch < hi; ch++) {
+      const int i = chain_elem_pos[ch], mdl = chain_model[ch];
+      const ElemPlan& pl = plans[run_ids[i]];
+      ChainTraceHost tr;
+      if (unpack_trace(ch, tr) != PA_OK) {
 #pragma omp critical
-      err = PA_ERR_STATE;
-      continue;
-    }
-    // MonitorChain: full log-likelihood and its arg-max after burn-in (bpp_c.cpp:768-814)
-    std::vector<double> full(T);
-    double max_ll = -INFINITY;
-    int max_m = -1;
-    for (int m = num_burn; m < T; m++) {  // only the post-burn-in rows are used (arg-max here, Eval2's averages below)
-      full[m] = tr.loglik[m] + 0.0;
-      full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
-      if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
-      if (full[m] > max_ll) {
-        max_ll = full[m];
-        max_m = m;
+        err = PA_ERR_STATE;
+        continue;
       }
-    }
-    std::vector<int8_t> Max_Z(N, 0);
-    if (max_m >= 0) Max_Z.assign(&tr.Z[(size_t)max_m * N], &tr.Z[(size_t)max_m * N] + N);
-    if (out->loglik_max) out->loglik_max[i * 3 + mdl] = max_ll;
-    if (out->max_Z) memcpy(out->max_Z + ((size_t)i * 3 + mdl) * N, Max_Z.data(), N);
-    if (max_m >= 0) logml[ch] = eval2_main(*this, pl, mdl, tr, full, Max_Z.data(), works[ch]);
-    else logml[ch] = NAN;
-    // Output_init: medians of the sorted FULL traces, Z frequencies after burn-in (bpp_c2.cpp:742-781)
-    if (out->median_rates) {
-      double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
-      std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
-      for (int k = 0; k < 5; k++) {  // the element the reference reads after sorting the whole trace (bpp_c2.cpp:742-760)
-        std::nth_element(cols[k]->begin(), cols[k]->begin() + cols[k]->size() / 2, cols[k]->end());
-        md[k] = (*cols[k])[cols[k]->size() / 2];
+      // MonitorChain: full log-likelihood and its arg-max after burn-in (bpp_c.cpp:768-814)
+      std::vector<double> full(T);
+      double max_ll = -INFINITY;
+      int max_m = -1;
+      for (int m = num_burn; m < T; m++) {  // only the post-burn-in rows are used (arg-max here, Eval2's averages below)
+        full[m] = tr.loglik[m] + 0.0;
+        full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
+        if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
+        if (full[m] > max_ll) {
+          max_ll = full[m];
+          max_m = m;
+        }
       }
-    }
-    if (out->post_Z) {
-      double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
-      std::vector<int> cnt((size_t)N * 4, 0);
-      {
-        // per-value passes over the row-major trace (vectorisable compare-and-add) instead of a scattered histogram
-        std::vector<int> c0(N, 0), c1(N, 0), c2(N, 0);
-        for (int m = num_burn; m < T; m++) {
-          const int8_t* row = &tr.Z[(size_t)m * N];
+      std::vector<int8_t> Max_Z(N, 0);
+      if (max_m >= 0) Max_Z.assign(&tr.Z[(size_t)max_m * N], &tr.Z[(size_t)max_m * N] + N);
+      if (out->loglik_max) out->loglik_max[i * 3 + mdl] = max_ll;
+      if (out->max_Z) memcpy(out->max_Z + ((size_t)i * 3 + mdl) * N, Max_Z.data(), N);
+      if (max_m >= 0) logml[ch] = eval2_main(*this, pl, mdl, tr, full, Max_Z.data(), works[ch]);
+      else logml[ch] = NAN;
+      // Output_init: medians of the sorted FULL traces, Z frequencies after burn-in (bpp_c2.cpp:742-781)
+      if (out->median_rates) {
+        double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
+        std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
+        for (int k = 0; k < 5; k++) {  // the element the reference reads after sorting the whole trace (bpp_c2.cpp:742-760)
+          std::nth_element(cols[k]->begin(), cols[k]->begin() + cols[k]->size() / 2, cols[k]->end());
+          md[k] = (*cols[k])[cols[k]->size() / 2];
+        }
+      }
+      if (out->post_Z) {
+        double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
+        std::vector<int> cnt((size_t)N * 4, 0);
+        {
+          // per-value passes over the row-major trace (vectorisable compare-and-add) instead of a scattered histogram
+          std::vector<int> c0(N, 0), c1(N, 0), c2(N, 0);
+          for (int m = num_burn; m < T; m++) {
+            const int8_t* row = &tr.Z[(size_t)m * N];
+            for (int s = 0; s < N; s++) {
+              c0[s] += row[s] == 0;
+              c1[s] += row[s] == 1;
+              c2[s] += row[s] == 2;
+            }
+          }
           for (int s = 0; s < N; s++) {
-            c0[s] += row[s] == 0;
-            c1[s] += row[s] == 1;
-            c2[s] += row[s] == 2;
+            cnt[s * 4 + 1] = c0[s];
+            cnt[s * 4 + 2] = c1[s];
+            cnt[s * 4 + 3] = c2[s];
+            cnt[s * 4] = num_mcmc - c0[s] - c1[s] - c2[s];  // Z == -1: the node is outside the element's pruned tree
           }
         }
         for (int s = 0; s < N; s++) {
-          cnt[s * 4 + 1] = c0[s];
-          cnt[s * 4 + 2] = c1[s];
-          cnt[s * 4 + 3] = c2[s];
-          cnt[s * 4] = num_mcmc - c0[s] - c1[s] - c2[s];  // Z == -1: the node is outside the element's pruned tree
+          if (pl.missing[s]) cnt[s * 4] = num_mcmc;
+          for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
         }
       }
-      for (int s = 0; s < N; s++) {
-        if (pl.missing[s]) cnt[s * 4] = num_mcmc;
-        for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
-      }
     }
-  }
   }  // chunks
   if (err != PA_OK) return err;
   rc = fetch_finish();
