@@ -129,6 +129,10 @@ int pa_engine_load_alignment(pa_engine* e, const uint8_t* X, int64_t G, int32_t 
 
 int pa_engine_num_elements(const pa_engine* e);
 int pa_engine_element_info(const pa_engine* e, int32_t elem, pa_element_info* out);
+/* The packed device image of one element (inspection / tests): header, tree arrays, pruning program, 4-bit tip codes per pattern,
+ * weights, gap masks, site -> pattern map and the tips' bit planes per 256-site tile (layout: ElemHeader in csrc/pa_internal.h).
+ * `*size` receives its length; the bytes are copied when `cap` is large enough.  A filtered element has no image (size 0). */
+int pa_engine_element_blob(pa_engine* e, int32_t elem, uint8_t* buf, int64_t cap, int64_t* size);
 
 /* Replayed log-likelihoods: for each state i, log P(X_elem | Z, n_rate, c_rate) exactly as the reference
  * evaluates it after initMCMC (bpp_c.cpp:131-236) + Update_Tg(.,.,false) (bpp_c.cpp:647-671) +

@@ -93,7 +93,7 @@ EXPORTS = [
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
-    "pa_engine_sample_hyper_sums",
+    "pa_engine_sample_hyper_sums", "pa_engine_element_blob",
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_set_hyper.argtypes = [C.c_void_p, C.POINTER(PaHyper)]
     lib.pa_engine_sample_hyper.argtypes = [C.c_void_p, C.c_int32, _i32p, C.c_int32, C.POINTER(PaHyper)]
     lib.pa_engine_hyper_sums.argtypes = [C.c_void_p, _i32p, C.c_int32, _f64p]
+    lib.pa_engine_element_blob.argtypes = [C.c_void_p, C.c_int32, _u8p, C.c_int64, C.POINTER(C.c_int64)]
     lib.pa_engine_sample_hyper_sums.argtypes = [C.c_void_p, C.c_int32, _f64p, C.POINTER(PaHyper)]
     lib.pa_engine_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(PaTrace)]
     lib.pa_engine_counters.argtypes = [C.c_void_p, C.POINTER(PaCounters)]
@@ -345,6 +346,15 @@ class Engine:
         h = PaHyper()
         _check(self._lib.pa_engine_sample_hyper(self._h, it, ids.ctypes.data_as(_i32p), len(ids), C.byref(h)))
         return h.as_dict()
+
+    def element_blob(self, c: int) -> np.ndarray:
+        """The packed device image of element `c` (ElemHeader + arrays, csrc/pa_internal.h); empty for a filtered element."""
+        size = C.c_int64(0)
+        _check(self._lib.pa_engine_element_blob(self._h, int(c), None, 0, C.byref(size)))
+        buf = np.zeros(size.value, dtype=np.uint8)
+        if size.value:
+            _check(self._lib.pa_engine_element_blob(self._h, int(c), buf.ctypes.data_as(_u8p), size.value, C.byref(size)))
+        return buf
 
     def hyper_sums(self, ids) -> np.ndarray:
         """This rank's partial sums of the hyper-parameter sweep over its own `ids` (pa_engine_hyper_sums)."""

@@ -155,6 +155,14 @@ int pa_engine_sample_hyper(pa_engine* e, int32_t iter, const int32_t* ids, int32
   return guarded([&]() { return e->eng.sample_hyper(iter, ids, n_ids, out); });
 }
 
+int pa_engine_element_blob(pa_engine* e, int32_t elem, uint8_t* buf, int64_t cap, int64_t* size) {
+  if (!e || !size) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.element_blob(elem, buf, cap, size); });
+}
+
 int pa_engine_hyper_sums(pa_engine* e, const int32_t* ids, int32_t n_ids, double* sums) {
   if (!e || !sums || (n_ids > 0 && !ids)) {
     g_last = "null argument";

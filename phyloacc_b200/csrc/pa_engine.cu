@@ -235,6 +235,31 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
   return PA_OK;
 }
 
+int Engine::element_blob(int32_t elem, uint8_t* buf, int64_t cap, int64_t* size) {
+  if (!loaded || elem < 0 || elem >= (int)plans.size() || !size) {
+    set_error("bad element id");
+    return PA_ERR_ARG;
+  }
+  *size = 0;
+  const ElemPlan& pl = plans[elem];
+  if (pl.filtered) return PA_OK;
+  if (!pl.blob.empty()) {  // no device bound: the image is still on the host
+    *size = (int64_t)pl.blob.size();
+    if (buf && cap >= *size) memcpy(buf, pl.blob.data(), pl.blob.size());
+    return PA_OK;
+  }
+  if (device < 0 || !d_blobs) {
+    set_error("the element image is not available");
+    return PA_ERR_STATE;
+  }
+  PA_CUDA(cudaSetDevice(device));
+  ElemHeader h;
+  PA_CUDA(cudaMemcpy(&h, d_blobs + blob_off[elem], sizeof(h), cudaMemcpyDeviceToHost));
+  *size = h.blob_bytes;
+  if (buf && cap >= *size) PA_CUDA(cudaMemcpy(buf, d_blobs + blob_off[elem], (size_t)h.blob_bytes, cudaMemcpyDeviceToHost));
+  return PA_OK;
+}
+
 int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out) {
   if (!loaded) {
     set_error("pa_engine_loglik_replay called before pa_engine_load_alignment");

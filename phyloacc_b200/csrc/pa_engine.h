@@ -80,6 +80,7 @@ struct Engine {
   int sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
   int hyper_sums(const int32_t* ids, int32_t n_ids, double* sums /* [PA_HYPER_NSUMS] */);
   int sample_hyper_from_sums(int iter, const double* sums, pa_hyper* out);
+  int element_blob(int32_t elem, uint8_t* buf, int64_t cap, int64_t* size);
   int fetch_traces();
   int fetch_range(int lo, int hi);  // wait for chains [fetched_prefix, hi) of the running launch and download their traces
   int fetch_finish();               // end of the launch: counters, warm-start states

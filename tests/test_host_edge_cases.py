@@ -195,3 +195,55 @@ def test_element_longer_than_the_device_index_range_is_refused(native_lib):
     eng.load_alignment(X, np.array([0], dtype=np.int64), np.array([60000], dtype=np.int32))  # below the limit: accepted
     assert not eng.element_info(0, gg_max=60000)["filtered"]
     eng.close()
+
+
+def test_element_image_tip_planes_follow_codes_and_site_order(native_lib):
+    """The packed element image (ElemHeader, csrc/pa_internal.h): the 4-bit codes per pattern, the site -> pattern map in the
+    canonical site order (sorted by pattern, then column) and the tips' bit planes per 256-site tile that the chain kernel's
+    pair-count pass intersects with the sampled bases -- bit t of word w of plane b of species s in tile k is set iff the code
+    of s at site 256 k + 32 w + t is exactly base b; ambiguity codes go to the `tipamb` plane, gaps / N to none."""
+    from phyloacc_b200 import synth
+
+    tree = synth.make_tree(S=9, seed=4, n_out=2, n_target=2)
+    batch = synth.simulate(tree, C=3, length=100, seed=6, lengths=[70, 300, 515], gap_frac=0.05, missing_frac=0.0, ambig_frac=0.03)
+    prm = pab.default_params()
+    eng = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup,
+                            conserve=tree.conserve, device=-1)
+    eng.load_alignment(batch.X, batch.elem_start, batch.elem_len)
+    names = ["n", "ni", "S", "P", "Ppad", "GG", "W", "n_slots", "n_up", "n_down", "elem_id", "blob_bytes", "off_parent", "off_child",
+             "off_flags", "off_tiprow", "off_orig", "off_dist", "off_int", "off_intidx", "off_su", "off_slot", "off_up_nodes", "off_up_off",
+             "off_down_nodes", "off_down_off", "off_codes", "off_weights", "off_gap", "off_sitepat", "off_tipplanes", "off_tipamb"]
+    n_amb = 0
+    for c in range(3):
+        info = eng.element_info(c, gg_max=600)
+        assert not info["filtered"]
+        blob = eng.element_blob(c)
+        h = dict(zip(names, np.frombuffer(blob[: 4 * len(names)].tobytes(), dtype=np.int32)))
+        S, P, Ppad, GG = int(h["S"]), int(h["P"]), int(h["Ppad"]), int(h["GG"])
+        assert h["blob_bytes"] == blob.size and S == tree.S and P == info["P"] and GG == info["GG"] and Ppad % 32 == 0
+        packed = blob[h["off_codes"]: h["off_codes"] + S * (Ppad // 2)].reshape(S, Ppad // 2)
+        codes = np.empty((S, Ppad), dtype=np.uint8)
+        codes[:, 0::2] = packed & 15
+        codes[:, 1::2] = packed >> 4
+        assert np.array_equal(codes[:, :P].T, info["pattern_codes"])
+        sitepat = np.frombuffer(blob[h["off_sitepat"]: h["off_sitepat"] + 2 * GG].tobytes(), dtype=np.uint16).astype(int)
+        assert np.all(np.diff(sitepat) >= 0) and np.array_equal(np.bincount(sitepat, minlength=P), info["pattern_weights"])
+        tiles = (GG + 255) // 256
+        planes = np.frombuffer(blob[h["off_tipplanes"]: h["off_tipplanes"] + tiles * S * 8 * 16].tobytes(), dtype=np.uint32).reshape(tiles, S, 8, 4)
+        amb = np.frombuffer(blob[h["off_tipamb"]: h["off_tipamb"] + tiles * S * 8 * 4].tobytes(), dtype=np.uint32).reshape(tiles, S, 8)
+        site_codes = codes[:, sitepat]  # [S][GG] in canonical site order
+        for s in range(S):
+            for g in range(tiles * 256):
+                k, w, t = g >> 8, (g >> 5) & 7, g & 31
+                bits = [(int(planes[k, s, w, b]) >> t) & 1 for b in range(4)]
+                a = (int(amb[k, s, w]) >> t) & 1
+                code = int(site_codes[s, g]) if g < GG else 15
+                if code in (1, 2, 4, 8):
+                    assert bits == [int(code == (1 << b)) for b in range(4)] and a == 0
+                elif code == 15:
+                    assert bits == [0, 0, 0, 0] and a == 0
+                else:
+                    assert bits == [0, 0, 0, 0] and a == 1
+                    n_amb += 1
+    assert n_amb > 10
+    eng.close()
