@@ -129,3 +129,25 @@ def test_replay_deep_tree_rescaling(native_lib, oracle_lib):
         assert np.isfinite(got).all()
         assert (np.abs(got - want) / np.abs(want)).max() < TOL
         eng.close()
+
+
+def test_element_image_on_the_device_equals_the_host_image(native_lib):
+    """pa_engine_element_blob: the image uploaded to HBM is the one the device-less engine keeps on the host."""
+    from phyloacc_b200 import synth
+
+    tree = synth.make_tree(S=10, seed=2, n_out=2, n_target=2)
+    batch = synth.simulate(tree, C=4, length=100, seed=3, lengths=[60, 280, 90, 40], gap_frac=0.03, missing_frac=0.02, ambig_frac=0.01)
+    prm = pab.default_params()
+    engs = [pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup,
+                              conserve=tree.conserve, device=d) for d in (-1, 0)]
+    for e in engs:
+        e.load_alignment(batch.X, batch.elem_start, batch.elem_len)
+    n = 0
+    for c in range(batch.C):
+        host, dev = engs[0].element_blob(c), engs[1].element_blob(c)
+        assert host.size == dev.size and np.array_equal(host, dev)
+        assert (host.size == 0) == bool(engs[0].element_info(c, gg_max=400)["filtered"])
+        n += host.size > 0
+    assert n >= 3
+    for e in engs:
+        e.close()
