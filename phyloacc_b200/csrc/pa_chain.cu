@@ -215,8 +215,8 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
         a0 = st[0]; a1 = st[kBD]; a2 = st[2 * kBD]; a3 = st[3 * kBD];                                                          \
         SCC = S.stack_sc[((PAY) >> 2) + tid];                                                                                  \
       } else {                                                                                                                 \
-        const double2* g2 = reinterpret_cast<const double2*>(gpart + (PAY));                                                   \
-        const double2 u = g2[0], v = g2[1];                                                                                    \
+        double2 u, v;                                                                                                          \
+        ldg256(gpart + (PAY), u, v);                                                                                           \
         a0 = u.x; a1 = u.y; a2 = v.x; a3 = v.y;                                                                                \
         SCC = gsc[(PAY) >> 2];                                                                                                 \
       }                                                                                                                        \
@@ -286,9 +286,7 @@ __device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const do
           st[0] = o0; st[kBD] = o1; st[2 * kBD] = o2; st[3 * kBD] = o3;
           S.stack_sc[park * kBD + tid] = (int16_t)sc;
         }
-        double2* g2 = reinterpret_cast<double2*>(gpart + op.x);
-        g2[0] = make_double2(o0, o1);
-        g2[1] = make_double2(o2, o3);
+        stg256(gpart + op.x, o0, o1, o2, o3);
         gsc[op.x >> 2] = (int16_t)sc;
       }
       // the last node of the program is the root (or nothing was computed: missing root -> likelihood 1)
@@ -640,9 +638,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           double2 pa[4], pc[4];
 #pragma unroll
           for (int j = 3; j >= 0; j--) {
-            const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * Gtop + j].y);
-            pa[j] = g2[0];
-            pc[j] = g2[1];
+            ldg256(gp + S.hs[4 * Gtop + j].y, pa[j], pc[j]);
           }
           for (int G = Gtop; G >= 0; G--) {
             if (G == Gtop || (G & 7) == 7) {  // "all-gap" flags of internal nodes 32 * (G >> 3) .. + 31 at this site's pattern (bpp_c.cpp:686-690)
@@ -691,9 +687,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
             if (G > 0) {
 #pragma unroll
               for (int j = 3; j >= 0; j--) {
-                const double2* g2 = reinterpret_cast<const double2*>(gp + S.hs[4 * (G - 1) + j].y);
-                pa[j] = g2[0];
-                pc[j] = g2[1];
+                ldg256(gp + S.hs[4 * (G - 1) + j].y, pa[j], pc[j]);
               }
             }
 #pragma unroll

@@ -139,6 +139,14 @@ __device__ __forceinline__ void build_P_row_quad(const SubstDev& sd, double t, d
   r3 = ((e0 * sd.A[0][k + 3] + e1 * sd.A[1][k + 3]) + e2 * sd.A[2][k + 3]) + e3 * sd.A[3][k + 3];
 }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one partial = four doubles = one 32-byte sector, moved by one instruction
+__device__ __forceinline__ void ldg256(const double* p, double2& u, double2& v) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(u.x), "=d"(u.y), "=d"(v.x), "=d"(v.y) : "l"(p));
+}
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- element view (pointers into the blob)
 struct ElemView {
   const ElemHeader* h;
