@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
             const double2* lp2 = reinterpret_cast<const double2*>(logP + ((size_t)k * L.n_max + i) * 16);
             double2 lp[8];
 #pragma unroll
-            for (int b = 0; b < 8; b++) lp[b] = lp2[b];
+            for (int b = 0; b < 8; b += 2) ldg256(reinterpret_cast<const double*>(lp2 + b), lp[b], lp[b + 1]);
             const uint4* c4 = reinterpret_cast<const uint4*>(&S.cnt[i * 16]);
 #pragma unroll
             for (int w = 0; w < 4; w++) {
@@ -1044,7 +1044,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
               r0 = pp[0]; r1 = pp[1]; r2 = pp[2]; r3 = pp[3];
             } else build_P_row_quad(sd, S.dist[i], new_rate, j, r0, r1, r2, r3);
             double* lp = logP + ((size_t)cls * L.n_max + i) * 16 + j * 4;
-            lp[0] = log(r0); lp[1] = log(r1); lp[2] = log(r2); lp[3] = log(r3);
+            stg256(lp, log(r0), log(r1), log(r2), log(r3));
             if (S.Z[i] == cls) {
               double* pc = S.Pcur + i * 16 + j * 4;
               pc[0] = r0; pc[1] = r1; pc[2] = r2; pc[3] = r3;
