@@ -2,20 +2,29 @@
 """bench.py -- throughput of the PhyloAcc-ST hot path (per-element MCMC) on B200, BASELINE.json's metric:
 element x MCMC-iterations / second.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3] [--full-run]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one resident batch of synthetic elements drawn from the cfg2 workload
-(BASELINE.json configs[1]: 43-taxon ratite-shaped tree, element lengths lognormal(median 150, sigma 0.8) clipped to
-[50, 2000] bp): every element runs its M0, M1 and M2 chains for BURNIN+MCMC = 1500 iterations on the device.
-value   = elements x 3 x 1500 / device time of the chain kernel, inputs resident in HBM (CUDA events);
-e2e     = the same count / time of the public C-ABI call sequence with HOST buffers: pa_engine_load_alignment
-          (integer front-end + H2D) + pa_engine_run (chains + D2H of traces + Eval2 / summaries on the host, finished chains
-          summarised while later ones are still being sampled);
-roofline: FP64 FMA (north_star) -- algorithmic FMA per SURVEY.md §8d from the engine's work counters over the measured
-          FP64 FMA peak of this GPU (micro-benchmark, MEASURED_PEAKS.json has no FP64 entry);
-cpu_baseline / --impl reference: the UNMODIFIED reference sources built against the compat shim
-          (oracle/_ref/PhyloAcc-ST-ref) on the host cores, on a bounded sample of the same workload.
+Workloads (BASELINE.json configs[0..2]; `config.workload` names the one that ran, cfg2 is the default / headline):
+  cfg1  simu_500_200 shape: 43-taxon ratite-shaped tree, 500 elements x 200 bp (one step = the whole 500-element job)
+  cfg2  ratite-genome scale: 43 taxa, element lengths lognormal(median 150, sigma 0.8) clipped to [50, 2000] bp, 2048 elements
+        resident per GPU per step
+  cfg3  240-taxon Zoonomia-shaped tree x 200 bp (deep-tree layout), 592 elements resident per GPU per step
+A "step" is one pass of the hot path over one resident batch: every element runs its M0, M1 and M2 chains for BURNIN + MCMC = 1500
+iterations on the device.
+value   = elements x 3 x 1500 / device time of the chain kernel, inputs resident in HBM (CUDA events on the launching stream);
+e2e     = the same count / wall time of the public C-ABI call sequence with HOST buffers, over the same K steps:
+          pa_engine_load_alignment (integer front-end + H2D) + pa_engine_run (chains + summaries + D2H);
+roofline: FP64 FMA (north_star) -- algorithmic FMA per SURVEY.md §8d from the engine's work counters over the FP64 FMA peak of this
+          GPU measured live (MEASURED_PEAKS.json has no FP64 entry; the theoretical 148 SM x 64 DFMA/clk is printed beside it);
+cpu_baseline / --impl reference: the UNMODIFIED reference sources built against the compat shim (oracle/_ref/PhyloAcc-ST-ref) on all
+          host cores, on a bounded STRATIFIED sample of the same workload: every step takes a fresh slice of >= 8 elements per core
+          whose lengths are evenly spaced quantiles of the workload's length distribution, with short chains (per-iteration cost
+          does not depend on chain length).  Two shapes are timed -- one process with NUM_THREAD = cores (OpenMP, schedule(guided))
+          and the reference's native deployment shape, `cores` concurrent single-thread processes over length-balanced batches
+           -- and the FASTER one is reported, named in `cpu_baseline.shape`.
+--full-run: additionally run BASELINE's whole cfg2 job (280k elements, sharded over the ranks by the cost model of shard.py) once
+          through the public API in resident waves and report it under "full_run".
 """
 from __future__ import annotations
 
@@ -37,8 +46,25 @@ sys.path.insert(0, ROOT)
 METRIC = "element×MCMC-iter/sec (PhyloAcc-ST)"
 UNIT = "element-iterations/s"
 BURNIN, MCMC = 500, 1000  # driver defaults (params.py:130-131 of the reference)
-ELEMS_PER_GPU = int(os.environ.get("PA_BENCH_ELEMS", "2048"))
-WORKLOAD = "cfg2: PhyloAcc-ST ratite-genome scale, 43 taxa, element lengths lognormal(150,0.8) in [50,2000] bp, M0+M1+M2 x (500+1000) iterations"
+
+WORKLOADS = {
+    "cfg1": dict(name="cfg1: PhyloAcc-ST simu_500_200 shape, 43 taxa, 500 elements x 200 bp, M0+M1+M2 x (500+1000) iterations",
+                 taxa=43, length=200, elems=500, ref_elems_per_core=8, ref_chain=(20, 40)),
+    "cfg2": dict(name="cfg2: PhyloAcc-ST ratite-genome scale, 43 taxa, element lengths lognormal(150,0.8) in [50,2000] bp, M0+M1+M2 x (500+1000) iterations",
+                 taxa=43, length="cfg2", elems=int(os.environ.get("PA_BENCH_ELEMS", "2048")), ref_elems_per_core=8, ref_chain=(20, 40)),
+    "cfg3": dict(name="cfg3: PhyloAcc-ST on a 240-taxon Zoonomia-shaped tree, elements x 200 bp, M0+M1+M2 x (500+1000) iterations",
+                 taxa=240, length=200, elems=592, ref_elems_per_core=4, ref_chain=(10, 20)),
+}
+FULL_RUN_ELEMS = 280000  # BASELINE.json configs[1]
+
+
+def make_workload_tree(wl):
+    from phyloacc_b200 import synth
+
+    if wl["taxa"] == 43:
+        return synth.make_tree()
+    S = wl["taxa"]
+    return synth.make_tree(S=S, seed=9, n_out=max(2, S // 6), n_target=max(2, S // 5))
 
 
 def _clock_sampler(stop, out, dev):
@@ -67,90 +93,193 @@ def _clock_summary(samples):
             "reasons": sorted(reasons)}
 
 
-def make_batch(n_elems, seed):
-    from phyloacc_b200 import synth
+# ------------------------------------------------------------------------------------------------ the CPU reference
+def stratified_lengths(wl, n, slice_index, n_slices):
+    """Lengths of slice `slice_index` of a stratified sample of n * n_slices elements: evenly spaced quantiles of the workload's
+    length distribution, interleaved so that every slice is itself stratified and no two slices share an element."""
+    if wl["length"] != "cfg2":
+        return np.full(n, int(wl["length"]), dtype=np.int32)
+    from statistics import NormalDist
 
-    tree = synth.make_tree()
-    batch = synth.simulate(tree, C=n_elems, length="cfg2", seed=seed)
-    return tree, batch
+    tot = n * n_slices
+    q = (np.arange(n) * n_slices + (slice_index % n_slices) + 0.5) / tot
+    z = np.array([NormalDist().inv_cdf(float(x)) for x in q])
+    return np.clip(np.round(150.0 * np.exp(0.8 * z)), 50, 2000).astype(np.int32)
 
 
-def reference_throughput(tree, cores, seconds_target=20.0, label="reference"):
-    """Time the unmodified reference (shim build) with NUM_THREAD = all host cores on a bounded sample of the workload:
-    per-iteration cost does not depend on chain length, so the sample uses shorter chains (BURNIN 30 + MCMC 60)."""
+def _lpt_batches(lengths, k):
+    """Longest-processing-time split of element indices into k batches of near-equal total length (the steady state of the
+    reference's deployment -- many 50-locus batches streaming through `cores` workers -- has no tail; a bounded sample must not
+    invent one)."""
+    order = np.argsort(-np.asarray(lengths), kind="stable")
+    loads = np.zeros(k)
+    out = [[] for _ in range(k)]
+    for i in order:
+        j = int(np.argmin(loads))
+        out[j].append(int(i))
+        loads[j] += lengths[i]
+    return [sorted(b) for b in out if b]
+
+
+def _count_done(path):
+    try:
+        with open(path) as f:
+            return max(0, len(f.read().strip().split("\n")) - 1)
+    except OSError:
+        return 0
+
+
+def reference_step(wl, tree, cores, slice_index, n_slices, shape):
+    """One bounded sample of the workload through the unmodified reference binary (shim build).  shape = "omp" (one process,
+    NUM_THREAD = cores) or "procs" (cores concurrent single-thread processes, length-balanced batches).
+    Returns (element-iterations/s, wall seconds, elements done, description)."""
     from phyloacc_b200 import synth
 
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-ST-ref")
-    burn, mc = 30, 60
-    kind = "reference"
-    if not os.path.exists(ref_bin):
-        kind = "port"
-    n_el = max(cores, 8) * 2
-    batch = synth.simulate(tree, C=n_el, length="cfg2", seed=4242)
+    burn, mc = wl["ref_chain"]
+    n_el = max(32, wl["ref_elems_per_core"] * cores)
+    lengths = stratified_lengths(wl, n_el, slice_index, n_slices)
+    batch = synth.simulate(tree, lengths=lengths, seed=4242 + slice_index)
     tmp = tempfile.mkdtemp(prefix="pa_bench_ref_")
     try:
-        if kind == "reference":
-            cfg = synth.write_files(batch, tmp, prefix="ref", params=dict(BURNIN=burn, MCMC=mc, CHAIN=1, ADAPT_FREQ=500, SEED=1, NUM_THREAD=cores))
+        if not os.path.exists(ref_bin):
+            return _port_step(wl, tree, batch, burn, mc, tmp)
+        prm = dict(BURNIN=burn, MCMC=mc, CHAIN=1, ADAPT_FREQ=500, SEED=1 + slice_index)
+        if shape == "omp":
+            cfg = synth.write_files(batch, tmp, prefix="ref", params=dict(prm, NUM_THREAD=cores))
             t0 = time.time()
             with open(os.path.join(tmp, "log.txt"), "w") as lf:
                 subprocess.run([ref_bin, cfg], stdout=lf, stderr=subprocess.STDOUT, check=True)
             dt = time.time() - t0
-            n_done = 0
-            with open(os.path.join(tmp, "out", "ref_rate_postZ_M0.txt")) as f:
-                n_done = max(0, len(f.read().strip().split("\n")) - 1)
+            n_done = _count_done(os.path.join(tmp, "out", "ref_rate_postZ_M0.txt"))
         else:
-            from oracle import coracle, frontend as fe  # cpu_baseline leg only
-
-            cfg = synth.write_files(batch, tmp, prefix="ref", params=dict(BURNIN=burn, MCMC=mc, CHAIN=1, ADAPT_FREQ=500, SEED=1))
-            P = fe.load_params(cfg)
-            otree = fe.parse_mod(P.PHYTREE_FILE)
-            names, X = fe.load_fasta(P.ALIGN_FILE)
-            _, pos = fe.load_bed(P.SEG_FILE)
-            starts, lens = fe.element_layout(pos)
-            model = fe.build_model(otree, P)
-            X = fe.reorder_alignment(otree, names, X)
+            batches = _lpt_batches(lengths, cores)
+            cfgs = []
+            for b, ids in enumerate(batches):
+                d = os.path.join(tmp, f"b{b}")
+                cfgs.append(synth.write_files(batch, d, prefix="ref", ids=ids, params=dict(prm, NUM_THREAD=1)))
             t0 = time.time()
-            n_done = 0
-            for c in range(min(n_el, 4)):
-                el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
-                if el.filter:
-                    continue
-                h = coracle.ElementHandle(model, el)
-                for resZ in (0, 2, 1):
-                    h.chain(resZ, 1, c * 4 + resZ)
-                n_done += 1
+            procs = []
+            for b, cfg in enumerate(cfgs):
+                lf = open(os.path.join(tmp, f"b{b}", "log.txt"), "w")
+                procs.append((subprocess.Popen([ref_bin, cfg], stdout=lf, stderr=subprocess.STDOUT), lf))
+            for p, lf in procs:
+                p.wait()
+                lf.close()
             dt = time.time() - t0
-            cores = 1
+            n_done = sum(_count_done(os.path.join(tmp, f"b{b}", "out", "ref_rate_postZ_M0.txt")) for b in range(len(cfgs)))
         value = n_done * 3 * (burn + mc) / dt
-        return dict(value=value, unit=UNIT, cores=cores, kind=kind,
-                    sample=f"{n_done} cfg2 elements x 3 models x ({burn}+{mc}) iterations, NUM_THREAD={cores}, {dt:.1f} s wall "
-                           f"(reference sources + Armadillo/GSL compat shim, g++ -O2 -fopenmp)"), dt
+        what = (f"{n_done} {wl['name'].split(':')[0]} elements (stratified slice {slice_index} of {n_slices}, lengths {int(lengths.min())}-{int(lengths.max())} bp, "
+                f"mean {lengths.mean():.0f}) x 3 models x ({burn}+{mc}) iterations, "
+                + (f"one process NUM_THREAD={cores}" if shape == "omp" else f"{len(batches)} concurrent single-thread processes, length-balanced batches")
+                + f", {dt:.1f} s wall (reference sources + Armadillo/GSL compat shim, g++ -O2 -fopenmp)")
+        return value, dt, n_done, what
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def run_reference_arm(args, rank, world):
-    if rank != 0:
-        return
+def _port_step(wl, tree, batch, burn, mc, tmp):
+    """No reference binary on this box: time the oracle port on one core (cpu_baseline.kind = "port")."""
+    from oracle import coracle, frontend as fe  # cpu_baseline leg only
     from phyloacc_b200 import synth
 
-    tree = synth.make_tree()
+    cfg = synth.write_files(batch, tmp, prefix="ref", params=dict(BURNIN=burn, MCMC=mc, CHAIN=1, ADAPT_FREQ=500, SEED=1))
+    P = fe.load_params(cfg)
+    otree = fe.parse_mod(P.PHYTREE_FILE)
+    names, X = fe.load_fasta(P.ALIGN_FILE)
+    _, pos = fe.load_bed(P.SEG_FILE)
+    starts, lens = fe.element_layout(pos)
+    model = fe.build_model(otree, P)
+    X = fe.reorder_alignment(otree, names, X)
+    t0 = time.time()
+    n_done = 0
+    for c in range(min(batch.C, 4)):
+        el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
+        if el.filter:
+            continue
+        h = coracle.ElementHandle(model, el)
+        for resZ in (0, 2, 1):
+            h.chain(resZ, 1, c * 4 + resZ)
+        n_done += 1
+    dt = time.time() - t0
+    return n_done * 3 * (burn + mc) / dt, dt, n_done, f"oracle port, {n_done} elements x 3 models x ({burn}+{mc}) iterations on 1 core, {dt:.1f} s"
+
+
+def reference_calibrate(wl, tree, cores, n_slices):
+    """Both shapes on slice 0; returns (best shape, {shape: rate})."""
+    rates = {}
+    have_bin = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-ST-ref"))
+    for shape in (("omp", "procs") if have_bin else ("omp",)):
+        rates[shape] = reference_step(wl, tree, cores, 0, n_slices, shape)[0]
+    best = max(rates, key=rates.get)
+    return best, rates
+
+
+def cpu_baseline_block(wl, tree, cores, n_slices=25, slices=(1, 2)):
+    """The cpu_baseline object of our arm's line: calibrate the shape on slice 0, then time `slices` with the faster one."""
+    have_bin = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-ST-ref"))
+    best, rates = reference_calibrate(wl, tree, cores, n_slices)
+    tot_units, tot_dt, what = 0.0, 0.0, ""
+    for s in slices:
+        v, dt, n_done, what = reference_step(wl, tree, cores, s, n_slices, best)
+        tot_units += v * dt
+        tot_dt += dt
+    return dict(value=tot_units / tot_dt, unit=UNIT, cores=cores if have_bin else 1, kind="reference" if have_bin else "port", shape=best,
+                shape_rates={k: round(v, 1) for k, v in rates.items()},
+                sample=f"{len(slices)} slices; last: {what}")
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    tree = make_workload_tree(wl)
     cores = os.cpu_count() or 1
-    vals, ms = [], []
-    last = None
-    for k in range(args.warmup + args.steps):
-        base, dt = reference_throughput(tree, cores)
-        if k >= args.warmup:
-            vals.append(base["value"])
-            ms.append(dt * 1e3)
-        last = base
-    v = float(np.mean(vals))
-    last["value"] = v
+    have_bin = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-ST-ref"))
+    n_slices = max(2, args.steps + args.warmup)
+    # warm-up steps alternate the two shapes on their own slices; the timed steps use the faster one (with fewer than two warm-up
+    # steps both shapes are calibrated on slice 0 first, untimed)
+    rates = {}
+    shapes = ("omp", "procs") if have_bin else ("omp",)
+    if args.warmup < len(shapes):
+        best, rates = reference_calibrate(wl, tree, cores, n_slices)
+    for k in range(args.warmup):
+        sh = shapes[k % len(shapes)]
+        v = reference_step(wl, tree, cores, k, n_slices, sh)[0]
+        rates[sh] = max(rates.get(sh, 0.0), v)
+    best = max(rates, key=rates.get)
+    units, secs, what = 0.0, 0.0, ""
+    for k in range(args.steps):
+        v, dt, n_done, what = reference_step(wl, tree, cores, args.warmup + k, n_slices, best)
+        units += v * dt
+        secs += dt
+    v = units / secs
+    base = dict(value=v, unit=UNIT, cores=cores if have_bin else 1, kind="reference" if have_bin else "port", shape=best,
+                shape_rates={k: round(x, 1) for k, x in rates.items()},
+                sample=f"{args.steps} distinct stratified slices ({args.steps + args.warmup} incl. warm-up); last: {what}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": last["sample"]}, "cpu_baseline": last,
+            "ms_per_step": secs * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl["name"], "sample": base["sample"]}, "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def newest_traffic(workload_key):
+    """DRAM bytes per chain-iteration of the chain kernel from the newest committed ncu capture of this workload
+    (profiles/r<round>_v<k>_traffic[_cfgN].json); (None, None) when there is none."""
+    import glob
+    import re
+
+    suffix = "" if workload_key == "cfg2" else f"_{workload_key}"
+    cands = [q for q in glob.glob(os.path.join(ROOT, "profiles", f"r*_v*_traffic{suffix}.json"))]
+    if not cands:
+        return None, None
+    cands.sort(key=lambda q: [int(x) for x in re.findall(r"\d+", os.path.basename(q))])
+    try:
+        with open(cands[-1]) as f:
+            return float(json.load(f)["dram_bytes_per_chain_iteration"]), os.path.basename(cands[-1])
+    except Exception:
+        return None, None
 
 
 def main():
@@ -159,9 +288,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--elems", type=int, default=ELEMS_PER_GPU, help="elements resident per GPU per step")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--elems", type=int, default=0, help="elements resident per GPU per step (default: the workload's)")
+    ap.add_argument("--full-run", action="store_true", help="also run the whole 280k-element cfg2 job once through the public API")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.elems:
+        wl["elems"] = args.elems
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -169,13 +303,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, wl, rank)
         return
 
     import torch
     import torch.distributed as dist
 
     import phyloacc_b200 as pab
+    from phyloacc_b200 import synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
@@ -185,7 +320,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic shard of this rank (elements are independent: contiguous element ranges per GPU, no data-path collective)
-    tree, batch = make_batch(args.elems, seed=1000 + rank)
+    tree = make_workload_tree(wl)
+    batch = synth.simulate(tree, C=wl["elems"], length=wl["length"], seed=1000 + rank)
     prm = pab.default_params()
     prm.burnin, prm.mcmc, prm.adapt_freq, prm.seed = BURNIN, MCMC, 500, 1 + rank
     prm.num_thread = max(1, (os.cpu_count() or 1) // max(world, 1))
@@ -197,7 +333,7 @@ def main():
     Xn = X_host.numpy()
     eng.load_alignment(Xn, batch.elem_start, batch.elem_len)
     ids = np.arange(batch.C, dtype=np.int32)
-    n_active = int(sum(not eng.element_info(int(c), gg_max=2048)["filtered"] for c in ids))
+    n_active = int(sum(not eng.element_info(int(c))["filtered"] for c in ids))
     T = BURNIN + MCMC
     units_per_step = n_active * 3 * T
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # L2 flush between timed steps (126 MB L2)
@@ -225,24 +361,60 @@ def main():
             ev[k][1].record(stream)
     barrier()
     wall_ms = (time.time() - t_wall0) * 1e3
-    stop.set()
-    sampler.join(timeout=2)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     ms_step = float(np.mean(kern_ms))
     cnt = eng.collect() and eng.counters()
 
-    # ---- end to end through the C ABI with host buffers (front-end + H2D + chains + D2H traces + Eval2)
+    # ---- end to end through the C ABI with host buffers, over the same number of steps (front-end + H2D + chains + summaries + D2H)
     barrier()
     t0 = time.time()
-    e2e_steps = max(1, min(args.steps, 2))
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         eng.load_alignment(Xn, batch.elem_start, batch.elem_len)
         res = eng.run(ids)
     barrier()
-    e2e_ms = (time.time() - t0) * 1e3 / e2e_steps
+    e2e_ms = (time.time() - t0) * 1e3 / args.steps
+    stop.set()
+    sampler.join(timeout=2)
     h2d = int(batch.X.nbytes)
-    d2h = int(n_active * 3 * T * (6 * 8 + ((2 * tree.S - 1 + 15) // 16) * 4))
+    d2h = int(eng.d2h_bytes()) if hasattr(eng, "d2h_bytes") else int(n_active * 3 * T * (6 * 8 + ((2 * tree.S - 1 + 15) // 16) * 4))
     n_acc = int(np.sum((res.logBF1 > 5) & (res.logBF2 > 5) & (res.filtered == 0)))
+
+    # ---- optional: BASELINE's whole cfg2 job (280k elements over all ranks) through the public API in resident waves
+    full = None
+    if args.full_run:
+        from phyloacc_b200 import shard
+
+        wl2 = WORKLOADS["cfg2"]
+        tree2 = tree if args.workload != "cfg3" else make_workload_tree(wl2)
+        rng = np.random.default_rng(280)
+        all_len = np.clip(np.round(150.0 * np.exp(0.8 * rng.standard_normal(FULL_RUN_ELEMS))), 50, 2000).astype(np.int32)
+        mine = shard.shard_ranges(all_len.astype(np.float64) * (tree2.S - 1), world)[rank]
+        my_len = all_len[mine.start:mine.stop]
+        big = synth.simulate(tree2, lengths=my_len, seed=2800 + rank)
+        eng2 = eng if args.workload != "cfg3" else pab.Engine.create(tree2.parent, tree2.children, tree2.dist, tree2.pi, tree2.Q, params=prm,
+                                                                      outgroup=tree2.outgroup, conserve=tree2.conserve, device=local_rank)
+        wave = 8192
+        barrier()
+        t0 = time.time()
+        n_full_active, n_full_acc = 0, 0
+        for w0 in range(0, big.C, wave):
+            w1 = min(big.C, w0 + wave)
+            g0, g1 = int(big.elem_start[w0]), int(big.elem_start[w1 - 1] + big.elem_len[w1 - 1])
+            Xw = np.ascontiguousarray(big.X[:, g0:g1])
+            eng2.load_alignment(Xw, big.elem_start[w0:w1] - g0, big.elem_len[w0:w1])
+            r2 = eng2.run(np.arange(w1 - w0, dtype=np.int32))
+            n_full_active += int((r2.filtered == 0).sum())
+            n_full_acc += int(np.sum((r2.logBF1 > 5) & (r2.logBF2 > 5) & (r2.filtered == 0)))
+        barrier()
+        full_s = time.time() - t0
+        tf = torch.tensor([full_s], device="cuda", dtype=torch.float64)
+        nf = torch.tensor([float(n_full_active), float(n_full_acc), float(big.C)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nf, op=dist.ReduceOp.SUM)
+        full = {"elements": int(nf[2]), "active_elements": int(nf[0]), "accelerated_calls": int(nf[1]), "seconds": float(tf[0]),
+                "value": float(nf[0]) * 3 * T / float(tf[0]), "unit": UNIT, "waves_of": wave,
+                "what": "whole cfg2 job through pa_engine_load_alignment + pa_engine_run with host buffers, elements sharded over the ranks by cost"}
 
     # ---- reduce over ranks: max time, summed units; one gather of per-element summaries (NCCL)
     t_ms = torch.tensor([ms_step, e2e_ms, wall_ms], device="cuda", dtype=torch.float64)
@@ -270,28 +442,22 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        hbm_bytes = float(eng_blob_bytes(eng, ids)) + d2h  # alignment streamed once + trace write-back
-        # DRAM traffic of the chain kernel per launch: measured once under ncu (newest profiles/r*_v*_traffic.json, bytes per
-        # chain-iteration of this workload) and scaled to this launch's chain-iterations; null when the file is absent
-        traffic, traffic_file = None, None
-        try:
-            import glob
-            import re
-
-            cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_v*_traffic.json")),
-                           key=lambda q: [int(x) for x in re.findall(r"\d+", os.path.basename(q))])
-            traffic_file = os.path.basename(cands[-1])
-            with open(cands[-1]) as f:
-                traffic = float(json.load(f)["dram_bytes_per_chain_iteration"]) * float(cnt["chain_iterations"])
-        except Exception:
-            pass
+        hbm_bytes = float(eng_blob_bytes(eng, ids)) + d2h  # alignment streamed once + result write-back
+        # DRAM traffic of the chain kernel per launch: measured once under ncu on this workload (newest committed capture, bytes per
+        # chain-iteration) and scaled to this launch's chain-iterations; null when no capture of this workload is committed
+        per_iter, traffic_file = newest_traffic(args.workload)
+        traffic = per_iter * float(cnt["chain_iterations"]) if per_iter else None
+        sm_clock = (_clock_summary(clocks)["sm_mhz"] or 1965) * 1e6
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "traffic_source": f"ncu dram__bytes_read+write of one bench-size chain_kernel launch (profiles/{traffic_file})",
-                "peak_source": "measured live: register-resident DFMA micro-benchmark (pa_device_fp64_peak)",
+                "traffic": traffic,
+                "traffic_source": (f"ncu dram__bytes_read+write of one bench-size chain_kernel launch (profiles/{traffic_file}), scaled by chain-iterations"
+                                   if traffic_file else None),
+                "peak_source": "measured live: register-resident DFMA micro-benchmark (pa_device_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "peak_theoretical": 148 * 64 * 2 * sm_clock / 1e12,
                 "algorithmic_fma_per_step": fma, "kernel": "chain_kernel",
                 "hbm": {"achieved": hbm_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s",
-                        "note": "algorithmic bytes (alignment read once + trace rows written); the kernel's measured DRAM traffic is below"},
+                        "note": "algorithmic bytes (alignment read once + results written); the kernel's measured DRAM traffic is below"},
                 # measured DRAM traffic of the launch (arena spills out of L2) over this run's kernel time: how far the kernel is from
                 # being bandwidth-bound
                 "dram_measured": ({"achieved": traffic / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -303,18 +469,19 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step_all, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "elements_per_gpu_per_step": args.elems, "active_elements_rank0": n_active,
+                "config": {"workload": wl["name"], "elements_per_gpu_per_step": wl["elems"], "active_elements_rank0": n_active,
                            "iterations_per_chain": T, "models": 3, "l2": "flushed between timed steps (256 MiB write)",
                            "parallelism": f"elements sharded over {world} GPU(s), no data-path collective, one all_gather of summaries"},
                 "roofline": roof,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.steps},
                 "pruned_site_liks": {"value": site_liks, "unit": "full-tree-equivalent site likelihoods/s", "columns_per_pattern": compression},
                 "gpu_launches": int(cnt["kernel_launches"]) * args.steps,
                 "clocks": _clock_summary(clocks),
                 "work": {k: int(v) for k, v in cnt.items()}, "accelerated_calls_rank0": n_acc}
+        if full is not None:
+            line["full_run"] = full
         if not args.no_cpu_baseline:
-            base, _ = reference_throughput(tree, os.cpu_count() or 1)
-            line["cpu_baseline"] = base
+            line["cpu_baseline"] = cpu_baseline_block(wl, tree, os.cpu_count() or 1)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -325,7 +492,7 @@ def eng_blob_bytes(eng, ids):
     # packed alignment bytes read by the chains: 4-bit codes of every pattern for every species
     tot = 0
     for c in ids[: min(len(ids), 256)]:
-        info = eng.element_info(int(c), gg_max=2048)
+        info = eng.element_info(int(c))
         if not info["filtered"]:
             tot += info["P"] * eng.S // 2
     return tot * (len(ids) / max(1, min(len(ids), 256)))

@@ -99,8 +99,11 @@ typedef struct pa_trace {
 } pa_trace;
 
 /* Integer front-end of one element (BPP_C::BPP_C, bpp_c.hpp:143-476) for parity tests. Caller-allocated:
- * missing/children2/parent2/distances2/nodes sized N (children2 2N); codes sized S*GG_max, weights/site_pattern GG_max. */
+ * missing/children2/parent2/distances2/nodes sized N (children2 2N); pattern_codes holds cap_P * S bytes, pattern_weights cap_P
+ * entries, site_pattern cap_GG entries.  The scalar fields are always filled (call once with null arrays to size the buffers); when
+ * an array is non-null and its capacity is smaller than the element needs, nothing is copied and PA_ERR_ARG is returned. */
 typedef struct pa_element_info {
+  int32_t cap_P, cap_GG;    /* in: capacities of pattern_codes / pattern_weights (patterns) and site_pattern (columns) */
   int32_t filtered, GG, P, root, n_nodes;
   uint8_t* missing; int32_t* nodes; int32_t* children2; int32_t* parent2; double* distances2;
   uint8_t* pattern_codes;   /* [P][S] nibble masks of the unique columns, sorted lexicographically */

@@ -64,7 +64,8 @@ class PaTrace(C.Structure):
 
 
 class PaElementInfo(C.Structure):
-    _fields_ = [("filtered", C.c_int32), ("GG", C.c_int32), ("P", C.c_int32), ("root", C.c_int32), ("n_nodes", C.c_int32),
+    _fields_ = [("cap_P", C.c_int32), ("cap_GG", C.c_int32),
+                ("filtered", C.c_int32), ("GG", C.c_int32), ("P", C.c_int32), ("root", C.c_int32), ("n_nodes", C.c_int32),
                 ("missing", _u8p), ("nodes", _i32p), ("children2", _i32p), ("parent2", _i32p), ("distances2", _f64p),
                 ("pattern_codes", _u8p), ("pattern_weights", _i32p), ("site_pattern", _i32p), ("fixZ", _u8p), ("n_slots", C.c_int32)]
 
@@ -283,12 +284,18 @@ class Engine:
         _check(self._lib.pa_engine_get_params(self._h, C.byref(p)))
         return p
 
-    def element_info(self, c: int, gg_max: int = 4096):
+    def element_info(self, c: int, gg_max: int | None = None):
+        """Integer front-end of element ``c``.  The pattern / column buffers are sized from the element itself (a first call with
+        null arrays returns GG and P); ``gg_max`` is accepted for compatibility and ignored."""
         N, S = self.N, self.S
+        probe = PaElementInfo()
+        _check(self._lib.pa_engine_element_info(self._h, c, C.byref(probe)))
+        gg_max = max(1, int(probe.GG), int(probe.P))
         bufs = dict(missing=np.zeros(N, np.uint8), nodes=np.zeros(N, np.int32), children2=np.zeros((N, 2), np.int32),
                     parent2=np.zeros(N, np.int32), distances2=np.zeros(N), pattern_codes=np.zeros((gg_max, S), np.uint8),
                     pattern_weights=np.zeros(gg_max, np.int32), site_pattern=np.zeros(gg_max, np.int32), fixZ=np.zeros((3, N), np.uint8))
         info = PaElementInfo()
+        info.cap_P = info.cap_GG = gg_max
         info.missing = bufs["missing"].ctypes.data_as(_u8p)
         info.nodes = bufs["nodes"].ctypes.data_as(_i32p)
         info.children2 = bufs["children2"].ctypes.data_as(_i32p)

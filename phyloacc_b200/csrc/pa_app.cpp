@@ -158,8 +158,10 @@ static int run_from_config(const char* cfg_path) {
       pa_results wres{wn, N, filtered.data() + w0, loglik.data() + (size_t)w0 * 3, loglik_max.data() + (size_t)w0 * 3,
                       maxZ.data() + (size_t)w0 * 3 * N, med.data() + (size_t)w0 * 15, postZ.data() + (size_t)w0 * 3 * N * 4};
       // SAMPLE_HYPER 1 runs only the full model (main.cpp:463-494); outer iterations after the first continue every chain
-      // from its last state (initMCMC with iter > 0, bpp_c.cpp:148-177)
-      rc = e->eng.sample(ids.data() + w0, wn, P.sample_hyper ? (1 << PA_M2) : 7, iter > 0, iter);
+      // from its last state (initMCMC with iter > 0, bpp_c.cpp:148-177).  The reference saves that state only `if(UpHyper)`
+      // (bpp_c.cpp:474-485): with SAMPLE_HYPER 0 and CHAIN > 1 its later iterations restart from bpp.cur_Z (all zeros: every node
+      // starts in the background state) and the INIT_* rates -- a fresh chain on a new random stream here (Z = 1 start as in iter 0).
+      rc = e->eng.sample(ids.data() + w0, wn, P.sample_hyper ? (1 << PA_M2) : 7, P.sample_hyper && iter > 0, iter);
       if (rc == PA_OK) rc = e->eng.collect(&wres);
       if (rc != PA_OK) {
         std::cerr << "(Error. " << get_error() << ")" << std::endl;

@@ -86,6 +86,10 @@ int pa_engine_element_info(const pa_engine* e, int32_t elem, pa_element_info* ou
   out->n_nodes = (int32_t)p.nodes.size();
   out->n_slots = p.n_slots;
   if (p.filtered) return PA_OK;
+  if (((out->pattern_codes || out->pattern_weights) && out->cap_P < p.P) || (out->site_pattern && out->cap_GG < p.GG)) {
+    g_last = "pa_element_info: cap_P / cap_GG smaller than the element's pattern / column count";
+    return PA_ERR_ARG;
+  }
   if (out->missing) memcpy(out->missing, p.missing.data(), N);
   if (out->nodes) memcpy(out->nodes, p.nodes.data(), sizeof(int32_t) * p.nodes.size());
   if (out->children2) memcpy(out->children2, p.children2.data(), sizeof(int32_t) * 2 * N);

@@ -97,11 +97,12 @@ struct SmemT {
 
 __device__ __forceinline__ double class_rate(int z, double n_rate, double c_rate) { return z == 2 ? n_rate : (z == 0 ? 1.0 : c_rate); }
 
-// mark the ancestors of node i dirty (getUpdateNode, bpp_c.cpp:620-642 / 836-858)
+// mark the ancestors of node i dirty (getUpdateNode, bpp_c.cpp:620-642 / 836-858).  Write-only: several threads may mark the same
+// ancestor (same value, no ordering needed); an early exit on an already marked ancestor would read what another thread is writing
+// (reported by compute-sanitizer racecheck in round 1's kernel; benign there, gone here)
 __device__ __forceinline__ void mark_ancestors(const int16_t* parent, uint8_t* dirty, int i) {
   int j = parent[i];
   while (j >= 0) {
-    if (dirty[j]) break;
     dirty[j] = 1;
     j = parent[j];
   }

@@ -128,7 +128,9 @@ __device__ __forceinline__ void build_P_row_quad(const SubstDev& sd, double t, d
     r0 = (j == 0) ? 1.0 : 0.0; r1 = (j == 1) ? 1.0 : 0.0; r2 = (j == 2) ? 1.0 : 0.0; r3 = (j == 3) ? 1.0 : 0.0;
     return;
   }
-  const unsigned mask = __activemask();
+  // explicit quad mask: the four lanes of a quad take the same branch at every call site (same branch of the tree, rows 0..3), but
+  // they need not be CONVERGED there under independent thread scheduling -- __activemask() could miss a source lane
+  const unsigned mask = 0xFu << (threadIdx.x & 28u);
   const double ej = exp(sd.eval[j] * t * rate);
   const int base = (int)(threadIdx.x & 28u);
   const double e0 = __shfl_sync(mask, ej, base), e1 = __shfl_sync(mask, ej, base + 1), e2 = __shfl_sync(mask, ej, base + 2), e3 = __shfl_sync(mask, ej, base + 3);

@@ -269,8 +269,25 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   // resident CTAs per SM: bounded by shared memory (228 KB per SM, 1 KB reserved per CTA) and by the layout's launch bounds
   int per_sm = std::max(1, std::min(chain_ctas_per_sm(n_max, model.tree.S, BD), (int)(233472 / (smem + 1024))));
   if (const char* env = getenv("PA_CTAS_PER_SM_RUNTIME")) per_sm = std::max(1, std::min(per_sm, atoi(env)));  // tuning knob
-  const int grid = std::min(n_chains, num_sms * per_sm);
+  int grid = std::min(n_chains, num_sms * per_sm);
   const size_t stride = chain_arena_bytes(n_max, P_max);
+  // the arena is sized by the longest element of the batch: one very long element inflates every CTA's share.  Run with fewer
+  // resident CTAs rather than fail when the full grid's arena does not fit beside the traces
+  if (stride * (size_t)grid > cap_arena) {
+    size_t free_b = 0, total_b = 0;
+    PA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t traces = (sizeof(double) * 6 + sizeof(uint32_t) * (size_t)((n_max + 15) / 16)) * (size_t)T * n_chains;
+    const size_t need_other = (traces > cap_trace_d + cap_trace_z ? traces - (cap_trace_d + cap_trace_z) : 0) + ((size_t)64 << 20);
+    const size_t avail = free_b + cap_arena > need_other ? free_b + cap_arena - need_other : 0;
+    if (stride * (size_t)grid > avail) {
+      const int fit = (int)(avail / stride);
+      if (fit < 1) {
+        set_error("not enough device memory for one chain arena (" + std::to_string(stride >> 20) + " MiB per resident chain)");
+        return PA_ERR_LIMIT;
+      }
+      grid = std::min(grid, fit);
+    }
+  }
   PA_CUDA(reserve((void*&)d_chain_list, cap_chain_list, sizeof(int32_t) * 2 * n_chains));
   PA_CUDA(reserve((void*&)d_trace_d, cap_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
   PA_CUDA(reserve((void*&)d_trace_z, cap_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));

@@ -44,11 +44,18 @@ CASES = {
     "post43": dict(S=43, tree_seed=43, C=6, length=100, seed=21, gap=0.01, missing=0.03, ambig=0.0,
                    params=dict(BURNIN=200, MCMC=400, CHAIN=1, ADAPT_FREQ=100, SEED=1), n_states=1, chains=[],
                    refrun_seeds=[1, 2, 3, 4, 5, 6], only=None),
+    # BASELINE cfg1 shape (simu_500_200: 43 taxa, 200 bp, 7 outgroup / 9 target / 27 conserved tips) at the DRIVER's default chain
+    # lengths (BURNIN 500, MCMC 1000), 100 elements, six seeds of the reference binary with VERBOSE traces: the sampler-behaviour
+    # targets of tests/test_gpu_cfg1.py (per-element z-scores, call set, KS on thinned c / n traces).  No probe dump.
+    "cfg1_100": dict(S=43, tree_seed=43, n_out=7, n_target=9, C=100, length=200, seed=1, gap=0.01, missing=0.03, ambig=0.0,
+                     params=dict(BURNIN=500, MCMC=1000, CHAIN=1, ADAPT_FREQ=500, SEED=1), n_states=0, chains=[], probe=False,
+                     refrun_seeds=[1, 2, 3, 4, 5, 6], trace_elements=list(range(12)), trace_thin=10, gz=True, threads=7),
 }
 
 
 def write_case_inputs(name, spec, outdir):
-    tree = synth.make_tree(S=spec["S"], seed=spec["tree_seed"], n_out=max(2, spec["S"] // 6), n_target=max(2, spec["S"] // 5))
+    tree = synth.make_tree(S=spec["S"], seed=spec["tree_seed"], n_out=spec.get("n_out", max(2, spec["S"] // 6)),
+                           n_target=spec.get("n_target", max(2, spec["S"] // 5)))
     batch = synth.simulate(tree, C=spec["C"], length=spec["length"], seed=spec["seed"], gap_frac=spec["gap"],
                            missing_frac=spec["missing"], ambig_frac=spec["ambig"])
     cfg = synth.write_files(batch, outdir, prefix="sim", params=spec["params"])
@@ -91,7 +98,7 @@ def main():
         N = tree.N
         script = []
         requests = []
-        for c in range(spec["C"]):
+        for c in range(spec["C"] if spec.get("probe", True) else 0):
             el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
             script.append(f"element {c}")
             if el.filter:
@@ -138,22 +145,25 @@ def main():
                         script.append(f"t {float(tr['loglik'][m])!r} {float(tr['n_rate'][m])!r} {float(tr['c_rate'][m])!r} " + " ".join(map(str, tr["Z"][m])))
                     requests.append(dict(c=c, eval2=resZ, trace={k: np.asarray(tr[k]).tolist() for k in ("loglik", "n_rate", "c_rate", "g_rate", "l_rate", "l2_rate", "Z")},
                                          oracle_seed=P.SEED, oracle_key=c * 4 + resZ))
-        sp = os.path.join(work, "script.txt")
-        with open(sp, "w") as f:
-            f.write("\n".join(script) + "\n")
-        r = subprocess.run([probe.PROBE, cfg, sp], capture_output=True, text=True, check=True)
-        with open(os.path.join(cdir, "probe.txt"), "w") as f:
-            f.write(r.stdout)
-        with open(os.path.join(cdir, "requests.json"), "w") as f:
-            json.dump(requests, f)
-        print(name, "probe done:", len(r.stdout), "bytes")
+        if spec.get("probe", True):
+            sp = os.path.join(work, "script.txt")
+            with open(sp, "w") as f:
+                f.write("\n".join(script) + "\n")
+            r = subprocess.run([probe.PROBE, cfg, sp], capture_output=True, text=True, check=True)
+            with open(os.path.join(cdir, "probe.txt"), "w") as f:
+                f.write(r.stdout)
+            with open(os.path.join(cdir, "requests.json"), "w") as f:
+                json.dump(requests, f)
+            print(name, "probe done:", len(r.stdout), "bytes")
 
         # full runs of the reference binary for a few seeds (distributional targets)
         for seed in spec["refrun_seeds"]:
             rw = tempfile.mkdtemp(prefix="pa_goldrun_")
             prm = dict(spec["params"])
             prm["SEED"] = seed
-            prm["NUM_THREAD"] = 8
+            prm["NUM_THREAD"] = spec.get("threads", 8)
+            if spec.get("trace_elements"):
+                prm["VERBOSE"] = 1  # the reference then writes <prefix>_mcmc_trace_M<m>_<c>.txt for every element (main.cpp:473-493)
             cfg2 = synth.write_files(batch, rw, prefix="sim", params=prm)
             with open(os.path.join(rw, "log.txt"), "w") as lf:
                 subprocess.run([probe.REF_BIN, cfg2], stdout=lf, stderr=subprocess.STDOUT, check=True)
@@ -162,8 +172,28 @@ def main():
                        "sim_M0_elem_Z.txt", "sim_M1_elem_Z.txt", "sim_M2_elem_Z.txt"):
                 with open(os.path.join(rw, "out", fn)) as f:
                     out[fn] = f.read()
-            with open(os.path.join(cdir, f"refrun_seed{seed}.json"), "w") as f:
-                json.dump(out, f)
+            if spec.get("trace_elements"):
+                # post-burn-in n / c traces of a few elements, thinned (autocorrelation), for the KS check
+                thin, burn = spec["trace_thin"], spec["params"]["BURNIN"]
+                tr = {}
+                for c in spec["trace_elements"]:
+                    for m in range(3):
+                        fn = os.path.join(rw, "out", f"sim_mcmc_trace_M{m}_{c}.txt")
+                        if not os.path.exists(fn):
+                            continue
+                        with open(fn) as f:
+                            rows = [l.split("\t") for l in f.read().split("\n")[1:] if l]
+                        tr[f"{c}_{m}"] = dict(n=[float(r[1]) for r in rows[burn::thin]], c=[float(r[2]) for r in rows[burn::thin]],
+                                              loglik=[float(r[0]) for r in rows[burn::thin]])
+                out["traces"] = tr
+            if spec.get("gz"):
+                import gzip
+
+                with gzip.open(os.path.join(cdir, f"refrun_seed{seed}.json.gz"), "wt") as f:
+                    json.dump(out, f)
+            else:
+                with open(os.path.join(cdir, f"refrun_seed{seed}.json"), "w") as f:
+                    json.dump(out, f)
             shutil.rmtree(rw)
             print(name, "reference run seed", seed, "done")
         shutil.rmtree(work)
