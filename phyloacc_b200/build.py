@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libphyloacc_b200.so")
+LIB = os.environ.get("PA_LIB_OUT", os.path.join(HERE, "libphyloacc_b200.so"))  # PA_LIB_OUT: build an A/B variant next to the product library
 BIN = os.path.join(HERE, "PhyloAcc-ST-b200")
 LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu"]
 NVCC = os.environ.get("PA_NVCC", "/usr/local/cuda/bin/nvcc")
@@ -26,7 +26,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(HERE, "..", "include", "phyloacc_b200.h"))
-    objdir = os.path.join(HERE, "_build")
+    objdir = os.path.join(HERE, "_build" + os.environ.get("PA_BUILD_TAG", ""))
     os.makedirs(objdir, exist_ok=True)
     if not (force is False and _newer(LIB, deps)):
         objs = []

@@ -1,0 +1,6 @@
+
+for lib in "$@"; do
+  echo "=== $lib"
+  PA_LIB=$PWD/phyloacc_b200/$lib PA_PROF_ELEMS=592 python tools/profile_chain.py 2>&1 | tail -2
+  PA_LIB=$PWD/phyloacc_b200/$lib PA_PROF_LEN=cfg2 PA_PROF_ELEMS=2048 PA_PROF_ITERS=200 python tools/profile_chain.py 2>&1 | tail -2
+done
