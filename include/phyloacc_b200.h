@@ -144,9 +144,10 @@ int pa_engine_loglik_replay(pa_engine* e, int32_t n_states, const int32_t* elem,
                             const double* c_rate, double* loglik_out);
 
 /* The element loop of main.cpp:452-500: for every id, M0 -> M1 -> M2 chains (initMCMC, Gibbs, Eval2,
- * Output_init).  pa_engine_sample launches the on-device chains asynchronously on the handle's stream
- * (traces stay in HBM); pa_engine_collect synchronises, runs Eval2 / summaries and fills `out`.
- * pa_engine_run = sample + collect. */
+ * Output_init).  pa_engine_sample launches the on-device chains and, right behind them on the handle's stream, the
+ * summary kernel (MonitorChain's arg-max, the medians and Z frequencies of Output_init, Eval2) -- traces stay in HBM;
+ * pa_engine_collect synchronises, copies one small record per chain and fills `out`; only chains whose Eval2 takes the
+ * reference's pruning fallback (bpp_c2.cpp:199-316) have their trace downloaded.  pa_engine_run = sample + collect. */
 int pa_engine_sample(pa_engine* e, const int32_t* ids, int32_t n_ids);
 int pa_engine_collect(pa_engine* e, pa_results* out);
 
@@ -184,6 +185,9 @@ int pa_engine_get_trace(pa_engine* e, int32_t i, int32_t model, pa_trace* out);
 typedef struct pa_counters {
   uint64_t node_pattern_updates, root_evals, pt_builds, history_draws, chain_iterations, kernel_launches;
   uint64_t node_site_updates; /* like node_pattern_updates, counted on UNCOMPRESSED columns (BASELINE metric "pruned site-liks/sec") */
+  uint64_t d2h_bytes;         /* bytes copied device -> host for the last run so far: summary records, counters, and any traces that were
+                               * asked for (pa_engine_get_trace, VERBOSE) or needed by Eval2's host fallback */
+  uint64_t host_eval_chains;  /* chains of the last run whose Eval2 ran on the host (pruning fallback, configuration-table overflow) */
 } pa_counters;
 int pa_engine_counters(pa_engine* e, pa_counters* out);
 /* SM cycles per phase of the chain kernel, summed over CTAs (thread 0 clock64 deltas): init, trace, history sampling,

@@ -84,7 +84,7 @@ class PaHyper(C.Structure):
 class PaCounters(C.Structure):
     _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
                 ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("node_site_updates", C.c_uint64)]
+                ("node_site_updates", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_eval_chains", C.c_uint64)]
 
 
 EXPORTS = [
@@ -406,6 +406,10 @@ class Engine:
         buf = (C.c_uint64 * 10)()
         _check(self._lib.pa_engine_phase_cycles(self._h, buf))
         return dict(zip(self.PHASES, [int(v) for v in buf]))
+
+    def d2h_bytes(self) -> int:
+        """Bytes copied device -> host for the last run so far (summary records, counters, traces that were asked for)."""
+        return int(self.counters()["d2h_bytes"])
 
     def counters(self) -> dict:
         c = PaCounters()

@@ -233,6 +233,7 @@ int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
 int pa_engine_counters(pa_engine* e, pa_counters* out) {
   if (!e || !out) return PA_ERR_ARG;
   *out = e->eng.counters;
+  out->d2h_bytes = e->eng.d2h_bytes;
   return PA_OK;
 }
 

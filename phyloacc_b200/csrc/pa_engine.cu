@@ -107,7 +107,11 @@ void Engine::release_device() {
   fr((void*&)d_blobs); fr((void*&)d_blob_off);
   cap_blobs = cap_blob_off = 0;
   fr((void*&)d_chain_list); fr((void*&)d_trace_d); fr((void*&)d_trace_z); fr((void*&)d_arena); fr((void*&)d_counters); fr((void*&)d_queue);
-  fr((void*&)d_init_rates); fr((void*&)d_init_z); fr((void*&)d_replay);
+  fr((void*&)d_init_rates); fr((void*&)d_init_z); fr((void*&)d_replay); fr((void*&)d_summary);
+  cap_d_summary = 0;
+  if (h_summary) cudaFreeHost(h_summary);
+  h_summary = nullptr;
+  cap_h_summary = 0;
   cap_replay = 0;
   cap_init_rates = cap_init_z = 0;
   if (h_trace_d) cudaFreeHost(h_trace_d);

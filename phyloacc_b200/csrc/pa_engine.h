@@ -61,6 +61,14 @@ struct Engine {
   double* h_trace_d = nullptr;           // pinned host copies of the traces of the last run (grow-only)
   uint32_t* h_trace_z = nullptr;
   size_t cap_h_trace_d = 0, cap_h_trace_z = 0;
+  // per-chain summaries computed on the device (pa_summary.cu): MonitorChain, medians, Z frequencies, Eval2; traces stay in HBM and
+  // are downloaded only for chains that need the host (Eval2's pruning fallback), for pa_engine_get_trace and for VERBOSE output
+  bool device_summaries = true;          // PA_HOST_SUMMARIES=1 selects round 1's host path (A/B, tests)
+  unsigned char* d_summary = nullptr;
+  unsigned char* h_summary = nullptr;    // pinned
+  size_t cap_d_summary = 0, cap_h_summary = 0, rec_bytes = 0;
+  bool traces_on_host = false;           // h_trace_* hold the last run's traces
+  size_t d2h_bytes = 0;                  // bytes copied device -> host by the last collect (measured, for bench.py's e2e line)
   bool sampled = false, collected = false;
   // completion flags of the running launch, written by the kernel into mapped pinned memory (one per chain, device order), and the
   // stream the finished chains' traces are downloaded on while the kernel is still running
@@ -85,6 +93,8 @@ struct Engine {
   int fetch_range(int lo, int hi);  // wait for chains [fetched_prefix, hi) of the running launch and download their traces
   int fetch_finish();               // end of the launch: counters, warm-start states
   int unpack_trace(int ch, ChainTraceHost& tr) const;
+  int unpack_trace_from(int ch, const double* d, const uint32_t* z, ChainTraceHost& tr) const;
+  int collect_device(pa_results* out);
   int collect(pa_results* out);
   int get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr);
 };

@@ -17,6 +17,7 @@
 
 #include "pa_chain.cuh"
 #include "pa_engine.h"
+#include "pa_summary.cuh"
 
 namespace pa {
 
@@ -218,6 +219,9 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   }
   sampled = true;
   collected = false;
+  traces_on_host = false;
+  d2h_bytes = 0;
+  device_summaries = !(getenv("PA_HOST_SUMMARIES") && atoi(getenv("PA_HOST_SUMMARIES")) != 0);
   done_prefix = fetched_prefix = 0;
   counters = pa_counters{};
   if (n_chains == 0) return PA_OK;
@@ -297,7 +301,20 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   PA_CUDA(cudaMemcpyAsync(d_chain_list, list.data(), sizeof(int32_t) * 2 * n_chains, cudaMemcpyHostToDevice, stream));
   PA_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 24, stream));
   PA_CUDA(cudaMemsetAsync(d_queue, 0, sizeof(int), stream));
-  // completion flags in mapped pinned memory (grow-only), the trace buffers on the host and the download stream
+  rec_bytes = summary_record_bytes(n_max, ZW);
+  if (device_summaries) {
+    PA_CUDA(reserve((void*&)d_summary, cap_d_summary, rec_bytes * (size_t)n_chains));
+    if (rec_bytes * (size_t)n_chains > cap_h_summary || !h_summary) {
+      if (h_summary) cudaFreeHost(h_summary);
+      h_summary = nullptr;
+      cap_h_summary = 0;
+      PA_CUDA(cudaHostAlloc((void**)&h_summary, rec_bytes * (size_t)n_chains, cudaHostAllocDefault));
+      cap_h_summary = rec_bytes * (size_t)n_chains;
+    }
+  }
+  // host-summary path only: completion flags in mapped pinned memory (grow-only), the trace buffers on the host and the download stream
+  int* d_done = nullptr;
+  if (!device_summaries) {
   if (sizeof(int) * (size_t)n_chains > cap_h_done || !h_done) {
     if (h_done) cudaFreeHost(h_done);
     h_done = nullptr;
@@ -306,7 +323,6 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     cap_h_done = sizeof(int) * (size_t)n_chains;
   }
   memset(h_done, 0, sizeof(int) * (size_t)n_chains);
-  int* d_done = nullptr;
   PA_CUDA(cudaHostGetDevicePointer((void**)&d_done, h_done, 0));
   if (!copy_stream) PA_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   {
@@ -322,6 +338,7 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     PA_CUDA(reserve_host((void*&)h_trace_d, cap_h_trace_d, sizeof(double) * 6 * (size_t)T * n_chains));
     PA_CUDA(reserve_host((void*&)h_trace_z, cap_h_trace_z, sizeof(uint32_t) * (size_t)ZW * T * n_chains));
   }
+  }  // !device_summaries
   bool any_warm = false;
   if (warm_start && !cur_set.empty()) {
     std::vector<double> ir((size_t)n_chains * 8, 0.0);
@@ -367,9 +384,22 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
   L.sel = nullptr; L.n_sel = n_chains; L.P_max = P_max;
   L.arena = d_arena; L.arena_stride = stride; L.queue = d_queue;
   L.done = d_done;
-  const int rc = launch_chains(L, grid, BD, stream);
+  int rc = launch_chains(L, grid, BD, stream);
   if (rc != PA_OK) return rc;
   counters.kernel_launches = 1;
+  if (device_summaries) {  // one CTA per chain reduces its trace to a summary record; same stream, right behind the chains
+    SummaryLaunch SL;
+    SL.blobs = d_blobs; SL.blob_off = d_blob_off; SL.chain_list = d_chain_list;
+    SL.n_chains = n_chains; SL.T = T; SL.ZW = ZW; SL.num_burn = P.burnin; SL.num_mcmc = P.mcmc;
+    SL.trace_d = d_trace_d; SL.trace_z = d_trace_z;
+    SL.cprior_a = cp.cprior_a; SL.cprior_b = cp.cprior_b; SL.nprior_a = cp.nprior_a; SL.nprior_b = cp.nprior_b;
+    SL.prior_l_a = cp.prior_l_a; SL.prior_l_b = cp.prior_l_b; SL.prior_l2_a = cp.prior_l2_a; SL.prior_l2_b = cp.prior_l2_b;
+    SL.prior_g_a = cp.prior_g_a; SL.prior_g_b = cp.prior_g_b;
+    SL.out = d_summary; SL.rec_bytes = rec_bytes;
+    rc = launch_summaries(SL, n_max, stream);
+    if (rc != PA_OK) return rc;
+    counters.kernel_launches = 2;
+  }
   return PA_OK;
 }
 
@@ -383,6 +413,10 @@ int Engine::fetch_range(int lo, int hi) {
     return PA_ERR_STATE;
   }
   hi = std::min(hi, n_chains);
+  if (device_summaries) {
+    set_error("fetch_range is part of the host-summary path");
+    return PA_ERR_STATE;
+  }
   if (collected || hi <= fetched_prefix) return PA_OK;
   PA_CUDA(cudaSetDevice(device));
   volatile int* done = h_done;
@@ -409,6 +443,7 @@ int Engine::fetch_range(int lo, int hi) {
   PA_CUDA(cudaMemcpyAsync(h_trace_d + a * per_d, d_trace_d + a * per_d, sizeof(double) * per_d * (b - a), cudaMemcpyDeviceToHost, copy_stream));
   PA_CUDA(cudaMemcpyAsync(h_trace_z + a * per_z, d_trace_z + a * per_z, sizeof(uint32_t) * per_z * (b - a), cudaMemcpyDeviceToHost, copy_stream));
   PA_CUDA(cudaStreamSynchronize(copy_stream));
+  d2h_bytes += (sizeof(double) * per_d + sizeof(uint32_t) * per_z) * (size_t)(b - a);
   fetched_prefix = b;
   return PA_OK;
 }
@@ -454,6 +489,29 @@ int Engine::fetch_traces() {
     set_error("nothing sampled yet");
     return PA_ERR_STATE;
   }
+  if (device_summaries) {
+    // traces stay in HBM; they come to the host only on demand (pa_engine_get_trace, VERBOSE output), all chains in one copy
+    if (traces_on_host || n_chains == 0) return PA_OK;
+    PA_CUDA(cudaSetDevice(device));
+    auto reserve_host = [&](void*& p, size_t& cap, size_t bytes) -> cudaError_t {
+      if (bytes <= cap && p) return cudaSuccess;
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+      if (e == cudaSuccess) cap = bytes;
+      return e;
+    };
+    const size_t bd = sizeof(double) * 6 * (size_t)T * n_chains, bz = sizeof(uint32_t) * (size_t)ZW * T * n_chains;
+    PA_CUDA(reserve_host((void*&)h_trace_d, cap_h_trace_d, bd));
+    PA_CUDA(reserve_host((void*&)h_trace_z, cap_h_trace_z, bz));
+    PA_CUDA(cudaMemcpyAsync(h_trace_d, d_trace_d, bd, cudaMemcpyDeviceToHost, stream));
+    PA_CUDA(cudaMemcpyAsync(h_trace_z, d_trace_z, bz, cudaMemcpyDeviceToHost, stream));
+    PA_CUDA(cudaStreamSynchronize(stream));
+    d2h_bytes += bd + bz;
+    traces_on_host = true;
+    return PA_OK;
+  }
   if (collected || n_chains == 0) {
     collected = true;
     return PA_OK;
@@ -479,9 +537,12 @@ int Engine::get_trace(int32_t i, int32_t mdl, ChainTraceHost& tr) {
 
 // host copy of chain `ch` (device order) from the downloaded trace buffers
 int Engine::unpack_trace(int ch, ChainTraceHost& tr) const {
+  return unpack_trace_from(ch, &h_trace_d[(size_t)ch * 6 * T], &h_trace_z[(size_t)ch * T * ZW], tr);
+}
+
+int Engine::unpack_trace_from(int ch, const double* d, const uint32_t* z, ChainTraceHost& tr) const {
   const ElemPlan& pl = plans[run_ids[chain_elem_pos[ch]]];
   const int N = model.tree.N, n = (int)pl.nodes.size();
-  const double* d = &h_trace_d[(size_t)ch * 6 * T];
   tr.loglik.assign(d, d + T);
   tr.n_rate.assign(d + T, d + 2 * T);
   tr.c_rate.assign(d + 2 * T, d + 3 * T);
@@ -489,7 +550,6 @@ int Engine::unpack_trace(int ch, ChainTraceHost& tr) const {
   tr.l_rate.assign(d + 4 * T, d + 5 * T);
   tr.l2_rate.assign(d + 5 * T, d + 6 * T);
   tr.Z.assign((size_t)T * N, -1);
-  const uint32_t* z = &h_trace_z[(size_t)ch * T * ZW];
   const int32_t* nodes = pl.nodes.data();
   for (int m = 0; m < T; m++) {
     int8_t* row = &tr.Z[(size_t)m * N];
@@ -647,6 +707,98 @@ double eval2_fallback_finish(const Engine& eng, int mdl, const Eval2Work& w, con
   return VB;
 }
 
+// MonitorChain, Eval2 (all but its pruning fallback) and Output_init's medians / Z frequencies of one chain from its host trace
+static void host_chain_summary(const Engine& eng, const ElemPlan& pl, int i, int mdl, ChainTraceHost& tr, pa_results* out, Eval2Work& work, double& logml_out,
+                           double lg_ca, double lg_na) {
+  const pa_params& P = eng.model.prm;
+  const int N = eng.model.tree.N, num_burn = P.burnin, num_mcmc = P.mcmc, T = num_burn + num_mcmc;
+  // MonitorChain: full log-likelihood and its arg-max after burn-in (bpp_c.cpp:768-814)
+  std::vector<double> full(T);
+  double max_ll = -INFINITY;
+  int max_m = -1;
+  for (int m = num_burn; m < T; m++) {  // only the post-burn-in rows are used (arg-max here, Eval2's averages below)
+    full[m] = tr.loglik[m] + 0.0;
+    full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
+    if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
+    if (full[m] > max_ll) {
+      max_ll = full[m];
+      max_m = m;
+    }
+  }
+  std::vector<int8_t> Max_Z(N, 0);
+  if (max_m >= 0) Max_Z.assign(&tr.Z[(size_t)max_m * N], &tr.Z[(size_t)max_m * N] + N);
+  if (out->loglik_max) out->loglik_max[i * 3 + mdl] = max_ll;
+  if (out->max_Z) memcpy(out->max_Z + ((size_t)i * 3 + mdl) * N, Max_Z.data(), N);
+  if (max_m >= 0) logml_out = eval2_main(eng, pl, mdl, tr, full, Max_Z.data(), work);
+  else logml_out = NAN;
+  // Output_init: medians of the sorted FULL traces, Z frequencies after burn-in (bpp_c2.cpp:742-781)
+  if (out->median_rates) {
+    double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
+    std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
+    for (int k = 0; k < 5; k++) {  // the element the reference reads after sorting the whole trace (bpp_c2.cpp:742-760)
+      std::nth_element(cols[k]->begin(), cols[k]->begin() + cols[k]->size() / 2, cols[k]->end());
+      md[k] = (*cols[k])[cols[k]->size() / 2];
+    }
+  }
+  if (out->post_Z) {
+    double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
+    std::vector<int> cnt((size_t)N * 4, 0);
+    {
+      // per-value passes over the row-major trace (vectorisable compare-and-add) instead of a scattered histogram
+      std::vector<int> c0(N, 0), c1(N, 0), c2(N, 0);
+      for (int m = num_burn; m < T; m++) {
+        const int8_t* row = &tr.Z[(size_t)m * N];
+        for (int s = 0; s < N; s++) {
+          c0[s] += row[s] == 0;
+          c1[s] += row[s] == 1;
+          c2[s] += row[s] == 2;
+        }
+      }
+      for (int s = 0; s < N; s++) {
+        cnt[s * 4 + 1] = c0[s];
+        cnt[s * 4 + 2] = c1[s];
+        cnt[s * 4 + 3] = c2[s];
+        cnt[s * 4] = num_mcmc - c0[s] - c1[s] - c2[s];  // Z == -1: the node is outside the element's pruned tree
+      }
+    }
+    for (int s = 0; s < N; s++) {
+      if (pl.missing[s]) cnt[s * 4] = num_mcmc;
+      for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
+    }
+  }
+}
+
+// Eval2 fallback (no configuration carries >= 2% weight with a finite log-det): exact log-likelihood of every
+// configuration at the posterior-mean rates, by the replay kernel, in one batch (bpp_c2.cpp:199-316)
+static int eval2_fallback_batch(Engine& eng, const std::vector<Eval2Work>& works, std::vector<double>& logml) {
+  std::vector<int32_t> elem;
+  std::vector<int8_t> Z;
+  std::vector<double> nr, cr;
+  const int n_chains = (int)works.size();
+  for (int ch = 0; ch < n_chains; ch++) {
+    const Eval2Work& w = works[ch];
+    if (!w.need_fallback) continue;
+    for (size_t k = 0; k < w.configZ.size(); k++) {
+      elem.push_back(eng.run_ids[eng.chain_elem_pos[ch]]);
+      Z.insert(Z.end(), w.configZ[k].begin(), w.configZ[k].end());
+      nr.push_back(eng.chain_model[ch] == PA_M0 ? 1.0 : w.rn);
+      cr.push_back(w.rc);
+    }
+  }
+  if (elem.empty()) return PA_OK;
+  std::vector<double> ll(elem.size());
+  const int rc = eng.loglik_replay((int32_t)elem.size(), elem.data(), Z.data(), nr.data(), cr.data(), ll.data());
+  if (rc != PA_OK) return rc;
+  size_t off = 0;
+  for (int ch = 0; ch < n_chains; ch++) {
+    const Eval2Work& w = works[ch];
+    if (!w.need_fallback) continue;
+    logml[ch] = eval2_fallback_finish(eng, eng.chain_model[ch], w, &ll[off]);
+    off += w.configZ.size();
+  }
+  return PA_OK;
+}
+
 }  // namespace
 
 int Engine::collect(pa_results* out) {
@@ -663,6 +815,7 @@ int Engine::collect(pa_results* out) {
     set_error("pa_results too small for this run");
     return PA_ERR_ARG;
   }
+  if (device_summaries) return collect_device(out);
   const pa_params& P = model.prm;
   const int N = model.tree.N, num_burn = P.burnin, num_mcmc = P.mcmc;
   for (int i = 0; i < n_ids; i++) {
@@ -702,100 +855,160 @@ int Engine::collect(pa_results* out) {
         err = PA_ERR_STATE;
         continue;
       }
-      // MonitorChain: full log-likelihood and its arg-max after burn-in (bpp_c.cpp:768-814)
-      std::vector<double> full(T);
-      double max_ll = -INFINITY;
-      int max_m = -1;
-      for (int m = num_burn; m < T; m++) {  // only the post-burn-in rows are used (arg-max here, Eval2's averages below)
-        full[m] = tr.loglik[m] + 0.0;
-        full[m] += std::log(gamma_pdf_lg(tr.c_rate[m], P.conserve_prior_a, P.conserve_prior_b, lg_ca));
-        if (mdl != PA_M0) full[m] += std::log(gamma_pdf_lg(tr.n_rate[m], P.acce_prior_a, P.acce_prior_b, lg_na));
-        if (full[m] > max_ll) {
-          max_ll = full[m];
-          max_m = m;
-        }
-      }
-      std::vector<int8_t> Max_Z(N, 0);
-      if (max_m >= 0) Max_Z.assign(&tr.Z[(size_t)max_m * N], &tr.Z[(size_t)max_m * N] + N);
-      if (out->loglik_max) out->loglik_max[i * 3 + mdl] = max_ll;
-      if (out->max_Z) memcpy(out->max_Z + ((size_t)i * 3 + mdl) * N, Max_Z.data(), N);
-      if (max_m >= 0) logml[ch] = eval2_main(*this, pl, mdl, tr, full, Max_Z.data(), works[ch]);
-      else logml[ch] = NAN;
-      // Output_init: medians of the sorted FULL traces, Z frequencies after burn-in (bpp_c2.cpp:742-781)
-      if (out->median_rates) {
-        double* md = &out->median_rates[((size_t)i * 3 + mdl) * 5];
-        std::vector<double>* cols[5] = {&tr.n_rate, &tr.c_rate, &tr.g_rate, &tr.l_rate, &tr.l2_rate};
-        for (int k = 0; k < 5; k++) {  // the element the reference reads after sorting the whole trace (bpp_c2.cpp:742-760)
-          std::nth_element(cols[k]->begin(), cols[k]->begin() + cols[k]->size() / 2, cols[k]->end());
-          md[k] = (*cols[k])[cols[k]->size() / 2];
-        }
-      }
-      if (out->post_Z) {
-        double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
-        std::vector<int> cnt((size_t)N * 4, 0);
-        {
-          // per-value passes over the row-major trace (vectorisable compare-and-add) instead of a scattered histogram
-          std::vector<int> c0(N, 0), c1(N, 0), c2(N, 0);
-          for (int m = num_burn; m < T; m++) {
-            const int8_t* row = &tr.Z[(size_t)m * N];
-            for (int s = 0; s < N; s++) {
-              c0[s] += row[s] == 0;
-              c1[s] += row[s] == 1;
-              c2[s] += row[s] == 2;
-            }
-          }
-          for (int s = 0; s < N; s++) {
-            cnt[s * 4 + 1] = c0[s];
-            cnt[s * 4 + 2] = c1[s];
-            cnt[s * 4 + 3] = c2[s];
-            cnt[s * 4] = num_mcmc - c0[s] - c1[s] - c2[s];  // Z == -1: the node is outside the element's pruned tree
-          }
-        }
-        for (int s = 0; s < N; s++) {
-          if (pl.missing[s]) cnt[s * 4] = num_mcmc;
-          for (int k = 0; k < 4; k++) pz[s * 4 + k] = (double)cnt[s * 4 + k] / num_mcmc;
-        }
-      }
+      host_chain_summary(*this, pl, i, mdl, tr, out, works[ch], logml[ch], lg_ca, lg_na);
     }
   }  // chunks
   if (err != PA_OK) return err;
   rc = fetch_finish();
   if (rc != PA_OK) return rc;
   const double t_sum = omp_get_wtime();
-  // Eval2 fallback (no configuration carries >= 2% weight with a finite log-det): exact log-likelihood of every
-  // configuration at the posterior-mean rates, by the replay kernel, in one batch
-  {
-    std::vector<int32_t> elem;
-    std::vector<int8_t> Z;
-    std::vector<double> nr, cr;
-    for (int ch = 0; ch < n_chains; ch++) {
-      const Eval2Work& w = works[ch];
-      if (!w.need_fallback) continue;
-      for (size_t k = 0; k < w.configZ.size(); k++) {
-        elem.push_back(run_ids[chain_elem_pos[ch]]);
-        Z.insert(Z.end(), w.configZ[k].begin(), w.configZ[k].end());
-        nr.push_back(chain_model[ch] == PA_M0 ? 1.0 : w.rn);
-        cr.push_back(w.rc);
-      }
-    }
-    if (!elem.empty()) {
-      std::vector<double> ll(elem.size());
-      rc = loglik_replay((int32_t)elem.size(), elem.data(), Z.data(), nr.data(), cr.data(), ll.data());
-      if (rc != PA_OK) return rc;
-      size_t off = 0;
-      for (int ch = 0; ch < n_chains; ch++) {
-        const Eval2Work& w = works[ch];
-        if (!w.need_fallback) continue;
-        logml[ch] = eval2_fallback_finish(*this, chain_model[ch], w, &ll[off]);
-        off += w.configZ.size();
-      }
-    }
-  }
+  rc = eval2_fallback_batch(*this, works, logml);
+  if (rc != PA_OK) return rc;
   if (out->loglik)
     for (int ch = 0; ch < n_chains; ch++) out->loglik[chain_elem_pos[ch] * 3 + chain_model[ch]] = logml[ch];
   if (timing)
     fprintf(stderr, "[pa timing] collect: waiting for chains + trace download %.3f s, MonitorChain/Eval2/summaries %.3f s (%d threads, overlapped with the kernel), Eval2 fallback %.3f s\n",
             t_wait, t_sum - t_start - t_wait, nt, omp_get_wtime() - t_sum);
+  return PA_OK;
+}
+
+
+// Summaries from the device records (pa_summary.cu); traces stay in HBM.  Chains whose Eval2 needs the host (pruning fallback at the
+// posterior-mean rates, more Z configurations than the device table holds) have their own trace downloaded and go through the
+// host path above.
+int Engine::collect_device(pa_results* out) {
+  const bool timing = getenv("PA_TIMING") != nullptr;
+  const double t_start = omp_get_wtime();
+  const pa_params& P = model.prm;
+  const int N = model.tree.N, num_mcmc = P.mcmc, n_ids = (int)run_ids.size();
+  for (int i = 0; i < n_ids; i++) {
+    const bool filt = plans[run_ids[i]].filtered;
+    if (out->filtered) out->filtered[i] = filt;
+    if (out->loglik) for (int k = 0; k < 3; k++) out->loglik[i * 3 + k] = 0;
+    if (out->loglik_max) for (int k = 0; k < 3; k++) out->loglik_max[i * 3 + k] = 0;
+    if (out->max_Z) memset(out->max_Z + (size_t)i * 3 * N, 0, (size_t)3 * N);
+    if (out->median_rates) for (int k = 0; k < 15; k++) out->median_rates[(size_t)i * 15 + k] = 0;
+    if (out->post_Z) for (size_t k = 0; k < (size_t)3 * N * 4; k++) out->post_Z[(size_t)i * 3 * N * 4 + k] = 0;
+  }
+  if (n_chains == 0) {
+    collected = true;
+    return PA_OK;
+  }
+  PA_CUDA(cudaSetDevice(device));
+  unsigned long long hc[24];
+  if (!collected) {
+    PA_CUDA(cudaMemcpyAsync(h_summary, d_summary, rec_bytes * (size_t)n_chains, cudaMemcpyDeviceToHost, stream));
+    PA_CUDA(cudaMemcpyAsync(hc, d_counters, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+    PA_CUDA(cudaStreamSynchronize(stream));
+    d2h_bytes += rec_bytes * (size_t)n_chains + sizeof(hc);
+    counters.node_pattern_updates = hc[0];
+    counters.root_evals = hc[1];
+    counters.pt_builds = hc[2];
+    counters.history_draws = hc[3];
+    counters.chain_iterations = hc[4];
+    counters.node_site_updates = hc[5];
+    for (int k = 0; k < 10; k++) phase_cycles[k] = hc[8 + k];
+  }
+  const double t_copy = omp_get_wtime();
+  const int nt = std::max(1, P.num_thread);
+  std::vector<int> host_chains;
+  {
+    const size_t C = plans.size();
+    if (cur_set.size() != C * 3 || cur_z.size() != C * 3 * (size_t)ZW) {
+      cur_set.assign(C * 3, 0);
+      cur_rates.assign(C * 15, 0.0);
+      cur_z.assign(C * 3 * (size_t)ZW, 0u);
+    }
+  }
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int ch = 0; ch < n_chains; ch++) {
+    const int i = chain_elem_pos[ch], mdl = chain_model[ch];
+    const ElemPlan& pl = plans[run_ids[i]];
+    const int n = (int)pl.nodes.size();
+    const unsigned char* rec = h_summary + (size_t)ch * rec_bytes;
+    const SummaryHead* hd = reinterpret_cast<const SummaryHead*>(rec);
+    const uint32_t* maxz = reinterpret_cast<const uint32_t*>(rec + sizeof(SummaryHead));
+    const uint32_t* lastz = maxz + ZW;
+    const uint16_t* cnt = reinterpret_cast<const uint16_t*>(lastz + ZW);
+    if (out->loglik_max) out->loglik_max[i * 3 + mdl] = hd->max_loglik;
+    if (out->loglik) out->loglik[i * 3 + mdl] = hd->logml;
+    if (out->max_Z) {
+      int8_t* mz = out->max_Z + ((size_t)i * 3 + mdl) * N;
+      if (hd->max_m >= 0) {
+        memset(mz, -1, N);
+        for (int k = 0; k < n; k++) mz[pl.nodes[k]] = (int8_t)((maxz[k >> 4] >> (2 * (k & 15))) & 3u);
+      }
+    }
+    if (out->median_rates)
+      for (int k = 0; k < 5; k++) out->median_rates[((size_t)i * 3 + mdl) * 5 + k] = hd->med[k];
+    if (out->post_Z) {  // bpp_c2.cpp:757-781: frequencies of Z = -1, 0, 1, 2; missing nodes force the first column to 1
+      double* pz = &out->post_Z[((size_t)i * 3 + mdl) * N * 4];
+      for (int s = 0; s < N; s++) pz[s * 4] = 1.0;  // nodes outside the pruned tree: Z == -1 in every row
+      for (int k = 0; k < n; k++) {
+        const int s = pl.nodes[k];
+        const int c0 = cnt[k * 3], c1 = cnt[k * 3 + 1], c2 = cnt[k * 3 + 2];
+        pz[s * 4 + 0] = pl.missing[s] ? 1.0 : (double)(num_mcmc - c0 - c1 - c2) / num_mcmc;
+        pz[s * 4 + 1] = (double)c0 / num_mcmc;
+        pz[s * 4 + 2] = (double)c1 / num_mcmc;
+        pz[s * 4 + 3] = (double)c2 / num_mcmc;
+      }
+    }
+    // the last state of every chain becomes the warm start of its next run (Gibbs with UpHyper, bpp_c.cpp:474-485)
+    const size_t slot = (size_t)run_ids[i] * 3 + mdl;
+    for (int j = 0; j < 5; j++) cur_rates[slot * 5 + j] = hd->last[j];
+    for (int w = 0; w < ZW; w++) cur_z[slot * ZW + w] = lastz[w];
+    cur_set[slot] = 1;
+    if (hd->flags & SUMMARY_NEEDS_HOST) {
+#pragma omp critical
+      host_chains.push_back(ch);
+    }
+  }
+  const double t_fin = omp_get_wtime();
+  counters.host_eval_chains = host_chains.size();
+  // chains that need the host: download their traces (one chain at a time: they are rare) and run the host summary + fallback
+  if (!host_chains.empty()) {
+    std::sort(host_chains.begin(), host_chains.end());
+    const double lg_ca = std::lgamma(P.conserve_prior_a), lg_na = std::lgamma(P.acce_prior_a);
+    std::vector<Eval2Work> works(n_chains);
+    std::vector<double> logml(n_chains, 0.0);
+    const size_t nh = host_chains.size(), per_d = (size_t)6 * T, per_z = (size_t)ZW * T;
+    std::vector<double> bd;
+    std::vector<uint32_t> bz;
+    if (!traces_on_host) {  // their traces, queued back to back, one synchronisation
+      bd.resize(nh * per_d);
+      bz.resize(nh * per_z);
+      for (size_t k = 0; k < nh; k++) {
+        const int ch = host_chains[k];
+        PA_CUDA(cudaMemcpyAsync(bd.data() + k * per_d, d_trace_d + (size_t)ch * per_d, sizeof(double) * per_d, cudaMemcpyDeviceToHost, stream));
+        PA_CUDA(cudaMemcpyAsync(bz.data() + k * per_z, d_trace_z + (size_t)ch * per_z, sizeof(uint32_t) * per_z, cudaMemcpyDeviceToHost, stream));
+      }
+      PA_CUDA(cudaStreamSynchronize(stream));
+      d2h_bytes += nh * (sizeof(double) * per_d + sizeof(uint32_t) * per_z);
+    }
+    pa_results scratch = *out;
+    scratch.median_rates = nullptr;  // medians / frequencies / arg-max already come from the device record
+    scratch.post_Z = nullptr;
+    scratch.max_Z = nullptr;
+    scratch.loglik_max = nullptr;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int k = 0; k < (int)nh; k++) {
+      const int ch = host_chains[k];
+      const double* src_d = traces_on_host ? &h_trace_d[(size_t)ch * per_d] : bd.data() + (size_t)k * per_d;
+      const uint32_t* src_z = traces_on_host ? &h_trace_z[(size_t)ch * per_z] : bz.data() + (size_t)k * per_z;
+      ChainTraceHost tr;
+      unpack_trace_from(ch, src_d, src_z, tr);
+      const int i = chain_elem_pos[ch], mdl = chain_model[ch];
+      host_chain_summary(*this, plans[run_ids[i]], i, mdl, tr, &scratch, works[ch], logml[ch], lg_ca, lg_na);
+    }
+    const int rc = eval2_fallback_batch(*this, works, logml);
+    if (rc != PA_OK) return rc;
+    if (out->loglik)
+      for (int ch : host_chains) out->loglik[chain_elem_pos[ch] * 3 + chain_model[ch]] = logml[ch];
+  }
+  collected = true;
+  if (timing)
+    fprintf(stderr, "[pa timing] collect (device summaries): wait + %zu B of records %.3f s, unpack %.3f s, %zu chains through the host path %.3f s\n",
+            rec_bytes * (size_t)n_chains, t_copy - t_start, t_fin - t_copy, host_chains.size(), omp_get_wtime() - t_fin);
   return PA_OK;
 }
 

@@ -64,7 +64,12 @@ class Case:
         out = []
         src = os.path.join(GOLD, self.name)
         for fn in sorted(os.listdir(src)):
-            if fn.startswith("refrun_seed"):
+            if fn.startswith("refrun_seed") and fn.endswith(".json.gz"):
+                import gzip
+
+                with gzip.open(os.path.join(src, fn), "rt") as f:
+                    out.append(json.load(f))
+            elif fn.startswith("refrun_seed"):
                 with open(os.path.join(src, fn)) as f:
                     out.append(json.load(f))
         return out

@@ -73,7 +73,7 @@ def test_chain_traces_match_oracle_draw_for_draw(case, native_lib, oracle_lib):
             n_chains += 1
     assert n_chains >= 6
     cnt = eng.counters()
-    assert cnt["kernel_launches"] == 1 and cnt["chain_iterations"] == n_chains * (case.P.BURNIN + case.P.MCMC - 1)
+    assert cnt["kernel_launches"] == 2 and cnt["chain_iterations"] == n_chains * (case.P.BURNIN + case.P.MCMC - 1)
     eng.close()
 
 
