@@ -10,6 +10,8 @@
 //   * replayed log-likelihoods for given (model, Z, n_rate, c_rate) (bpp_c.cpp:131-343,647-671)
 //   * emissions + upward Z messages for a given ancestral history   (bpp_c2.cpp:355-390, bpp_c.cpp:1182-1212)
 //   * Eval2 for a given trace                                       (bpp_c2.cpp:14-353)
+//   * the reference's own WRITERS fed with given traces: Output_sampling / BPP_C::Output_init / BPP::Output_init
+//     (bpp_c2.cpp:706-785, bpp.cpp:568-619) -- byte-level format parity of the result files
 // The reference's own traces carry only 8 significant digits (bpp_c2.cpp:710),
 // which cannot pin 1e-10, hence this probe.
 //
@@ -146,6 +148,9 @@ int main(int argc, char** argv) {
   BPP_C* el = NULL;
   int cur_c = -1;
   bool filter = false;
+  string w_prefix;
+  ofstream w_outZ[3];
+  vector<int> w_ids;
   while (getline(script, line)) {
     istringstream ss(line);
     string cmd;
@@ -274,6 +279,60 @@ int main(int argc, char** argv) {
       while (getline(lines, ln)) printf("hyper_log %s\n", ln.c_str());
       printf("hyper_after %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", bpp.nprior_a, bpp.nprior_b, bpp.cprior_a, bpp.cprior_b,
              bpp.prior_l_a, bpp.prior_l_b, bpp.prior_g_a, bpp.prior_g_b, bpp.prior_l2_a, bpp.prior_l2_b);
+    } else if (cmd == "writers") {
+      // writers <prefix> : open <prefix>_rate_postZ_M{0,1,2}.txt with main()'s header line (main.cpp:380-399)
+      ss >> w_prefix;
+      for (int k = 0; k < 3; k++) {
+        w_outZ[k].open((w_prefix + "_rate_postZ_M" + to_string(k) + ".txt").c_str());
+        w_outZ[k] << "No.\tn_rate\tc_rate\tg_rate\tl_rate\tl2_rate";
+        for (int s = 0; s < N; s++)
+          for (int q = 0; q < 4; q++) w_outZ[k] << "\t" << bpp.nodes_names[s] << "_" << q;
+        w_outZ[k] << endl;
+      }
+      printf("writers %s\n", w_prefix.c_str());
+    } else if (cmd == "out") {
+      // out <resZ> <file index> <T> then T lines "t <loglik> <n> <c> <g> <l> <l2> <Z[0..N-1]>": the traces of one chain as Gibbs leaves
+      // them; runs the reference's MonitorChain bookkeeping, Eval2, then ITS writers Output_sampling and Output_init (main.cpp:466-494)
+      if (!el || filter) { printf("out skipped\n"); continue; }
+      int resZ, fidx, T;
+      ss >> resZ >> fidx >> T;
+      if (T != num_burn + num_mcmc) { printf("out bad T\n"); continue; }
+      el->initMCMC(0, bpp, resZ);
+      for (int m = 0; m < T; m++) {
+        string tl;
+        getline(script, tl);
+        istringstream ts(tl);
+        string tag; double ll, nr, cr, gr, lr, l2r;
+        ts >> tag >> ll >> nr >> cr >> gr >> lr >> l2r;
+        for (int s = 0; s < N; s++) ts >> el->Z[s];
+        el->trace_n_rate[m] = nr; el->trace_c_rate[m] = cr;
+        el->trace_g_rate[m] = gr; el->trace_l_rate[m] = lr; el->trace_l2_rate[m] = l2r;
+        if (m == 0) {  // MonitorChain(0) recomputes the log-likelihood from lambda: take slot 1's path instead (see eval2 above)
+          el->trace_n_rate[1] = nr; el->trace_c_rate[1] = cr;
+          el->MonitorChain(1, bpp, ll, 0.0, resZ);
+          el->trace_loglik[0] = el->trace_loglik[1];
+          el->trace_full_loglik[0] = el->trace_full_loglik[1];
+          el->trace_Z[0] = el->trace_Z[1];
+        } else {
+          el->MonitorChain(m, bpp, ll, 0.0, resZ);
+        }
+      }
+      bpp.log_liks_Z[resZ][cur_c] = el->MaxLoglik;  // Gibbs, bpp_c.cpp:470-471
+      bpp.Max_Z[resZ][cur_c] = el->Max_Z;
+      el->Eval2(bpp, resZ);
+      el->Output_sampling(0, w_prefix, bpp, fidx);
+      el->Output_init(w_prefix, w_prefix, bpp, w_outZ[fidx], resZ);
+      if (std::find(w_ids.begin(), w_ids.end(), cur_c) == w_ids.end()) w_ids.push_back(cur_c);
+      printf("out %d %d done\n", resZ, fidx);
+    } else if (cmd == "skip") {
+      // skip <c> : an id whose element was filtered -- it still gets its (all-zero) row in _elem_lik.txt / _elem_Z.txt
+      int c; ss >> c;
+      if (std::find(w_ids.begin(), w_ids.end(), c) == w_ids.end()) w_ids.push_back(c);
+    } else if (cmd == "finish") {
+      // finish : BPP::Output_init (bpp.cpp:568-619) over the ids seen, in script order
+      for (int k = 0; k < 3; k++) w_outZ[k].close();
+      bpp.Output_init(profile, w_prefix, w_ids);
+      printf("finish %d ids\n", (int)w_ids.size());
     } else if (cmd == "eval2") {
       // eval2 <resZ> <T> then T lines "t <loglik> <n> <c> <Z[0..N-1]>" : fills the traces as Gibbs would, then runs
       // MonitorChain-equivalent bookkeeping (full loglik, Max_Z) through the reference's own MonitorChain and Eval2.

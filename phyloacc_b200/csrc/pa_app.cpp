@@ -7,9 +7,14 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <functional>
 #include <sstream>
+#include <thread>
+
+#include <cuda_runtime.h>
 
 #include "pa_engine.h"
+#include "pa_nvtx.h"
 #include "pa_internal.h"
 
 namespace pa {
@@ -25,42 +30,38 @@ static bool directory_exists(const std::string& p) {  // main.cpp:291-307
   return false;
 }
 
-// LoadParams + LoadPhyloProfiles + LoadPhyloTree + BPP::BPP + id selection (main.cpp:331-358,406-439)
-static int create_from_config(const char* cfg_path, int device, pa_engine** out) {
-  pa_engine* e = new pa_engine();
-  e->from_config = true;
-  Params& P = e->params;
-  std::cout << "Loading program configurations from " << cfg_path << "......" << std::endl;
+// what the parsers produce: LoadParams + LoadPhyloProfiles + LoadPhyloTree + id selection (main.cpp:331-358,406-439)
+struct ConfigInputs {
+  Params P;
   Tree tree;
+  std::vector<std::string> element_names;
+  std::vector<int64_t> elem_start;
+  std::vector<int32_t> elem_len;
+  std::vector<int32_t> og, cg;  // OUTGROUP / CONSERVE as leaf ids
+  std::vector<int> ids;
+  std::vector<uint8_t> X;       // [S][G]
+  int64_t G = 0;
+  int C = 0;
+};
+
+static int load_config_inputs(const char* cfg_path, ConfigInputs& in) {
+  Params& P = in.P;
+  std::cout << "Loading program configurations from " << cfg_path << "......" << std::endl;
   Alignment aln;
-  if (!load_params(cfg_path, P)) { delete e; return PA_ERR_ARG; }
-  if (!load_alignment_files(P.align_path, P.segment_path, aln)) { delete e; return PA_ERR_IO; }
+  if (!load_params(cfg_path, P)) return PA_ERR_ARG;
+  if (!load_alignment_files(P.align_path, P.segment_path, aln)) return PA_ERR_IO;
   std::cout << "Loading phylogenetic tree from " << P.phytree_path << "......" << std::endl;
-  if (!load_tree(P.phytree_path, tree)) { delete e; return PA_ERR_IO; }
-  if (!match_alignment_to_tree(tree, aln)) {
+  if (!load_tree(P.phytree_path, in.tree)) return PA_ERR_IO;
+  if (!match_alignment_to_tree(in.tree, aln)) {
     set_error("alignment has fewer species than the tree");
-    delete e;
     return PA_ERR_ARG;
   }
-  std::vector<int32_t> og = species_ids(tree, P.outgroup), cg = species_ids(tree, P.conservegroup);
-  P.num.n_outgroup = (int32_t)og.size();
-  P.num.outgroup = og.data();
-  P.num.n_conserve = (int32_t)cg.size();
-  P.num.conserve = cg.data();
-  pa_tree pt{tree.S, tree.N, tree.parent.data(), tree.children.data(), tree.dist.data()};
-  pa_subst ps;
-  memcpy(ps.pi, tree.pi, sizeof(ps.pi));
-  memcpy(ps.Q, tree.Q, sizeof(ps.Q));
-  int rc = e->eng.init(&pt, &ps, &P.num, device);
-  P.num.outgroup = nullptr;
-  P.num.conserve = nullptr;
-  if (rc != PA_OK) { delete e; return rc; }
-  e->eng.model.tree.names = tree.names;
-  e->element_names = aln.element_names;
-  const int C = (int)aln.element_names.size();
-  std::vector<int> ids;
-  if (!load_ids(P, C, ids)) { delete e; return PA_ERR_IO; }
-  e->ids.assign(ids.begin(), ids.end());
+  const Tree& tree = in.tree;
+  in.og = species_ids(tree, P.outgroup);
+  in.cg = species_ids(tree, P.conservegroup);
+  in.element_names = aln.element_names;
+  const int C = in.C = (int)aln.element_names.size();
+  if (!load_ids(P, C, in.ids)) return PA_ERR_IO;
   double mean_len = 0;
   for (int c = 0; c < C; c++) mean_len += (double)aln.elem_len[c] / std::max(C, 1);
   std::cout << "# total length = " << aln.G << " (" << C << "). # Species = " << tree.S << ". # elements = " << C
@@ -68,8 +69,9 @@ static int create_from_config(const char* cfg_path, int device, pa_engine** out)
   std::cout << "# Burn-ins = " << P.num.burnin << ". # MCMC Updates = " << P.num.mcmc << ". # adaptive frequency = " << P.num.adapt_freq
             << ".  RND SEED = " << P.num.seed << "." << std::endl;
   // rows -> one [S][G] byte matrix
-  std::vector<uint8_t> X((size_t)tree.S * aln.G);
-  for (int s = 0; s < tree.S; s++) memcpy(X.data() + (size_t)s * aln.G, aln.X[s].data(), aln.G);
+  in.G = aln.G;
+  in.X.resize((size_t)tree.S * aln.G);
+  for (int s = 0; s < tree.S; s++) memcpy(in.X.data() + (size_t)s * aln.G, aln.X[s].data(), aln.G);
   std::vector<std::string>().swap(aln.X);
   // elements running past the alignment are clipped like std::string::substr does in the reference (bpp_c.hpp:211)
   for (int c = 0; c < C; c++) {
@@ -77,10 +79,76 @@ static int create_from_config(const char* cfg_path, int device, pa_engine** out)
     if (aln.elem_start[c] + aln.elem_len[c] > aln.G) aln.elem_len[c] = (int32_t)(aln.G - aln.elem_start[c]);
     if (aln.elem_len[c] < 0) aln.elem_len[c] = 0;
   }
-  rc = e->eng.load_alignment(X.data(), aln.G, C, aln.elem_start.data(), aln.elem_len.data());
-  if (rc != PA_OK) { delete e; return rc; }
+  in.elem_start = aln.elem_start;
+  in.elem_len = aln.elem_len;
+  return PA_OK;
+}
+
+// BPP::BPP on one device (bpp.hpp:173-404): an engine handle with the batch model; the alignment is loaded by the caller
+static int make_engine(const ConfigInputs& in, int device, int num_thread, pa_engine** out) {
+  pa_engine* e = new pa_engine();
+  e->from_config = true;
+  e->params = in.P;
+  pa_params num = in.P.num;
+  num.n_outgroup = (int32_t)in.og.size();
+  num.outgroup = in.og.data();
+  num.n_conserve = (int32_t)in.cg.size();
+  num.conserve = in.cg.data();
+  if (num_thread > 0) num.num_thread = num_thread;
+  pa_tree pt{in.tree.S, in.tree.N, in.tree.parent.data(), in.tree.children.data(), in.tree.dist.data()};
+  pa_subst ps;
+  memcpy(ps.pi, in.tree.pi, sizeof(ps.pi));
+  memcpy(ps.Q, in.tree.Q, sizeof(ps.Q));
+  const int rc = e->eng.init(&pt, &ps, &num, device);
+  if (rc != PA_OK) {
+    delete e;
+    return rc;
+  }
+  e->eng.model.tree.names = in.tree.names;
+  e->element_names = in.element_names;
+  e->ids.assign(in.ids.begin(), in.ids.end());
   *out = e;
   return PA_OK;
+}
+
+static int create_from_config(const char* cfg_path, int device, pa_engine** out) {
+  ConfigInputs in;
+  int rc = load_config_inputs(cfg_path, in);
+  if (rc != PA_OK) return rc;
+  pa_engine* e = nullptr;
+  rc = make_engine(in, device, 0, &e);
+  if (rc != PA_OK) return rc;
+  rc = e->eng.load_alignment(in.X.data(), in.G, in.C, in.elem_start.data(), in.elem_len.data());
+  if (rc != PA_OK) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return PA_OK;
+}
+
+// GPUs of this process the run is spread over: all visible ones unless PA_DEVICES=<count> says fewer or PA_DEVICE_LIST=<a,b,...> names
+// them (an ordinal may repeat: several shards on one GPU, used by the tests), and never more than one shard per
+// PA_MIN_ELEMS_PER_DEVICE (default 128) elements -- the driver's 50-locus batches stay on one GPU, genome-scale id files use the box
+static std::vector<int> pick_devices(int n_elems) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return {0};  // the engine reports the missing device itself
+  std::vector<int> devs;
+  if (const char* env = getenv("PA_DEVICE_LIST")) {
+    std::stringstream ss(env);
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+      if (!tok.empty()) devs.push_back(std::max(0, std::min(count - 1, atoi(tok.c_str()))));
+  }
+  if (devs.empty()) {
+    if (const char* env = getenv("PA_DEVICES")) count = std::max(1, std::min(count, atoi(env)));
+    for (int d = 0; d < count; d++) devs.push_back(d);
+  }
+  int per = 128;
+  if (const char* env = getenv("PA_MIN_ELEMS_PER_DEVICE")) per = std::max(1, atoi(env));
+  const int use = std::max(1, std::min((int)devs.size(), n_elems / per));
+  devs.resize(use);
+  return devs;
 }
 
 // writers: main.cpp:362-401, bpp_c2.cpp:706-736,739-785, bpp.cpp:568-619
@@ -99,14 +167,14 @@ static int run_from_config(const char* cfg_path) {
       return 1;
     }
   }
-  pa_engine* e = nullptr;
-  int rc = create_from_config(cfg_path, 0, &e);
+  ConfigInputs in;
+  int rc = load_config_inputs(cfg_path, in);
   if (rc != PA_OK) {
     std::cerr << "(Error. " << get_error() << ")" << std::endl;
     return 1;
   }
-  const Params& P = e->params;
-  const Tree& tree = e->eng.model.tree;
+  const Params& P = in.P;
+  const Tree& tree = in.tree;
   const int N = tree.N;
   const std::string prefix = P.output_path + "/" + P.result_prefix;
   // model slot -> file suffix: M0, M1, M2 (crossed variable names in the reference)
@@ -132,11 +200,11 @@ static int run_from_config(const char* cfg_path) {
     std::ofstream sp((prefix + "_species_names.txt").c_str());
     for (int s = 0; s < N; s++) sp << tree.names[s] << std::endl;
   }
-  std::cout << e->ids.size() << " of elements to be computed" << std::endl;
+  std::cout << in.ids.size() << " of elements to be computed" << std::endl;
 
-  const int C = (int)e->eng.plans.size();
+  const int C = in.C;
   std::vector<int32_t> ids;
-  for (int32_t c : e->ids) {
+  for (int32_t c : in.ids) {
     if (c < 0 || c >= C) {
       std::cout << c << " 1 Standard exception: element id out of range" << std::endl;  // reference: caught per element (main.cpp:497-499)
       continue;
@@ -148,53 +216,130 @@ static int run_from_config(const char* cfg_path) {
   std::vector<double> loglik((size_t)std::max(n, 1) * 3, 0.0), loglik_max((size_t)std::max(n, 1) * 3, 0.0), med((size_t)std::max(n, 1) * 15, 0.0),
       postZ((size_t)std::max(n, 1) * 3 * N * 4, 0.0);
   std::vector<int8_t> maxZ((size_t)std::max(n, 1) * 3 * N, 0);
-  pa_results res{n, N, filtered.data(), loglik.data(), loglik_max.data(), maxZ.data(), med.data(), postZ.data()};
+  // ---- shards: the ids are cut into contiguous ranges of equal cost (columns), one engine + host thread per GPU; no traffic between
+  // GPUs while sampling, the per-element summaries meet in the host arrays above.  Every engine holds only its shard;
+  // chains are keyed by the batch-wide element number, so the files do not depend on the number of GPUs.
+  const std::vector<int> devices = pick_devices(n);
+  const int n_dev = (int)devices.size();
+  std::vector<int> shard_lo(n_dev + 1, 0);
+  {
+    double total = 0;
+    for (int i = 0; i < n; i++) total += std::max(1, in.elem_len[ids[i]]);
+    double acc = 0;
+    int d = 1;
+    for (int i = 0; i < n && d < n_dev; i++) {
+      acc += std::max(1, in.elem_len[ids[i]]);
+      while (d < n_dev && acc >= total * d / n_dev) shard_lo[d++] = i + 1;
+    }
+    for (; d <= n_dev; d++) shard_lo[d] = n;
+    shard_lo[n_dev] = n;
+  }
+  std::vector<pa_engine*> engines(n_dev, nullptr);
+  std::vector<int> dev_rc(n_dev, PA_OK);
+  std::vector<std::string> dev_err(n_dev);
+  auto for_each_device = [&](const std::function<int(int)>& fn) {
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_dev; d++)
+      th.emplace_back([&, d]() {
+        try {
+          dev_rc[d] = fn(d);
+          if (dev_rc[d] != PA_OK) dev_err[d] = get_error();
+        } catch (const std::exception& ex) {
+          dev_rc[d] = PA_ERR_ARG;
+          dev_err[d] = std::string("internal error: ") + ex.what();
+        }
+      });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_dev; d++)
+      if (dev_rc[d] != PA_OK) {
+        std::cerr << "(Error. GPU " << d << ": " << dev_err[d] << ")" << std::endl;
+        return false;
+      }
+    return true;
+  };
+  auto destroy_all = [&]() {
+    for (pa_engine* e : engines) delete e;
+  };
+  const int threads_per_dev = std::max(1, P.num.num_thread / n_dev);
+  if (n_dev > 1) std::cout << "# element shards = " << n_dev << " (one engine and host thread per shard)." << std::endl;
+  if (!for_each_device([&](int d) {
+        PA_NVTX_RANGE("load shard");
+        int r = make_engine(in, devices[d], threads_per_dev, &engines[d]);
+        if (r != PA_OK) return r;
+        const int lo = shard_lo[d], cnt = shard_lo[d + 1] - lo;
+        std::vector<int64_t> st(cnt);
+        std::vector<int32_t> ln(cnt), gid(cnt);
+        for (int k = 0; k < cnt; k++) {
+          st[k] = in.elem_start[ids[lo + k]];
+          ln[k] = in.elem_len[ids[lo + k]];
+          gid[k] = ids[lo + k];
+        }
+        return engines[d]->eng.load_alignment(in.X.data(), in.G, cnt, st.data(), ln.data(), gid.data());
+      })) {
+    destroy_all();
+    return 1;
+  }
   for (int iter = 0; iter < P.num_chain; iter++) {
     std::cout << "Running MCMC chain " << iter + 1 << " ..." << std::endl;
-    // elements go to the device in waves so that the traces of one wave fit comfortably in HBM and host memory
-    const int wave = 4096;
-    for (int w0 = 0; w0 < n; w0 += wave) {
-      const int wn = std::min(wave, n - w0);
-      pa_results wres{wn, N, filtered.data() + w0, loglik.data() + (size_t)w0 * 3, loglik_max.data() + (size_t)w0 * 3,
-                      maxZ.data() + (size_t)w0 * 3 * N, med.data() + (size_t)w0 * 15, postZ.data() + (size_t)w0 * 3 * N * 4};
-      // SAMPLE_HYPER 1 runs only the full model (main.cpp:463-494); outer iterations after the first continue every chain
-      // from its last state (initMCMC with iter > 0, bpp_c.cpp:148-177).  The reference saves that state only `if(UpHyper)`
-      // (bpp_c.cpp:474-485): with SAMPLE_HYPER 0 and CHAIN > 1 its later iterations restart from bpp.cur_Z (all zeros: every node
-      // starts in the background state) and the INIT_* rates -- a fresh chain on a new random stream here (Z = 1 start as in iter 0).
-      rc = e->eng.sample(ids.data() + w0, wn, P.sample_hyper ? (1 << PA_M2) : 7, P.sample_hyper && iter > 0, iter);
-      if (rc == PA_OK) rc = e->eng.collect(&wres);
-      if (rc != PA_OK) {
-        std::cerr << "(Error. " << get_error() << ")" << std::endl;
-        delete e;
-        return 1;
-      }
-      // VERBOSE: per-chain traces (Output_sampling, bpp_c2.cpp:706-736); file index is the reference's third argument 0,1,2
-      if (P.verbose) {
-        for (int i = 0; i < wn; i++) {
-          if (filtered[w0 + i]) continue;
-          for (int m = 0; m < 3; m++) {
-            ChainTraceHost tr;
-            if (e->eng.get_trace(i, m, tr) != PA_OK) continue;
-            const std::string path = prefix + "_mcmc_trace_M" + std::to_string(m) + "_" + std::to_string(ids[w0 + i]) + ".txt";
-            std::ofstream ot;
-            ot.precision(8);
-            if (iter == 0) {
-              ot.open(path.c_str());
-              ot << "loglik\trate_n\trate_c\tgrate\tlrate\tlrate2\t";
-              for (int s = 0; s < N; s++) ot << tree.names[s] << "\t";
-              ot << std::endl;
-            } else ot.open(path.c_str(), std::ios::app);
-            const int T = (int)tr.loglik.size();
-            for (int t = 0; t < T; t++) {
-              ot << tr.loglik[t] << "\t" << tr.n_rate[t] << "\t" << tr.c_rate[t] << "\t" << tr.g_rate[t] << "\t" << tr.l_rate[t] << "\t" << tr.l2_rate[t] << "\t";
-              for (int s = 0; s < N; s++) ot << (int)tr.Z[(size_t)t * N + s] << "\t";
-              ot << std::endl;
+    const bool ok = for_each_device([&](int d) {
+      Engine& eng = engines[d]->eng;
+      const int lo = shard_lo[d], cnt = shard_lo[d + 1] - lo;
+      // elements go through the device in waves so that the traces of one wave fit comfortably in HBM
+      const int wave = 8192;
+      std::vector<int32_t> local(std::min(wave, std::max(cnt, 1)));
+      for (int w0 = 0; w0 < cnt; w0 += wave) {
+        const int wn = std::min(wave, cnt - w0);
+        for (int k = 0; k < wn; k++) local[k] = w0 + k;
+        const size_t g0 = (size_t)lo + w0;
+        pa_results wres{wn, N, filtered.data() + g0, loglik.data() + g0 * 3, loglik_max.data() + g0 * 3, maxZ.data() + g0 * 3 * N, med.data() + g0 * 15,
+                        postZ.data() + g0 * 3 * N * 4};
+        // SAMPLE_HYPER 1 runs only the full model (main.cpp:463-494); outer iterations after the first continue every chain
+        // from its last state (initMCMC with iter > 0, bpp_c.cpp:148-177).  The reference saves that state only `if(UpHyper)`
+        // (bpp_c.cpp:474-485): with SAMPLE_HYPER 0 and CHAIN > 1 its later iterations restart from bpp.cur_Z (all zeros: every node
+        // starts in the background state) and the INIT_* rates -- a fresh chain on a new random stream here (Z = 1 start as in iter 0).
+        int r;
+        {
+          PA_NVTX_RANGE("sample wave");
+          r = eng.sample(local.data(), wn, P.sample_hyper ? (1 << PA_M2) : 7, P.sample_hyper && iter > 0, iter);
+        }
+        if (r == PA_OK) {
+          PA_NVTX_RANGE("collect wave");
+          r = eng.collect(&wres);
+        }
+        if (r != PA_OK) return r;
+        // VERBOSE: per-chain traces (Output_sampling, bpp_c2.cpp:706-736); file index is the reference's third argument 0,1,2
+        if (P.verbose) {
+          PA_NVTX_RANGE("write traces");
+          for (int i = 0; i < wn; i++) {
+            if (filtered[g0 + i]) continue;
+            for (int m = 0; m < 3; m++) {
+              ChainTraceHost tr;
+              if (eng.get_trace(i, m, tr) != PA_OK) continue;
+              const std::string path = prefix + "_mcmc_trace_M" + std::to_string(m) + "_" + std::to_string(ids[g0 + i]) + ".txt";
+              std::ofstream ot;
+              ot.precision(8);
+              if (iter == 0) {
+                ot.open(path.c_str());
+                ot << "loglik\trate_n\trate_c\tgrate\tlrate\tlrate2\t";
+                for (int s = 0; s < N; s++) ot << tree.names[s] << "\t";
+                ot << std::endl;
+              } else ot.open(path.c_str(), std::ios::app);
+              const int T = (int)tr.loglik.size();
+              for (int t = 0; t < T; t++) {
+                ot << tr.loglik[t] << "\t" << tr.n_rate[t] << "\t" << tr.c_rate[t] << "\t" << tr.g_rate[t] << "\t" << tr.l_rate[t] << "\t" << tr.l2_rate[t] << "\t";
+                for (int s = 0; s < N; s++) ot << (int)tr.Z[(size_t)t * N + s] << "\t";
+                ot << std::endl;
+              }
             }
           }
         }
       }
+      return (int)PA_OK;
+    });
+    if (!ok) {
+      destroy_all();
+      return 1;
     }
-    (void)res;
     // rows of _rate_postZ_Mk.txt (Output_init, bpp_c2.cpp:776-783; default ofstream precision = 6 significant digits)
     for (int i = 0; i < n; i++) {
       if (filtered[i]) continue;
@@ -210,8 +355,19 @@ static int run_from_config(const char* cfg_path) {
     }
     if (P.sample_hyper) {
       // BPP::sample_hyperparam + BPP::Output_init0 (main.cpp:504-506, bpp.cpp:324-477, 622-635)
+      // the sweep needs the elements only through PA_HYPER_NSUMS sums: every shard adds its own, every engine draws the same sweep
       pa_hyper hy;
-      rc = e->eng.sample_hyper(iter, e->ids.data(), (int32_t)e->ids.size(), &hy);
+      double sums[PA_HYPER_NSUMS] = {0};
+      rc = PA_OK;
+      for (int d = 0; d < n_dev && rc == PA_OK; d++) {
+        const int cnt = shard_lo[d + 1] - shard_lo[d];
+        std::vector<int32_t> local(cnt);
+        for (int k = 0; k < cnt; k++) local[k] = k;
+        double part[PA_HYPER_NSUMS];
+        rc = engines[d]->eng.hyper_sums(local.data(), cnt, part);
+        for (int k = 0; k < PA_HYPER_NSUMS; k++) sums[k] += part[k];
+      }
+      for (int d = 0; d < n_dev && rc == PA_OK; d++) rc = engines[d]->eng.sample_hyper_from_sums(iter, sums, &hy);
       if (rc != PA_OK) {
         std::cout << " 2 Standard exception: " << get_error() << std::endl;
       } else {
@@ -219,7 +375,7 @@ static int run_from_config(const char* cfg_path) {
                   << hy.prior_l_b << "\t" << hy.prior_g_a << "\t" << hy.prior_g_b << "\t" << hy.prior_l2_a << "\t" << hy.prior_l2_b << std::endl;
       }
       for (int i = 0; i < n; i++)
-        out_lik_hyper << ids[i] << "\t" << e->element_names[ids[i]] << "\t" << loglik[i * 3 + PA_M2] << "\t" << loglik_max[i * 3 + PA_M2] << std::endl;
+        out_lik_hyper << ids[i] << "\t" << in.element_names[ids[i]] << "\t" << loglik[i * 3 + PA_M2] << "\t" << loglik_max[i * 3 + PA_M2] << std::endl;
       continue;
     }
     // _elem_lik.txt and _M{k}_elem_Z.txt (BPP::Output_init, bpp.cpp:568-619): one row per id, zeros for filtered ones
@@ -229,7 +385,7 @@ static int run_from_config(const char* cfg_path) {
       ol << "No.\tID\tloglik_Null\tloglik_Acc\tloglik_Full\tlogBF1\tlogBF2\tloglik_Max_M0\tloglik_Max_M1\tloglik_Max_M2" << std::endl;
       for (int i = 0; i < n; i++) {
         const double l0 = loglik[i * 3 + 0], l1 = loglik[i * 3 + 1], l2 = loglik[i * 3 + 2];
-        ol << ids[i] << "\t" << e->element_names[ids[i]] << "\t" << l0 << "\t" << l1 << "\t" << l2 << "\t";
+        ol << ids[i] << "\t" << in.element_names[ids[i]] << "\t" << l0 << "\t" << l1 << "\t" << l2 << "\t";
         ol << l1 - l0 << "\t" << l1 - l2;
         ol << "\t" << loglik_max[i * 3 + 0] << "\t" << loglik_max[i * 3 + 1] << "\t" << loglik_max[i * 3 + 2];
         ol << std::endl;
@@ -248,7 +404,7 @@ static int run_from_config(const char* cfg_path) {
     }
   }
   for (int m = 0; m < 3; m++) out_Z[m].close();
-  delete e;
+  destroy_all();
   std::cout << std::endl << std::endl << "time used:  " << (time(NULL) - start) / 60 << " min." << std::endl << std::endl;
   return 0;
 }

@@ -439,7 +439,8 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
     const int chain = L.sel ? L.sel[qslot] : qslot;
     const int elem = L.chain_list[2 * chain], mdl = L.chain_list[2 * chain + 1];
     const int resZ = (mdl == PA_M0) ? 0 : (mdl == PA_M1 ? 2 : 1);
-    const uint32_t key = (uint32_t)elem * 4u + (uint32_t)mdl;
+    // random streams are keyed by the element's batch-wide number (= elem unless this engine holds a shard of the batch)
+    const uint32_t key = (uint32_t)reinterpret_cast<const ElemHeader*>(L.blobs + L.blob_off[elem])->elem_id * 4u + (uint32_t)mdl;
     // the element's array pointers live in shared memory: in registers they spill, and local memory misses the (small) L1 here
     if (tid == 0) S.ev = make_view(L.blobs + L.blob_off[elem]);
     __syncthreads();

@@ -17,6 +17,7 @@
 #include "pa_device.cuh"
 #include "pa_engine.h"
 #include "pa_internal.h"
+#include "pa_nvtx.h"
 
 namespace pa {
 
@@ -162,7 +163,8 @@ int Engine::init(const pa_tree* tree, const pa_subst* subst, const pa_params* pa
   return PA_OK;
 }
 
-int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len) {
+int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len, const int32_t* global_ids) {
+  PA_NVTX_RANGE("pa_engine_load_alignment");
   if (C < 0 || G < 0) {
     set_error("bad alignment dimensions");
     return PA_ERR_ARG;
@@ -177,7 +179,7 @@ int Engine::load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t
 
   const int nt = std::max(1, model.prm.num_thread);
 #pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
-  for (int c = 0; c < C; c++) plan_element(model, X, G, elem_start[c], elem_len[c], c, plans[c]);
+  for (int c = 0; c < C; c++) plan_element(model, X, G, elem_start[c], elem_len[c], global_ids ? global_ids[c] : c, plans[c]);
   blob_off.assign(C, -1);
   size_t total = 0;
   n_max = 0; slots_max = 1; P_max = 0; GG_max = 0;

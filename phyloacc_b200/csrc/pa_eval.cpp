@@ -17,6 +17,7 @@
 
 #include "pa_chain.cuh"
 #include "pa_engine.h"
+#include "pa_nvtx.h"
 #include "pa_summary.cuh"
 
 namespace pa {
@@ -178,6 +179,7 @@ int Engine::sample_hyper_from_sums(int iter, const double* sums, pa_hyper* out) 
 
 // ------------------------------------------------------------------------------------------ launch
 int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_start, int chain_iter) {
+  PA_NVTX_RANGE("pa_engine_sample");
   if (!loaded) {
     set_error("pa_engine_sample called before pa_engine_load_alignment");
     return PA_ERR_STATE;
@@ -802,6 +804,7 @@ static int eval2_fallback_batch(Engine& eng, const std::vector<Eval2Work>& works
 }  // namespace
 
 int Engine::collect(pa_results* out) {
+  PA_NVTX_RANGE("pa_engine_collect");
   const bool timing = getenv("PA_TIMING") != nullptr;
   const double t_start = omp_get_wtime();
   if (!sampled) {

@@ -115,3 +115,46 @@ def test_drop_in_binary_writes_reference_formats(native_lib):
         if np.isfinite(v[:5]).all():
             assert abs((v[1] - v[0]) - v[3]) < 1e-4 * max(1, abs(v[3])) and abs((v[1] - v[2]) - v[4]) < 1e-4 * max(1, abs(v[4]))
     case.close()
+
+
+def _run_binary(cfg, env_extra):
+    env = dict(os.environ)
+    env.update(env_extra)
+    r = subprocess.run([pab.BIN_PATH, cfg], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def _read_outputs(case):
+    out = os.path.join(case.dir, "out")
+    files = {}
+    for fn in sorted(os.listdir(out)):
+        with open(os.path.join(out, fn), "rb") as f:
+            files[fn] = f.read()
+    return files
+
+
+@pytest.mark.parametrize("name,extra", [("ratite43", dict(VERBOSE=1)), ("tiny8", dict(SAMPLE_HYPER=1, CHAIN=3))])
+def test_sharded_run_writes_byte_identical_files(native_lib, name, extra):
+    """pa_run_from_config spreads the ids over all GPUs of the box (one engine + host thread per shard, pa_app.cpp).  Chains are keyed
+    by the batch-wide element number, so every output file -- traces included, SAMPLE_HYPER's outer iterations included -- must be
+    byte-identical whatever the number of shards.  With one GPU the shards share it (PA_DEVICE_LIST=0,0,0); with several they run on
+    different GPUs."""
+    import torch
+
+    one = Case(name, extra_params=extra)
+    _run_binary(one.cfg, dict(PA_DEVICES="1"))
+    ref = _read_outputs(one)
+    assert any(k.endswith("_elem_lik.txt") for k in ref)
+    n_gpu = torch.cuda.device_count()
+    lists = ["0,0,0"] + ([",".join(str(d) for d in range(min(n_gpu, 4)))] if n_gpu > 1 else [])
+    for lst in lists:
+        many = Case(name, extra_params=extra)
+        log = _run_binary(many.cfg, dict(PA_DEVICE_LIST=lst, PA_MIN_ELEMS_PER_DEVICE="1"))
+        assert "# element shards = " in log
+        got = _read_outputs(many)
+        assert sorted(got) == sorted(ref)
+        for fn in ref:
+            assert got[fn] == ref[fn], (lst, fn)
+        many.close()
+    one.close()
