@@ -198,6 +198,12 @@ int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10);
  * register-resident DFMA micro-benchmark run for about `millis` ms. Not part of the reference's interface. */
 int pa_device_fp64_peak(int device, int millis, double* tflops_out);
 
+/* PhyloAcc-ST-GBGC groundwork (not yet a chain): the per-branch GC-biased matrices of BPP_C::getRate and
+ * BPP_C::getTransition (src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:13-30,1405-1427) for n (selection, bias, branch length) triples on `device`:
+ * rate_out (may be NULL) and P_out are [n][16] row-major, rate i -> j and P(i -> j | t).  The reference returns log P transposed. */
+int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const double* sel, const double* bias, const double* t, double* rate_out,
+                       double* P_out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

@@ -1,0 +1,89 @@
+// oracle/gbgc_probe.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Driver linked against the UNMODIFIED translation units of src/PhyloAcc-ST-GBGC/SRC (oracle/Makefile, target ref-gbgc) that
+// dumps, as hex floats, what the GC-biased model computes for a branch:
+//   * BPP_C::getRate(Q0, s, b)           Q o f(s + b B), rows renormalised            (GBGC/SRC/bpp_c.cpp:13-30)
+//   * BPP_C::getTransition(node, s, b)   log P(t)^T from the eigensystem of that Q    (GBGC/SRC/bpp_c.cpp:1405-1427)
+// for the grid of (node, selection, bias) triples in the script.  It pins oracle/gbgc.py and the CUDA kernel behind
+// pa_gbgc_transition (phyloacc_b200/csrc/pa_gbgc.cu).
+//
+// usage: gbgc_probe <cfg> <script>     script lines: "tm <node> <sel> <bias>"
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <unistd.h>
+#include <armadillo>
+
+#define private public
+#define protected public
+#include "bpp.hpp"
+#include "bpp_c.hpp"
+#undef private
+#undef protected
+
+using namespace std;
+using namespace arma;
+
+int main(int argc, char** argv) {
+  if (argc < 3) { fprintf(stderr, "usage: gbgc_probe <cfg> <script>\n"); return 2; }
+  map<string, string> kv;
+  {
+    ifstream in(argv[1]);
+    string line;
+    while (getline(in, line)) {
+      istringstream ss(line);
+      string k, v;
+      if (!(ss >> k)) continue;
+      ss >> v;
+      kv[k] = v;
+    }
+  }
+  auto get = [&](const char* k, const char* d) { return kv.count(k) ? kv[k] : string(d); };
+  // defaults of GBGC/SRC/main.cpp:40-90
+  fflush(stdout);
+  streambuf* old_cout = cout.rdbuf();
+  ostringstream sink;
+  cout.rdbuf(sink.rdbuf());
+  FILE* real_stdout = fdopen(dup(fileno(stdout)), "w");
+  freopen("/dev/null", "w", stdout);
+  PhyloProf profile = LoadPhyloProfiles(get("ALIGN_FILE", ""), get("SEG_FILE", ""));
+  PhyloTree phytree = LoadPhyloTree(get("PHYTREE_FILE", ""));
+  BPP bpp(0, profile, phytree, string("."), get("TARGETSPECIES", ""), get("OUTGROUP", ""), 0.8, get("CONSERVE", ""), get("REF", ""), -2, 0, 0, 1, 0.6, 5, 0.4, 5,
+          0.4, 4, 0.8, 0.2, 1, 1, 7728, 0.1, 0.8, 0.01, 0.1, 0.8, false);
+  bpp.InitMCMC(20, 40, 10);
+  bool filter = false;
+  string gc = get("GAPCHAR", "*");
+  BPP_C el(0, profile, bpp, gc[0], 0.8, filter, false);
+  fflush(stdout);
+  dup2(fileno(real_stdout), fileno(stdout));
+  printf("gbgc N %d filter %d\n", bpp.N, (int)filter);
+  {
+    printf("Q");
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) printf(" %a", bpp.submat(i, j));
+    printf("\n");
+  }
+  ifstream script(argv[2]);
+  string line;
+  while (getline(script, line)) {
+    istringstream ss(line);
+    string cmd;
+    if (!(ss >> cmd)) continue;
+    if (cmd == "tm") {
+      int s; double sel, bias;
+      ss >> s >> sel >> bias;
+      mat Q = el.getRate(bpp.submat, sel, bias);
+      mat L = el.getTransition(s, sel, bias, bpp);
+      printf("tm %d %a %a t %a\nrate", s, sel, bias, el.distances2[s]);
+      for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) printf(" %a", Q(i, j));
+      printf("\nlogtm");
+      for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) printf(" %a", L(i, j));  // (child, parent) layout like the ST caches
+      printf("\n");
+    }
+  }
+  cout.rdbuf(old_cout);
+  return 0;
+}

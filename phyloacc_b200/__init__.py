@@ -94,7 +94,7 @@ EXPORTS = [
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
-    "pa_engine_sample_hyper_sums", "pa_engine_element_blob",
+    "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition",
 ]
 
 _lib = None
@@ -151,6 +151,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
     lib.pa_run_from_config.argtypes = [C.c_char_p]
     lib.pa_device_fp64_peak.argtypes = [C.c_int, C.c_int, _f64p]
+    lib.pa_gbgc_transition.argtypes = [C.c_int, C.POINTER(PaSubst), C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p]
     _lib = lib
     return lib
 
@@ -158,6 +159,20 @@ def load_library(build_if_missing: bool = True):
 def _check(rc: int):
     if rc != PA_OK:
         raise PhyloAccError(rc, load_library().pa_last_error().decode(errors="replace"))
+
+
+def gbgc_transition(Q, sel, bias, t, device: int = 0):
+    """PhyloAcc-ST-GBGC's per-branch matrices on the device (pa_gbgc.cu): returns (rate [n, 4, 4], P [n, 4, 4]) for n
+    (selection coefficient, gBGC bias, branch length) triples; rate i -> j, P(i -> j | t)."""
+    lib = load_library()
+    s = PaSubst()
+    s.Q[:] = list(map(float, np.asarray(Q).reshape(-1)))
+    sel, bias, t = (np.ascontiguousarray(x, dtype=np.float64) for x in (sel, bias, t))
+    n = len(sel)
+    rate, P = np.zeros((n, 4, 4)), np.zeros((n, 4, 4))
+    _check(lib.pa_gbgc_transition(device, C.byref(s), n, sel.ctypes.data_as(_f64p), bias.ctypes.data_as(_f64p), t.ctypes.data_as(_f64p),
+                                  rate.ctypes.data_as(_f64p), P.ctypes.data_as(_f64p)))
+    return rate, P
 
 
 def default_params() -> PaParams:

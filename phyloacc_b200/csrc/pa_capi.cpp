@@ -224,6 +224,15 @@ int pa_engine_get_trace(pa_engine* e, int32_t i, int32_t model, pa_trace* out) {
   });
 }
 
+int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const double* sel, const double* bias, const double* t, double* rate_out,
+                       double* P_out) {
+  if (!subst || n < 0 || (n > 0 && (!sel || !bias || !t || !P_out))) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return pa::gbgc_transition(device, subst->Q, n, sel, bias, t, rate_out, P_out); });
+}
+
 int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
   if (!e || !out10) return PA_ERR_ARG;
   for (int k = 0; k < 10; k++) out10[k] = e->eng.phase_cycles[k];

@@ -41,7 +41,7 @@ namespace {
 enum { SC_N = 0, SC_C, SC_G, SC_L, SC_L2, SC_LL, SC_PROPN, SC_PROPC, SC_PROPOSAL, SC_MHPART, SC_R,
        // scalars of the two MH steps, computed ahead of time by the last warp while the others sample histories
        SC_PRE_R_N = 16, SC_PRE_PROP_N, SC_PRE_PRIOR_N, SC_PRE_MH_N, SC_PRE_R_C, SC_PRE_PROP_C, SC_PRE_PRIOR_C, SC_PRE_MH_C, SC_COUNT = 24 };
-enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_KSLICE, IV_COUNT = 16 };
+enum { IV_CHAIN = 0, IV_ANY_CHANGED, IV_HAS1, IV_HAS2, IV_VALID, IV_ACCEPT, IV_RATE_CHANGED, IV_ACC_N, IV_ACC_C, IV_ZFALLBACK, IV_NSU, IV_STAGED, IV_NACT, IV_KSLICE, IV_ANYAMB, IV_COUNT = 16 };
 
 template <int NMAX, int SLOTS_, int BD_, bool STAGE_>
 struct SmemT {
@@ -90,7 +90,7 @@ struct SmemT {
   int16_t parent[NMAX], child[2 * NMAX], up_nodes[NMAX], up_off[NMAX + 1], down_nodes[NMAX], down_off[NMAX + 1];
   int16_t qof[NMAX];  // internal index of a node (-1 for tips)
   uint16_t tk[BD_];   // pair-count pass: thread -> branch | word slice << 8 (trees with at most 128 branches)
-  uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX];
+  uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX], amb[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
   alignas(4) uint8_t codes[STAGE_ ? NI * CODEROW : 4];
 };
@@ -356,29 +356,37 @@ __device__ __noinline__ void z_update_logspace(SM& S, int n) {
   }
 }
 
-// pair-count pass, rare path: the sites of 32-site word `word` of the current tile at which tip `row` carries an ambiguity code
-// (bits of `am`) contribute log sum_{b in code} P_k(x_parent -> b) to the branch's emissions (bpp_c2.cpp:372-378)
+// pair-count pass, rare path: the sites of the current tile at which tip `row` carries an ambiguity code contribute
+// log sum_{b in code} P_k(x_parent -> b) to the branch's emissions (bpp_c2.cpp:372-378).  One thread per flagged branch walks the
+// tile's words and sites in order, so the sum -- and with it the chain -- is reproducible bit for bit (round 1 added the terms with
+// shared-memory atomics from several word slices: same value up to the order of the additions).
 template <class SM>
 __device__ __noinline__ void count_ambiguous(SM& S, const ElemView& ev, const double* __restrict__ logP, int n_max, int i, uint32_t row, uint32_t qp,
-                                             int site0, int word, uint32_t am) {
+                                             int g0, int nw, size_t tcell) {
   const int Ppad = ev.h->Ppad;
-  const uint4 pp = S.planes[qp * SM::NWARP + word];
-  while (am) {
-    const int bit = __ffs(am) - 1;
-    am &= am - 1u;
-    if (!(((pp.x | pp.y | pp.z | pp.w) >> bit) & 1u)) continue;  // no base drawn for the parent at this site
-    const uint32_t xp = ((pp.y >> bit) & 1u) + 2u * ((pp.z >> bit) & 1u) + 3u * ((pp.w >> bit) & 1u);
-    const int pat = ev.sitepat[site0 + bit];
-    const uint32_t code4 = ((uint32_t)ev.codes[(size_t)row * (Ppad >> 1) + (pat >> 1)] >> ((pat & 1) * 4)) & 15u;
+  double e[3] = {0.0, 0.0, 0.0};
+  for (int word = 0; word < nw; word++) {
+    uint32_t am = __ldg(ev.tipamb + tcell + word);
+    if (!am) continue;
+    const uint4 pp = S.planes[qp * SM::NWARP + word];
+    while (am) {
+      const int bit = __ffs(am) - 1;
+      am &= am - 1u;
+      if (!(((pp.x | pp.y | pp.z | pp.w) >> bit) & 1u)) continue;  // no base drawn for the parent at this site
+      const uint32_t xp = ((pp.y >> bit) & 1u) + 2u * ((pp.z >> bit) & 1u) + 3u * ((pp.w >> bit) & 1u);
+      const int pat = ev.sitepat[g0 + 32 * word + bit];
+      const uint32_t code4 = ((uint32_t)ev.codes[(size_t)row * (Ppad >> 1) + (pat >> 1)] >> ((pat & 1) * 4)) & 15u;
 #pragma unroll 1
-    for (int kk = 0; kk < 3; kk++) {
-      const double* lp = logP + ((size_t)kk * n_max + i) * 16 + xp * 4;
-      double sum = 0;
-      for (int b = 0; b < 4; b++)
-        if ((code4 >> b) & 1u) sum += exp(lp[b]);
-      atomicAdd(&S.eamb[i * 3 + kk], log(sum));
+      for (int kk = 0; kk < 3; kk++) {
+        const double* lp = logP + ((size_t)kk * n_max + i) * 16 + xp * 4;
+        double sum = 0;
+        for (int b = 0; b < 4; b++)
+          if ((code4 >> b) & 1u) sum += exp(lp[b]);
+        e[kk] += log(sum);
+      }
     }
   }
+  for (int kk = 0; kk < 3; kk++) S.eamb[i * 3 + kk] += e[kk];
 }
 
 template <int NMAX, int SLOTS, int BD, int MINB, bool STAGE>
@@ -468,6 +476,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       S.Z[i] = warm ? (int8_t)((L.init_z[(size_t)chain * L.ZW + (i >> 4)] >> (2 * (i & 15))) & 3u) : (int8_t)((i == root) ? 0 : 1);  // bpp_c.cpp:141-151
       S.dirty[i] = 0;
       S.sel[i] = 0;
+      S.amb[i] = 0;
       S.qof[i] = ev.intidx[i];
     }
     // pair-count descriptors: the branch above node i joins the sampled base of its parent with the node's own sampled
@@ -521,6 +530,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       int nsu = 0;
       while (nsu < ni && ev.su[nsu] >= 0) nsu++;
       S.ivars[IV_NSU] = nsu;
+      S.ivars[IV_ANYAMB] = 0;
       S.scal[SC_N] = init_n;
       S.scal[SC_C] = init_c;
       S.scal[SC_G] = init_g;
@@ -735,8 +745,10 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
                 uint4 c;
                 if (tip) {
                   c = __ldg(ev.tipplanes + tcell + w);
-                  const uint32_t am = __ldg(ev.tipamb + tcell + w);
-                  if (am) count_ambiguous(S, ev, logP, L.n_max, i, cx, qp, g0 + 32 * w, w, am);
+                  if (__ldg(ev.tipamb + tcell + w)) {  // rare: handled by one thread per branch below (fixed summation order)
+                    S.amb[i] = 1;
+                    S.ivars[IV_ANYAMB] = 1;
+                  }
                 } else c = crow[w];
                 c0 += (uint32_t)__popc(a.x & c.x) + ((uint32_t)__popc(a.x & c.y) << 8) + ((uint32_t)__popc(a.x & c.z) << 16) + ((uint32_t)__popc(a.x & c.w) << 24);
                 c1 += (uint32_t)__popc(a.y & c.x) + ((uint32_t)__popc(a.y & c.y) << 8) + ((uint32_t)__popc(a.y & c.z) << 16) + ((uint32_t)__popc(a.y & c.w) << 24);
@@ -753,6 +765,18 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           }
         }
         __syncthreads();
+        if (S.ivars[IV_ANYAMB]) {  // ambiguity-coded tips in this tile (uniform over the CTA)
+          const int nw = (min(kTile, GG - g0) + 31) >> 5;
+          const size_t tile_row0 = (size_t)(g0 / kTile) * (size_t)h->S;
+          for (int i = tid; i < n - 1; i += kBD) {
+            if (!S.amb[i]) continue;
+            S.amb[i] = 0;
+            const uint32_t d = S.cb[i];
+            count_ambiguous(S, ev, logP, L.n_max, i, d & 0xffffu, (d >> 16) & 0x7fffu, g0, nw, (tile_row0 + (d & 0xffffu)) * 8);
+          }
+          __syncthreads();
+          if (tid == 0) S.ivars[IV_ANYAMB] = 0;
+        }
       }
       if (tid == 0) w_hist += (unsigned long long)GG * ni;
       PA_PHASE(2)

@@ -150,6 +150,7 @@ bool match_alignment_to_tree(const Tree& t, Alignment& a);
 std::vector<int32_t> species_ids(const Tree& t, const std::string& semicolon_list);
 bool build_model(const Tree& t, const pa_params& prm, Model& out);
 bool eigen_real4(const double Q[16], double eval[4], double V[16], double Vinv[16]);
+int gbgc_transition(int device, const double* Q0, int n, const double* sel, const double* bias, const double* t, double* rate_out, double* P_out);  // pa_gbgc.cu
 void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, int32_t len, int elem_id, ElemPlan& out);
 
 }  // namespace pa
