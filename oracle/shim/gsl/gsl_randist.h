@@ -83,6 +83,13 @@ static inline void gsl_ran_multinomial(gsl_rng* r, size_t K, unsigned int N, con
   }
 }
 
+/* exponential with MEAN mu (GSL's parameterisation), used by PhyloAcc-GT's coalescent times (genetree.cpp:414,1004) */
+static inline double gsl_ran_exponential(gsl_rng* r, double mu) {
+  double u;
+  do { u = gsl_rng_uniform(r); } while (u <= 0.0);
+  return -mu * std::log(u);
+}
+
 static inline double gsl_ran_gamma_pdf(double x, double a, double b) {
   if (x < 0) return 0;
   if (x == 0) return (a == 1) ? 1 / b : 0;

@@ -49,7 +49,8 @@ struct SmemT {
   static constexpr bool XS8 = STAGE_;      // sampled bases also kept as a byte matrix (false: the parent's base is read back from the bit planes)
   static constexpr int NI = NMAX / 2 + 1;  // internal nodes / tip rows
   static constexpr int SLOTS = SLOTS_;     // temp-stack slots kept in shared memory; results parked deeper are re-read from the arena
-  static constexpr int BD = BD_, CODEROW = BD_ / 2 + 4, XS = BD_ + 4, NWARP = BD_ / 32;
+  // CODEROW: BD / 2 code bytes per staged tip row + 16 (rows start 16-byte aligned for the bulk copies and fall into different banks)
+  static constexpr int BD = BD_, CODEROW = BD_ / 2 + 16, XS = BD_ + 4, NWARP = BD_ / 32;
   alignas(16) double Pcur[NMAX * 16];  // current P(t) of every branch; the root's slot holds pi in its first row (history sampling)
   union {  // buffers that are live in disjoint phases of an iteration share storage
     struct { alignas(16) double Pprop[NMAX * 16]; };  // rate steps: proposal P(t)
@@ -92,7 +93,8 @@ struct SmemT {
   uint16_t tk[BD_];   // pair-count pass: thread -> branch | word slice << 8 (trees with at most 128 branches)
   uint8_t flags[NMAX], fix[NMAX], dirty[NMAX], sel[NMAX], amb[NMAX];
   int8_t Z[NMAX], Znew[NMAX];
-  alignas(4) uint8_t codes[STAGE_ ? NI * CODEROW : 4];
+  unsigned long long mbar;  // mbarrier the bulk copies of the tip codes complete on
+  alignas(16) uint8_t codes[STAGE_ ? NI * CODEROW : 16];
 };
 
 __device__ __forceinline__ double class_rate(int z, double n_rate, double c_rate) { return z == 2 ? n_rate : (z == 0 ? 1.0 : c_rate); }
@@ -115,22 +117,54 @@ struct Arena {
   uint32_t sc_stride;
 };
 
-// stage the packed tip codes of patterns [pb, pb + 264) (pb a multiple of 8) into shared memory
+// ---- 1-D bulk copies global -> shared (the TMA engine: cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stage the packed 4-bit tip codes of patterns [pb, pb + BD) (pb a multiple of BD) into shared memory: one 1-D bulk copy per tip row
+// (cp.async.bulk: the rows of a tile are BD / 2 contiguous bytes of the blob, 16-byte aligned on both sides), all completing on one
+// mbarrier; `parity` is the barrier's phase, flipped by every staging.  Patterns beyond the element's last one are never read.
 template <class SM>
-__device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb, int n_rows, int tid) {
+__device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb, int n_rows, int tid, uint32_t& parity) {
   PA_LAYOUT_CONSTANTS(SM);
   if (!SM::STAGE) return;
   if (S.ivars[IV_STAGED] == pb) return;
-  __syncthreads();
+  __syncthreads();  // every reader of the previous tile is done
   const int half = ev.h->Ppad >> 1;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(ev.codes);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(S.codes);
-  for (int idx = tid; idx < n_rows * (kCodeRow / 4); idx += kBD) {
-    const int r = idx / (kCodeRow / 4), w = idx - r * (kCodeRow / 4);
-    const int byte = (pb >> 1) + 4 * w;
-    dst[r * (kCodeRow / 4) + w] = (byte < half) ? src[(r * half + byte) >> 2] : 0xffffffffu;
+  const int byte0 = pb >> 1;
+  const uint32_t row_bytes = (uint32_t)min(kBD / 2, half - byte0);
+  if (tid == 0) {
+    // reads of the old tile through the generic proxy are ordered before the async proxy overwrites it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&S.mbar, row_bytes * (uint32_t)n_rows);
+    for (int r = 0; r < n_rows; r++) bulk_g2s(S.codes + r * kCodeRow, ev.codes + (size_t)r * half + byte0, row_bytes, &S.mbar);
+    S.ivars[IV_STAGED] = pb;
   }
-  if (tid == 0) S.ivars[IV_STAGED] = pb;
+  mbar_wait(&S.mbar, parity);
+  parity ^= 1u;
   __syncthreads();
 }
 
@@ -250,12 +284,13 @@ __device__ __forceinline__ int build_pass_program(SM& S, const Arena& A, int Ppa
 // forwarded in registers when the next node of the pass is its parent, so the shared-memory stack only holds results
 // that wait for a sibling subtree.  Returns sum_p w_p log L_p.
 template <class SM>
-__device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, const Arena& A, int n_act, int n_rows, int tid) {
+__device__ __forceinline__ double prune_pass(const ElemView& ev, SM& S, const double* __restrict__ Pm, const Arena& A, int n_act, int n_rows, int tid,
+                                             uint32_t& stage_parity) {
   PA_LAYOUT_CONSTANTS(SM);
   const int P = ev.h->P, Ppad = ev.h->Ppad;
   double acc = 0.0;
   for (int p0 = 0; p0 < Ppad; p0 += kTile) {
-    ensure_staged(S, ev, p0, n_rows, tid);
+    ensure_staged(S, ev, p0, n_rows, tid, stage_parity);
     const int p = p0 + tid;
     if (p < P) {
       const uint8_t* __restrict__ cp = SM::STAGE ? (S.codes + (tid >> 1)) : (ev.codes + (p >> 1));
@@ -410,6 +445,11 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
   A.sc = reinterpret_cast<int16_t*>(A.part + 2 * (size_t)A.part_stride);
   A.sc_stride = (uint32_t)L.n_max * L.P_max;
   const int n_rows = L.S_rows;
+  if (SM::STAGE && tid == 0) {
+    mbar_init(&S.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t stage_parity = 0;  // phase of the staging mbarrier
 
   if (tid < 6) S.work[tid] = 0ull;
   if (tid < 10) S.phase[tid] = 0ll;
@@ -570,7 +610,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
     // initial upward pass over every pattern (Gibbs, bpp_c.cpp:355-356), partials stored in arena copy 0
     {
       const int n_act = make_pass<false>(S, A, Ppad, 0, n_su, tid);
-      const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid);
+      const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid, stage_parity);
       if (tid == 0) {
         S.scal[SC_LL] = ll;
         w_npu += (unsigned long long)n_act * h->P;
@@ -913,7 +953,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
       __syncthreads();
       if (S.ivars[IV_ANY_CHANGED]) {  // bpp_c.cpp:422-431 (recomputed partials overwrite the current copy in place)
         const int n_act = make_pass<true>(S, A, Ppad, 0, n_su, tid);
-        const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid);
+        const double ll = prune_pass(ev, S, S.Pcur, A, n_act, n_rows, tid, stage_parity);
         if (tid == 0) {
           S.scal[SC_LL] = ll;
           w_npu += (unsigned long long)n_act * h->P;
@@ -1036,7 +1076,7 @@ __global__ void __launch_bounds__(BD, MINB) chain_kernel(ChainLaunch L) {
           const double proposal = S.scal[SC_PROPOSAL];
           const long long tp0 = clock64();
           const int n_act = S.ivars[IV_NACT];
-          const double ll_new = prune_pass(ev, S, S.Pprop, A, n_act, n_rows, tid);  // log_f_Xz, into the non-current copy
+          const double ll_new = prune_pass(ev, S, S.Pprop, A, n_act, n_rows, tid, stage_parity);  // log_f_Xz, into the non-current copy
           if (tid == 0 && !neut) S.phase[8] += clock64() - tp0;  // the c-rate pruning pass alone (also included in the c_rate phase)
           if (warp == 0) {
             const int cnt_nodes = n_act;
