@@ -14,7 +14,8 @@ A "step" is one pass of the hot path over one resident batch: every element runs
 iterations on the device.
 value   = elements x 3 x 1500 / device time of the chain kernel, inputs resident in HBM (CUDA events on the launching stream);
 e2e     = the same count / wall time of the public C-ABI call sequence with HOST buffers, over the same K steps:
-          pa_engine_load_alignment (integer front-end + H2D) + pa_engine_run (chains + summaries + D2H);
+          pa_engine_load_alignment (integer front-end + H2D) + pa_engine_run (chains + summaries + D2H of one record per chain),
+          issued on two handles per GPU by two host threads so that the front-end of step k+1 overlaps the chains of step k;
 roofline: FP64 FMA (north_star) -- algorithmic FMA per SURVEY.md §8d from the engine's work counters over the FP64 FMA peak of this
           GPU measured live (MEASURED_PEAKS.json has no FP64 entry; the theoretical 148 SM x 64 DFMA/clk is printed beside it);
 cpu_baseline / --impl reference: the UNMODIFIED reference sources built against the compat shim (oracle/_ref/PhyloAcc-ST-ref) on all
@@ -365,14 +366,36 @@ def main():
     ms_step = float(np.mean(kern_ms))
     cnt = eng.collect() and eng.counters()
 
-    # ---- end to end through the C ABI with host buffers, over the same number of steps (front-end + H2D + chains + summaries + D2H)
+    # ---- end to end through the C ABI with host buffers, over the same number of steps (front-end + H2D + chains + summaries + D2H).
+    # Two handles per GPU, used alternately by two host threads: the integer front-end and upload of step k+1 (pa_engine_load_alignment
+    # on the second handle) overlap the chains of step k, as a caller with a queue of batches would arrange it.  Every step still makes
+    # both calls with host buffers; all of it is inside the timed region; the two handles' kernels share the GPU.
+    eng_b = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup,
+                              conserve=tree.conserve, device=local_rank)
+    stream_b = torch.cuda.Stream()
+    eng_b.set_stream(stream_b.cuda_stream)
+    engines = [eng, eng_b]
+    for e in engines:  # untimed: buffers of both handles allocated once
+        e.load_alignment(Xn, batch.elem_start, batch.elem_len)
+        e.run(ids)
+    last_res = [None, None]
+
+    def e2e_worker(slot):
+        torch.cuda.set_device(local_rank)
+        for k in range(slot, args.steps, 2):
+            engines[slot].load_alignment(Xn, batch.elem_start, batch.elem_len)
+            last_res[slot] = engines[slot].run(ids)
+
     barrier()
     t0 = time.time()
-    for _ in range(args.steps):
-        eng.load_alignment(Xn, batch.elem_start, batch.elem_len)
-        res = eng.run(ids)
+    workers = [threading.Thread(target=e2e_worker, args=(s,)) for s in range(2)]
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join()
     barrier()
     e2e_ms = (time.time() - t0) * 1e3 / args.steps
+    res = last_res[0] if last_res[0] is not None else last_res[1]
     stop.set()
     sampler.join(timeout=2)
     h2d = int(batch.X.nbytes)
@@ -394,17 +417,29 @@ def main():
         eng2 = eng if args.workload != "cfg3" else pab.Engine.create(tree2.parent, tree2.children, tree2.dist, tree2.pi, tree2.Q, params=prm,
                                                                       outgroup=tree2.outgroup, conserve=tree2.conserve, device=local_rank)
         wave = 8192
+        engs2 = [eng2, eng_b] if args.workload != "cfg3" else [eng2]
+        totals = [[0, 0] for _ in engs2]
+        waves = list(range(0, big.C, wave))
+
+        def full_worker(slot):
+            torch.cuda.set_device(local_rank)
+            for w0 in waves[slot::len(engs2)]:
+                w1 = min(big.C, w0 + wave)
+                g0, g1 = int(big.elem_start[w0]), int(big.elem_start[w1 - 1] + big.elem_len[w1 - 1])
+                Xw = np.ascontiguousarray(big.X[:, g0:g1])
+                engs2[slot].load_alignment(Xw, big.elem_start[w0:w1] - g0, big.elem_len[w0:w1])
+                r2 = engs2[slot].run(np.arange(w1 - w0, dtype=np.int32))
+                totals[slot][0] += int((r2.filtered == 0).sum())
+                totals[slot][1] += int(np.sum((r2.logBF1 > 5) & (r2.logBF2 > 5) & (r2.filtered == 0)))
+
         barrier()
         t0 = time.time()
-        n_full_active, n_full_acc = 0, 0
-        for w0 in range(0, big.C, wave):
-            w1 = min(big.C, w0 + wave)
-            g0, g1 = int(big.elem_start[w0]), int(big.elem_start[w1 - 1] + big.elem_len[w1 - 1])
-            Xw = np.ascontiguousarray(big.X[:, g0:g1])
-            eng2.load_alignment(Xw, big.elem_start[w0:w1] - g0, big.elem_len[w0:w1])
-            r2 = eng2.run(np.arange(w1 - w0, dtype=np.int32))
-            n_full_active += int((r2.filtered == 0).sum())
-            n_full_acc += int(np.sum((r2.logBF1 > 5) & (r2.logBF2 > 5) & (r2.filtered == 0)))
+        fw = [threading.Thread(target=full_worker, args=(s,)) for s in range(len(engs2))]
+        for w in fw:
+            w.start()
+        for w in fw:
+            w.join()
+        n_full_active, n_full_acc = sum(t[0] for t in totals), sum(t[1] for t in totals)
         barrier()
         full_s = time.time() - t0
         tf = torch.tensor([full_s], device="cuda", dtype=torch.float64)
@@ -473,7 +508,8 @@ def main():
                            "iterations_per_chain": T, "models": 3, "l2": "flushed between timed steps (256 MiB write)",
                            "parallelism": f"elements sharded over {world} GPU(s), no data-path collective, one all_gather of summaries"},
                 "roofline": roof,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.steps,
+                        "pipeline": "two handles per GPU on two host threads: front-end + upload of step k+1 overlap the chains of step k"},
                 "pruned_site_liks": {"value": site_liks, "unit": "full-tree-equivalent site likelihoods/s", "columns_per_pattern": compression},
                 "gpu_launches": int(cnt["kernel_launches"]) * args.steps,
                 "clocks": _clock_summary(clocks),
@@ -483,6 +519,7 @@ def main():
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_block(wl, tree, os.cpu_count() or 1)
         print(json.dumps(line))
+    eng_b.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

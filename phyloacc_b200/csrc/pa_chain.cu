@@ -156,6 +156,22 @@ __device__ __forceinline__ void ensure_staged(SM& S, const ElemView& ev, int pb,
   const int half = ev.h->Ppad >> 1;
   const int byte0 = pb >> 1;
   const uint32_t row_bytes = (uint32_t)min(kBD / 2, half - byte0);
+#ifdef PA_STAGE_LDG
+  // A/B variant (profiles/r2_kernel_experiments.txt): round 1's staging, a cooperative LDG -> STS loop
+  {
+    (void)parity;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ev.codes);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(S.codes);
+    const int wpr = (int)row_bytes / 4;
+    for (int idx = tid; idx < n_rows * wpr; idx += kBD) {
+      const int r = idx / wpr, w = idx - r * wpr;
+      dst[r * (kCodeRow / 4) + w] = src[(r * half + byte0) / 4 + w];
+    }
+    if (tid == 0) S.ivars[IV_STAGED] = pb;
+    __syncthreads();
+    return;
+  }
+#endif
   if (tid == 0) {
     // reads of the old tile through the generic proxy are ordered before the async proxy overwrites it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
