@@ -393,6 +393,7 @@ int Engine::sample(const int32_t* ids, int32_t n_ids, int model_mask, bool warm_
     SummaryLaunch SL;
     SL.blobs = d_blobs; SL.blob_off = d_blob_off; SL.chain_list = d_chain_list;
     SL.n_chains = n_chains; SL.T = T; SL.ZW = ZW; SL.num_burn = P.burnin; SL.num_mcmc = P.mcmc;
+    SL.n_max_pad = (n_max + 1) & ~1;
     SL.trace_d = d_trace_d; SL.trace_z = d_trace_z;
     SL.cprior_a = cp.cprior_a; SL.cprior_b = cp.cprior_b; SL.nprior_a = cp.nprior_a; SL.nprior_b = cp.nprior_b;
     SL.prior_l_a = cp.prior_l_a; SL.prior_l_b = cp.prior_l_b; SL.prior_l2_a = cp.prior_l2_a; SL.prior_l2_b = cp.prior_l2_b;

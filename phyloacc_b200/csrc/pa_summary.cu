@@ -25,6 +25,7 @@ namespace {
 constexpr int kBD = 256;
 constexpr int kCap = SUMMARY_MAX_CONFIGS;  // configurations the shared-memory table holds
 constexpr int kRowTile = 128;              // trace rows staged per step of the clustering
+constexpr int kTab = 2 * SUMMARY_MAX_CONFIGS;  // slots of the configuration hash table (power of two)
 
 __device__ __forceinline__ double lnbeta_dev(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
 
@@ -41,15 +42,29 @@ __device__ double radix_select(const double* __restrict__ x, int T, int k, int* 
       if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 0xffull)], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int acc = 0, b = 0;
-      for (; b < 256; b++) {
-        if (acc + hist[b] > k) break;
-        acc += hist[b];
+    if (tid < 32) {
+      // the bin where the running count passes k: every lane owns 8 consecutive bins, a warp prefix sum finds the lane, the lane its bin
+      int local[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) { local[j] = hist[tid * 8 + j]; sum += local[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
       }
-      k -= acc;
-      s_prefix[0] = prefix | ((unsigned long long)b << shift);
-      s_prefix[1] = (unsigned long long)k;
+      const int excl = incl - sum;
+      const unsigned hit = __ballot_sync(0xffffffffu, incl > k);
+      const int owner = __ffs(hit) - 1;  // T > k, so some lane's inclusive count exceeds k
+      if (tid == owner) {
+        int acc = excl, b = 0;
+        for (; b < 7; b++) {
+          if (acc + local[b] > k) break;
+          acc += local[b];
+        }
+        s_prefix[0] = prefix | ((unsigned long long)(tid * 8 + b) << shift);
+        s_prefix[1] = (unsigned long long)(k - acc);
+      }
     }
     __syncthreads();
     prefix = s_prefix[0];
@@ -95,6 +110,7 @@ __global__ void __launch_bounds__(kBD) summary_kernel(SummaryLaunch L) {
   double* s_rc = s_full + kRowTile;                                     // [kRowTile] c
   double* s_rn = s_rc + kRowTile;                                       // [kRowTile] n
   int* s_cnt = reinterpret_cast<int*>(s_rn + kRowTile);                 // [n][3] Z frequencies
+  uint16_t* s_tab = reinterpret_cast<uint16_t*>(s_cnt + (size_t)L.n_max_pad * 3);  // [kTab] configuration index + 1 by hash slot, 0 = empty
 
   const double lg_ca = lgamma(L.cprior_a), lg_na = lgamma(L.nprior_a);
   auto full_of = [&](int m) {  // trace_full_loglik (bpp_c.cpp:775-806); density first, then log, as the reference evaluates it
@@ -204,6 +220,16 @@ __global__ void __launch_bounds__(kBD) summary_kernel(SummaryLaunch L) {
       s_iv[0] = 1;  // configurations so far
     }
     for (int w = tid; w < ZW; w += kBD) s_cfg[w] = s_maxz[w];
+    for (int k = tid; k < kTab; k += kBD) s_tab[k] = 0;
+    __syncthreads();
+    if (warp == 0) {  // configuration 0 = Max_Z goes into the table under its own hash
+      uint32_t hv = 0u;
+      for (int w = lane; w < ZW; w += 32) hv ^= (s_maxz[w] & s_mask[w]) * (0x9E3779B1u * (2u * (uint32_t)w + 1u));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) hv ^= __shfl_xor_sync(0xffffffffu, hv, o);
+      hv ^= hv >> 15;
+      if (lane == 0) s_tab[hv & (uint32_t)(kTab - 1)] = 1;
+    }
     __syncthreads();
     for (int hi = T; hi > burn && !s_iv[1]; hi -= kRowTile) {
       const int lo = max(burn, hi - kRowTile), cnt = hi - lo;
@@ -219,16 +245,23 @@ __global__ void __launch_bounds__(kBD) summary_kernel(SummaryLaunch L) {
         int ncfg = s_iv[0];
         for (int r = cnt - 1; r >= 0; r--) {
           const uint32_t* row = s_rows + (size_t)r * ZW;
+          // look the row up by the hash of its uncertain nodes' states (open addressing, <= 50 % load): the cost of a row does not
+          // grow with the number of configurations; indices are still handed out in order of first appearance
+          uint32_t hv = 0u;
+          for (int w = lane; w < ZW; w += 32) hv ^= (row[w] & s_mask[w]) * (0x9E3779B1u * (2u * (uint32_t)w + 1u));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) hv ^= __shfl_xor_sync(0xffffffffu, hv, o);
+          hv ^= hv >> 15;
+          uint32_t slot = hv & (uint32_t)(kTab - 1);
           int j = -1;
-          for (int c0 = 0; c0 < ncfg && j < 0; c0 += 32) {
-            const int c = c0 + lane;
-            bool eq = c < ncfg;
-            if (eq) {
-              const uint32_t* cf = s_cfg + (size_t)c * ZW;
-              for (int w = 0; w < ZW; w++) eq = eq && (((row[w] ^ cf[w]) & s_mask[w]) == 0u);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, eq);
-            if (bal) j = c0 + __ffs(bal) - 1;
+          for (;;) {
+            const int idx = s_tab[slot];
+            if (idx == 0) break;
+            const uint32_t* cf = s_cfg + (size_t)(idx - 1) * ZW;
+            bool eq = true;
+            for (int w = lane; w < ZW; w += 32) eq = eq && (((row[w] ^ cf[w]) & s_mask[w]) == 0u);
+            if (__all_sync(0xffffffffu, eq)) { j = idx - 1; break; }
+            slot = (slot + 1u) & (uint32_t)(kTab - 1);
           }
           if (j < 0) {
             if (ncfg >= kCap) {  // more configurations than the table holds: the host summarises this chain
@@ -238,6 +271,7 @@ __global__ void __launch_bounds__(kBD) summary_kernel(SummaryLaunch L) {
             j = ncfg++;
             for (int w = lane; w < ZW; w += 32) s_cfg[(size_t)j * ZW + w] = row[w];
             if (lane == 0) {
+              s_tab[slot] = (uint16_t)(j + 1);
               s_num[j] = 0;
               s_first[j] = lo + r;
               for (int k = 0; k < 6; k++) s_acc[j * 6 + k] = 0.0;
@@ -368,7 +402,7 @@ static size_t summary_smem_bytes(int n_max, int ZW) {
   size_t b = (size_t)kBD * 8 + (size_t)kBD * 4 + 256 * 4 + 16;                       // red, redi, hist, prefix
   b += (size_t)kCap * 6 * 8 + (size_t)kCap * 4 * 2 + 8 * 4;                            // acc, num, first, iv
   b += (size_t)2 * ZW * 4 + (size_t)kCap * ZW * 4 + (size_t)kRowTile * ZW * 4 + 8;     // mask, maxz, cfg, rows
-  b += (size_t)3 * kRowTile * 8 + (size_t)n_max * 3 * 4;                               // full, c, n, cnt
+  b += (size_t)3 * kRowTile * 8 + (size_t)n_max * 3 * 4 + (size_t)kTab * 2 + 16;       // full, c, n, cnt, hash table
   return (b + 63) & ~size_t(63);
 }
 

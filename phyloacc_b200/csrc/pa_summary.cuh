@@ -26,6 +26,7 @@ struct SummaryLaunch {
   const uint8_t* blobs; const int64_t* blob_off;
   const int32_t* chain_list;  // [n_chains][2] element, model
   int n_chains, T, ZW, num_burn, num_mcmc;
+  int n_max_pad;  // rows of the per-node count table in shared memory (n_max rounded up to an even number)
   const double* trace_d; const uint32_t* trace_z;
   double cprior_a, cprior_b, nprior_a, nprior_b;
   double prior_l_a, prior_l_b, prior_l2_a, prior_l2_b, prior_g_a, prior_g_b;
