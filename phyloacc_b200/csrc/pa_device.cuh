@@ -24,7 +24,12 @@ __device__ __forceinline__ uint4 philox4(uint32_t seed, uint32_t key, uint32_t i
   return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ double u01(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
+// (w + 0.5) * 2^-32, exactly: the 32 random bits become the top of the mantissa of a double in [1, 2), and 1 - 2^-33 is subtracted (both
+// operands and the difference have at most 33 significant bits, so the one DADD is exact and the value equals the oracle's
+// ((double)w + 0.5) * 2^-32).  Replaces an integer-to-double conversion, an add and a multiply per draw.
+__device__ __forceinline__ double u01(uint32_t w) {
+  return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20)) - 0.99999999988358467817306518554688;
+}
 
 __device__ __forceinline__ uint32_t pick(const uint4& w, int k) { return k == 0 ? w.x : (k == 1 ? w.y : (k == 2 ? w.z : w.w)); }
 

@@ -247,3 +247,23 @@ def test_element_image_tip_planes_follow_codes_and_site_order(native_lib):
                     n_amb += 1
     assert n_amb > 10
     eng.close()
+
+
+def test_drop_in_binary_fails_loudly_without_a_gpu(native_lib, tmp_path):
+    """There is no CPU fallback anywhere in the product: with a valid parameter file and no CUDA device the binary parses everything,
+    then stops with exit code 1 and says why (the driver's log shows it); with no arguments it still answers the driver's probe."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from phyloacc_b200 import synth
+
+    tree = synth.make_tree(S=8, seed=5, n_out=2, n_target=2)
+    batch = synth.simulate(tree, C=3, length=80, seed=11)
+    cfg = synth.write_files(batch, str(tmp_path), prefix="sim", params=dict(BURNIN=5, MCMC=10))
+    r = subprocess.run([pab.BIN_PATH, cfg], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1
+    assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+    assert not any(f.endswith("_elem_lik.txt") for f in os.listdir(tmp_path / "out"))
