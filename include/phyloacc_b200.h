@@ -204,6 +204,14 @@ int pa_device_fp64_peak(int device, int millis, double* tflops_out);
 int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const double* sel, const double* bias, const double* t, double* rate_out,
                        double* P_out);
 
+/* PhyloAcc-ST-GBGC groundwork: replayed log-likelihoods under the GC-biased model.  For each state i: element elem[i], latent class Z
+ * ([n_states][N], original node numbering) and gBGC indicator B ([n_states][N], 0 / 1) per branch, selection coefficients of the
+ * accelerated / conserved classes, the element's gBGC bias.  Every branch gets exp(t * Q o f(s + b B)) with s = 0 / sel_c / sel_n by class
+ * and b = gbc on the branches with B = 1 -- the six rate matrices of BPP_C::initMCMC and init_cache_TM (GBGC/SRC/bpp_c.cpp:196-204,
+ * 1563-1621) -- and the upward pass of Update_Tg(., ., ., false) (:477-528); result = sum over columns of log sum_b pi_b L_root(b). */
+int pa_engine_gbgc_replay(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n,
+                          const double* sel_c, const double* gbc, double* loglik_out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

@@ -63,6 +63,44 @@ def transition_uniformised(Q0: np.ndarray, s: float, b: float, t: float) -> np.n
     return P
 
 
+def replay_loglik(Q0, pi, el, Z, B, sel_c, sel_n, gbc, uniformised=False):
+    """Replayed log-likelihood of one element under the GC-biased model: per-branch P(t) from the six rate matrices of
+    BPP_C::initMCMC (GBGC/SRC/bpp_c.cpp:196-204: class 0 / 1 / 2 -> s = 0 / sel_c / sel_n, B -> bias gbc) through init_cache_TM
+    (:1563-1621), the upward pass Update_Tg(g, ., ., false) (:477-528) column by column, sum_g log sum_b pi_b L_root(b).
+    `el` is the oracle's element front-end (oracle/frontend.py: masks [GG][S], nodes, children2, distances2, missing)."""
+    N = len(Z)
+    P = {}
+    for s in el.nodes:
+        if s == el.root:
+            continue
+        sel = sel_n if Z[s] == 2 else (0.0 if Z[s] == 0 else sel_c)
+        bias = gbc if B[s] else 0.0
+        if uniformised:
+            P[s] = transition_uniformised(Q0, sel, bias, float(el.distances2[s]))
+        else:
+            with np.errstate(over="ignore"):
+                P[s] = np.exp(log_transition(Q0, sel, bias, float(el.distances2[s]))).T  # [i, j] = P(i -> j)
+    S = el.masks.shape[1]
+    total = 0.0
+    for g in range(el.masks.shape[0]):
+        L = {}
+        for s in el.nodes:
+            if s < S:
+                m = int(el.masks[g, s])
+                L[s] = np.array([(m >> b) & 1 for b in range(4)], dtype=np.float64)
+                continue
+            if el.missing[s]:
+                continue
+            v = np.ones(4)
+            for ch in el.children2[s]:
+                if ch < 0 or el.missing[ch]:
+                    continue
+                v = v * (P[ch] @ L[ch])
+            L[s] = v
+        total += np.log(float(np.dot(pi, L[el.root])))
+    return total
+
+
 def parse_probe(text: str):
     out, cur = [], None
     Q0 = None
@@ -80,3 +118,8 @@ def parse_probe(text: str):
         elif f[0] == "logtm":
             cur["logtm"] = np.array([float.fromhex(x) for x in f[1:]]).reshape(4, 4)
     return Q0, out
+
+
+def parse_logliks(text: str):
+    """Replayed log-likelihoods of the `state` commands, in script order."""
+    return [float.fromhex(line.split()[1]) for line in text.split("\n") if line.startswith("loglik ")]

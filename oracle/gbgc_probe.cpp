@@ -4,10 +4,13 @@
 // dumps, as hex floats, what the GC-biased model computes for a branch:
 //   * BPP_C::getRate(Q0, s, b)           Q o f(s + b B), rows renormalised            (GBGC/SRC/bpp_c.cpp:13-30)
 //   * BPP_C::getTransition(node, s, b)   log P(t)^T from the eigensystem of that Q    (GBGC/SRC/bpp_c.cpp:1405-1427)
-// for the grid of (node, selection, bias) triples in the script.  It pins oracle/gbgc.py and the CUDA kernel behind
-// pa_gbgc_transition (phyloacc_b200/csrc/pa_gbgc.cu).
+// for the grid of (node, selection, bias) triples in the script, and
+//   * replayed log-likelihoods of an element for a given state (Z, B per branch; conserved / accelerated selection coefficients;
+//     the element's gBGC bias): the six rate matrices of initMCMC (GBGC/SRC/bpp_c.cpp:196-204), init_cache_TM (:1563-1621), the
+//     upward pass Update_Tg(g, ., ., false) (:477-528) and sum_g log_exp_sum(lambda[g][root]).
+// It pins oracle/gbgc.py and the CUDA kernels behind pa_gbgc_transition / pa_engine_gbgc_replay (phyloacc_b200/csrc/pa_gbgc.cu).
 //
-// usage: gbgc_probe <cfg> <script>     script lines: "tm <node> <sel> <bias>"
+// usage: gbgc_probe <cfg> <script>     script lines: "tm <node> <sel> <bias>", "element <c>", "state <sel_c> <sel_n> <gbc> Z[N] B[N]"
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -57,7 +60,8 @@ int main(int argc, char** argv) {
   bpp.InitMCMC(20, 40, 10);
   bool filter = false;
   string gc = get("GAPCHAR", "*");
-  BPP_C el(0, profile, bpp, gc[0], 0.8, filter, false);
+  BPP_C* elp = new BPP_C(0, profile, bpp, gc[0], 0.8, filter, false);
+#define el (*elp)
   fflush(stdout);
   dup2(fileno(real_stdout), fileno(stdout));
   printf("gbgc N %d filter %d\n", bpp.N, (int)filter);
@@ -82,6 +86,38 @@ int main(int argc, char** argv) {
       printf("\nlogtm");
       for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) printf(" %a", L(i, j));  // (child, parent) layout like the ST caches
       printf("\n");
+    } else if (cmd == "element") {
+      int c; ss >> c;
+      delete elp;
+      filter = false;
+      elp = new BPP_C(c, profile, bpp, gc[0], 0.8, filter, false);
+      printf("element %d filter %d GG %d root %d nodes %d\n", c, (int)filter, filter ? 0 : el.GG, filter ? -1 : el.root, filter ? 0 : (int)el.nodes.size());
+    } else if (cmd == "state") {
+      if (filter) { printf("state skipped\n"); continue; }
+      double sc, sn, gb;
+      ss >> sc >> sn >> gb;
+      const int N = bpp.N;
+      el.initMCMC(0, bpp, 1);
+      for (int s = 0; s < N; s++) { int z; ss >> z; el.Z[s] = z; }
+      for (int s = 0; s < N; s++) { int b; ss >> b; el.isGB[s] = (b != 0); }
+      for (int s = 0; s < N; s++) el.fixZ[s] = -1;  // init_cache_TM skips the accelerated tables where fixZ == 1
+      vector<mat> Qs(6);
+      Qs[0] = bpp.submat;
+      Qs[1] = el.getRate(bpp.submat, sc, 0);
+      Qs[2] = el.getRate(bpp.submat, sn, 0);
+      Qs[3] = el.getRate(bpp.submat, 0, gb);
+      Qs[4] = el.getRate(bpp.submat, sc, gb);
+      Qs[5] = el.getRate(bpp.submat, sn, gb);
+      el.init_cache_TM(Qs);
+      for (int s = bpp.S; s < N; s++)
+        for (int g = 0; g < el.GG; g++) el.lambda[g][s].fill(0);
+      vector<bool> visited(N, false);
+      double ll = 0;
+      for (int g = 0; g < el.GG; g++) {
+        el.Update_Tg(g, visited, bpp, false);
+        ll += BPP::log_exp_sum(el.lambda[g][el.root]);
+      }
+      printf("loglik %a\n", ll);
     }
   }
   cout.rdbuf(old_cout);

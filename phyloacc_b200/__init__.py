@@ -94,7 +94,7 @@ EXPORTS = [
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
-    "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition",
+    "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay",
 ]
 
 _lib = None
@@ -151,6 +151,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
     lib.pa_run_from_config.argtypes = [C.c_char_p]
     lib.pa_device_fp64_peak.argtypes = [C.c_int, C.c_int, _f64p]
+    lib.pa_engine_gbgc_replay.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _f64p, _f64p, _f64p, _f64p]
     lib.pa_gbgc_transition.argtypes = [C.c_int, C.POINTER(PaSubst), C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p]
     _lib = lib
     return lib
@@ -401,6 +402,18 @@ class Engine:
     def run(self, ids) -> Results:
         self.sample(ids)
         return self.collect()
+
+    def gbgc_replay(self, elem, Z, B, sel_n, sel_c, gbc) -> np.ndarray:
+        """PhyloAcc-ST-GBGC groundwork: replayed log-likelihoods under the GC-biased model (see pa_engine_gbgc_replay)."""
+        elem = np.ascontiguousarray(elem, dtype=np.int32)
+        Z = np.ascontiguousarray(Z, dtype=np.int8).reshape(len(elem), self.N)
+        B = np.ascontiguousarray(B, dtype=np.int8).reshape(len(elem), self.N)
+        sel_n, sel_c, gbc = (np.ascontiguousarray(x, dtype=np.float64) for x in (sel_n, sel_c, gbc))
+        out = np.zeros(len(elem))
+        _check(self._lib.pa_engine_gbgc_replay(self._h, len(elem), elem.ctypes.data_as(_i32p), Z.ctypes.data_as(_i8p), B.ctypes.data_as(_i8p),
+                                               sel_n.ctypes.data_as(_f64p), sel_c.ctypes.data_as(_f64p), gbc.ctypes.data_as(_f64p),
+                                               out.ctypes.data_as(_f64p)))
+        return out
 
     def trace(self, i: int, model: int):
         p = self.params()

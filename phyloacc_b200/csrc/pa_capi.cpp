@@ -233,6 +233,15 @@ int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const doubl
   return guarded([&]() { return pa::gbgc_transition(device, subst->Q, n, sel, bias, t, rate_out, P_out); });
 }
 
+int pa_engine_gbgc_replay(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n,
+                          const double* sel_c, const double* gbc, double* loglik_out) {
+  if (!e || (n_states > 0 && (!elem || !Z || !B || !sel_n || !sel_c || !gbc || !loglik_out))) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.gbgc_replay(n_states, elem, Z, B, sel_n, sel_c, gbc, loglik_out); });
+}
+
 int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
   if (!e || !out10) return PA_ERR_ARG;
   for (int k = 0; k < 10; k++) out10[k] = e->eng.phase_cycles[k];

@@ -16,6 +16,7 @@
 #include "pa_chain.cuh"
 #include "pa_device.cuh"
 #include "pa_engine.h"
+#include "pa_gbgc.cuh"
 #include "pa_internal.h"
 #include "pa_nvtx.h"
 
@@ -33,10 +34,16 @@ namespace pa {
 // ------------------------------------------------------------------------------------------ replay kernel
 // One CTA per (element, Z, n_rate, c_rate) state: builds P(t) for every branch from its class, prunes every
 // pattern with the shared-memory temp stack only (no global partials) and reduces sum_p w_p log L_p.
+// GBGC = true: the GC-biased model of PhyloAcc-ST-GBGC (groundwork).  n_rate / c_rate are then the accelerated / conserved
+// SELECTION COEFFICIENTS, `Bflag` says per branch whether gBGC acts on it, `gbc` is the element's bias, and every branch's P(t) is
+// exp(t * Q o f(s + b B)) (BPP_C::initMCMC's six rate matrices + init_cache_TM, GBGC/SRC/bpp_c.cpp:196-204,1563-1621) by uniformisation.
+struct Q16 { double q[16]; };
+template <bool GBGC>
 __global__ void __launch_bounds__(128) replay_kernel(const uint8_t* __restrict__ blobs, const int64_t* __restrict__ blob_off, SubstDev sd,
                                                       int n_states, const int32_t* __restrict__ elem, const int8_t* __restrict__ Z,
                                                       const double* __restrict__ n_rate, const double* __restrict__ c_rate, int N, int n_max,
-                                                      int slots_max, double* __restrict__ out) {
+                                                      int slots_max, double* __restrict__ out, const int8_t* __restrict__ Bflag,
+                                                      const double* __restrict__ gbc, Q16 Q0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int BD = blockDim.x, tid = threadIdx.x;
   const int st = blockIdx.x;
@@ -71,9 +78,17 @@ __global__ void __launch_bounds__(128) replay_kernel(const uint8_t* __restrict__
     s_slot[i] = ev.slot[i];
     // P(t) of the branch above node i for its class (initMCMC, bpp_c.cpp:187-228; Update_Tg bpp_c.cpp:661-663)
     const int z = Z[(size_t)st * N + ev.orig[i]];
-    const double rate = (z == 2) ? n_rate[st] : (z == 0 ? 1.0 : c_rate[st]);
     double P16[16];
-    build_P(sd, ev.dist[i], rate, true, P16);
+    if (GBGC) {
+      const double sel = (z == 2) ? n_rate[st] : (z == 0 ? 0.0 : c_rate[st]);
+      const double bias = Bflag[(size_t)st * N + ev.orig[i]] ? gbc[st] : 0.0;
+      double Q[16];
+      gbgc_rate(Q0.q, sel, bias, Q);
+      expm_uniformised(Q, ev.dist[i], P16);
+    } else {
+      const double rate = (z == 2) ? n_rate[st] : (z == 0 ? 1.0 : c_rate[st]);
+      build_P(sd, ev.dist[i], rate, true, P16);
+    }
 #pragma unroll
     for (int k = 0; k < 16; k++) Pm[i * 16 + k] = P16[k];
   }
@@ -309,8 +324,70 @@ int Engine::loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z
     set_error("tree too large for the replay kernel's shared memory");
     return PA_ERR_LIMIT;
   }
-  PA_CUDA(cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  replay_kernel<<<n_states, BD, smem, stream>>>(d_blobs, d_blob_off, model.subst_dev, n_states, d_elem, d_Z, d_n, d_c, N, n_max, slots_max, d_out);
+  PA_CUDA(cudaFuncSetAttribute(replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  replay_kernel<false><<<n_states, BD, smem, stream>>>(d_blobs, d_blob_off, model.subst_dev, n_states, d_elem, d_Z, d_n, d_c, N, n_max, slots_max, d_out,
+                                                       nullptr, nullptr, Q16{});
+  PA_CUDA(cudaGetLastError());
+  PA_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_states, cudaMemcpyDeviceToHost, stream));
+  PA_CUDA(cudaStreamSynchronize(stream));
+  return PA_OK;
+}
+
+// PhyloAcc-ST-GBGC groundwork: replayed log-likelihoods under the GC-biased model for states (Z, B per branch, selection coefficients of
+// the conserved / accelerated classes, gBGC bias); same pruning as loglik_replay, per-branch P(t) from exp(t * Q o f(s + b B))
+int Engine::gbgc_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n, const double* sel_c,
+                        const double* gbc, double* out) {
+  if (!loaded) {
+    set_error("pa_engine_gbgc_replay called before pa_engine_load_alignment");
+    return PA_ERR_STATE;
+  }
+  if (device < 0) {
+    set_error("no CUDA device bound to this engine (there is no CPU fallback)");
+    return PA_ERR_CUDA;
+  }
+  if (n_states <= 0) return PA_OK;
+  const int N = model.tree.N;
+  for (int i = 0; i < n_states; i++)
+    if (elem[i] < 0 || elem[i] >= (int)plans.size()) {
+      set_error("element id out of range");
+      return PA_ERR_ARG;
+    }
+  PA_CUDA(cudaSetDevice(device));
+  const size_t ns = (size_t)n_states;
+  const size_t off_n = 0, off_c = 8 * ns, off_g = 16 * ns, off_out = 24 * ns, off_elem = 32 * ns, off_Z = off_elem + ((4 * ns + 15) & ~size_t(15)),
+               off_B = off_Z + ((ns * N + 15) & ~size_t(15));
+  const size_t need = off_B + ns * N;
+  if (need > cap_replay || !d_replay) {
+    if (d_replay) cudaFree(d_replay);
+    d_replay = nullptr;
+    cap_replay = 0;
+    PA_CUDA(cudaMalloc(&d_replay, need));
+    cap_replay = need;
+  }
+  double* d_n = reinterpret_cast<double*>(d_replay + off_n);
+  double* d_c = reinterpret_cast<double*>(d_replay + off_c);
+  double* d_g = reinterpret_cast<double*>(d_replay + off_g);
+  double* d_out = reinterpret_cast<double*>(d_replay + off_out);
+  int32_t* d_elem = reinterpret_cast<int32_t*>(d_replay + off_elem);
+  int8_t* d_Z = reinterpret_cast<int8_t*>(d_replay + off_Z);
+  int8_t* d_B = reinterpret_cast<int8_t*>(d_replay + off_B);
+  PA_CUDA(cudaMemcpyAsync(d_elem, elem, sizeof(int32_t) * n_states, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_Z, Z, ns * N, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_B, B, ns * N, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_n, sel_n, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_c, sel_c, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
+  PA_CUDA(cudaMemcpyAsync(d_g, gbc, sizeof(double) * n_states, cudaMemcpyHostToDevice, stream));
+  const int BD = 128;
+  const size_t smem = replay_smem_bytes(n_max, slots_max, BD);
+  if ((int)smem > smem_optin) {
+    set_error("tree too large for the replay kernel's shared memory");
+    return PA_ERR_LIMIT;
+  }
+  Q16 Q0;
+  for (int k = 0; k < 16; k++) Q0.q[k] = model.tree.Q[k];
+  PA_CUDA(cudaFuncSetAttribute(replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  replay_kernel<true><<<n_states, BD, smem, stream>>>(d_blobs, d_blob_off, model.subst_dev, n_states, d_elem, d_Z, d_n, d_c, N, n_max, slots_max, d_out,
+                                                      d_B, d_g, Q0);
   PA_CUDA(cudaGetLastError());
   PA_CUDA(cudaMemcpyAsync(out, d_out, sizeof(double) * n_states, cudaMemcpyDeviceToHost, stream));
   PA_CUDA(cudaStreamSynchronize(stream));

@@ -86,6 +86,8 @@ struct Engine {
   // batch -- it keys the element's random streams, so a chain draws the same numbers whichever GPU runs it
   int load_alignment(const uint8_t* X, int64_t G, int32_t C, const int64_t* elem_start, const int32_t* elem_len, const int32_t* global_ids = nullptr);
   int loglik_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const double* n_rate, const double* c_rate, double* out);
+  int gbgc_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n, const double* sel_c, const double* gbc,
+                  double* out);
   int sample(const int32_t* ids, int32_t n_ids, int model_mask = 7, bool warm_start = false, int chain_iter = 0);
   int sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);
   int hyper_sums(const int32_t* ids, int32_t n_ids, double* sums /* [PA_HYPER_NSUMS] */);

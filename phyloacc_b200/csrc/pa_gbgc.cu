@@ -9,43 +9,12 @@
 // reference's is, and nothing depends on the spectrum being real.  fp64 throughout; about 1.5 k FMA per matrix.
 #include <cuda_runtime.h>
 
+#include "pa_gbgc.cuh"
 #include "pa_internal.h"
 
 namespace pa {
 
 namespace {
-
-__device__ __forceinline__ void matmul4(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ c) {
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) c[i * 4 + j] = ((a[i * 4] * b[j] + a[i * 4 + 1] * b[4 + j]) + a[i * 4 + 2] * b[8 + j]) + a[i * 4 + 3] * b[12 + j];
-}
-
-// Q' of BPP_C::getRate, same expression order: off-diagonals scaled, then the row sums of the WHOLE matrix subtracted from the diagonal
-__device__ __forceinline__ void gbgc_rate(const double* __restrict__ Q0, double s, double b, double* __restrict__ Q) {
-  if (s == 0.0 && b == 0.0) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) Q[k] = Q0[k];
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const bool si = (i == 1 || i == 2);  // strong bases C, G
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const bool sj = (j == 1 || j == 2);
-      const double B = s + ((!si && sj) ? b : ((si && !sj) ? -b : 0.0));
-      const double f = (B == 0.0) ? 1.0 : B / (1.0 - exp(-B));
-      Q[i * 4 + j] = Q0[i * 4 + j] * f;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const double c = ((Q[i * 4] + Q[i * 4 + 1]) + Q[i * 4 + 2]) + Q[i * 4 + 3];
-    Q[i * 4 + i] -= c;
-  }
-}
 
 __global__ void __launch_bounds__(128) gbgc_transition_kernel(const double* __restrict__ Q0g, int n, const double* __restrict__ sel, const double* __restrict__ bias,
                                                              const double* __restrict__ t, double* __restrict__ rate_out, double* __restrict__ P_out) {
@@ -58,34 +27,8 @@ __global__ void __launch_bounds__(128) gbgc_transition_kernel(const double* __re
   if (rate_out)
 #pragma unroll
     for (int k = 0; k < 16; k++) rate_out[(size_t)idx * 16 + k] = Q[k];
-  const double tt = t[idx];
-  double mu = fmax(fmax(-Q[0], -Q[5]), fmax(-Q[10], -Q[15]));
   double P[16];
-  if (!(mu > 0.0) || !(tt > 0.0)) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) P[k] = ((k >> 2) == (k & 3)) ? 1.0 : 0.0;
-  } else {
-    int ksq = 0;
-    double x = mu * tt;
-    while (x > 0.5 && ksq < 60) { x *= 0.5; ksq++; }
-    double A[16], term[16], nxt[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) A[k] = Q[k] / mu + (((k >> 2) == (k & 3)) ? 1.0 : 0.0);
-    const double e = exp(-x);
-#pragma unroll
-    for (int k = 0; k < 16; k++) { term[k] = ((k >> 2) == (k & 3)) ? e : 0.0; P[k] = term[k]; }
-    for (int j = 1; j < 20; j++) {  // x <= 1/2: the Poisson tail beyond 19 terms is below 1e-24
-      matmul4(term, A, nxt);
-      const double w = x / j;
-#pragma unroll
-      for (int k = 0; k < 16; k++) { term[k] = nxt[k] * w; P[k] += term[k]; }
-    }
-    for (int q = 0; q < ksq; q++) {
-      matmul4(P, P, nxt);
-#pragma unroll
-      for (int k = 0; k < 16; k++) P[k] = nxt[k];
-    }
-  }
+  expm_uniformised(Q, t[idx], P);
 #pragma unroll
   for (int k = 0; k < 16; k++) P_out[(size_t)idx * 16 + k] = P[k];
 }

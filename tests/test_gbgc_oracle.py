@@ -66,3 +66,54 @@ def test_cuda_gbgc_transition_matches_reference(native_lib):
     _, P = pab.gbgc_transition(Q0, sel, bias, t)
     assert np.all(P >= 0) and np.allclose(P.sum(axis=2), 1.0, rtol=0, atol=1e-10)  # up to ~14 squarings for the 500-unit branches
     assert np.allclose(P[:100, 0], P[:100, 3], rtol=1e-9)  # every starting base forgotten after 500 substitutions per site
+
+
+def _replay_case():
+    import json
+
+    from tests._util import Case
+
+    case = Case("gbgc43")
+    gdir = os.path.dirname(GOLD)
+    with open(os.path.join(gdir, "requests.json")) as f:
+        reqs = json.load(f)
+    with open(GOLD) as f:
+        want = gbgc.parse_logliks(f.read())
+    assert len(reqs) == len(want) == 24
+    return case, reqs, want
+
+
+def test_replayed_gbgc_likelihoods_match_reference():
+    """oracle/gbgc.py: replay_loglik against the reference's init_cache_TM + Update_Tg on 24 (element, Z, B, rates) states."""
+    case, reqs, want = _replay_case()
+    Q0, _ = _load()
+    for k, (r, w) in enumerate(zip(reqs, want)):
+        if k % 3:  # every third state through the eigen route (slow in numpy), all through the uniformised one below
+            continue
+        got = gbgc.replay_loglik(Q0, np.asarray(case.tree.pi), case.element(r["c"]), r["Z"], r["B"], r["sel_c"], r["sel_n"], r["gbc"])
+        assert abs(got - w) <= 1e-10 * abs(w), (k, got, w)
+    for k, (r, w) in enumerate(zip(reqs, want)):
+        got = gbgc.replay_loglik(Q0, np.asarray(case.tree.pi), case.element(r["c"]), r["Z"], r["B"], r["sel_c"], r["sel_n"], r["gbc"], uniformised=True)
+        assert abs(got - w) <= 1e-10 * abs(w), (k, got, w)
+    case.close()
+
+
+@pytest.mark.gpu
+def test_cuda_gbgc_replay_matches_reference(native_lib):
+    """pa_engine_gbgc_replay (replay_kernel<GBGC>: per-branch exp(t Q o f(s + b B)) by uniformisation, fp64 pruning over compressed site
+    patterns) against the reference's replayed log-likelihoods: 1e-10 relative (north_star's tolerance for replayed likelihoods)."""
+    import phyloacc_b200 as pab
+
+    case, reqs, want = _replay_case()
+    eng = pab.Engine.from_config(case.cfg, device=0)
+    got = eng.gbgc_replay([r["c"] for r in reqs], [r["Z"] for r in reqs], [r["B"] for r in reqs], [r["sel_n"] for r in reqs],
+                          [r["sel_c"] for r in reqs], [r["gbc"] for r in reqs])
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert abs(g - w) <= 1e-10 * abs(w), (k, g, w)
+    # B = 0 everywhere and zero selection is the ST model at rates 1: the GBGC replay must agree with the ST replay kernel
+    Z = np.zeros((1, eng.N), dtype=np.int8)
+    a = eng.gbgc_replay([0], Z, Z, [0.0], [0.0], [0.0])[0]
+    b = eng.loglik_replay([0], Z, [1.0], [1.0])[0]
+    assert abs(a - b) <= 1e-10 * abs(b)
+    eng.close()
+    case.close()
