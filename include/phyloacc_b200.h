@@ -212,6 +212,20 @@ int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const doubl
 int pa_engine_gbgc_replay(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n,
                           const double* sel_c, const double* gbc, double* loglik_out);
 
+/* PhyloAcc-ST-GBGC groundwork: the random-number-free half of one GBGC iteration at given states -- expected (child base, parent base)
+ * pairs per branch (Update_Tg(g,.,.,true), GBGC/SRC/bpp_c.cpp:530-583), the six (Z, B) emissions of every branch, the 6-state upward messages
+ * and the ELBO term (initial_prob_back, GBGC/SRC/bpp_c2.cpp:354-407).  fixZ is the model's constraint per node (1: class 2 forbidden), as
+ * BPP_C::initMCMC sets it (GBGC/SRC/bpp_c.cpp:145-180).  post_out [n_states][N][16] (row: child base, column: parent base), emis_out
+ * [n_states][N][6] (class k = Z + 3 B), root_out [n_states][8]: log_prob_back[root][0..5], the ELBO term, the upward log-likelihood. */
+typedef struct pa_gbgc_consts {
+  double grate, lrate;              /* PREP_GRATE, PREP_LRATE: the 3 x 3 transition matrix of Z (GBGC/SRC/bpp.hpp:286-293) */
+  double prior_gb;                  /* nGBprior_c: prior probability that gBGC acts on a branch */
+  double cons_to_mis, ncons_to_mis; /* CONSTOMIS and its non-conserved counterpart */
+} pa_gbgc_consts;
+int pa_engine_gbgc_integrate(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ,
+                             const double* sel_n, const double* sel_c, const double* gbc, const pa_gbgc_consts* consts, double* post_out,
+                             double* emis_out, double* root_out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

@@ -118,6 +118,59 @@ int main(int argc, char** argv) {
         ll += BPP::log_exp_sum(el.lambda[g][el.root]);
       }
       printf("loglik %a\n", ll);
+    } else if (cmd == "integ") {
+      // integ <resZ> <sel_c> <sel_n> <gbc> Z[N] B[N]: the evaluations of one Gibbs iteration that do not involve random numbers, at a given
+      // state -- expected parent / child base pairs per branch (Update_Tg(g, ., ., true), GBGC/SRC/bpp_c.cpp:530-583), the six
+      // (Z, B) emissions of every branch, the 6-state upward messages and the ELBO term (initial_prob_back, bpp_c2.cpp:354-407).
+      // The model's own fixZ is kept (resZ); where it forbids class 2 the requested Z is lowered to 1 (printed back).
+      if (filter) { printf("integ skipped\n"); continue; }
+      int resZ; double sc, sn, gb;
+      ss >> resZ >> sc >> sn >> gb;
+      const int N = bpp.N;
+      vector<int> Zin(N), Bin(N);
+      for (int s = 0; s < N; s++) ss >> Zin[s];
+      for (int s = 0; s < N; s++) ss >> Bin[s];
+      el.initMCMC(0, bpp, resZ);
+      for (int s = 0; s < N; s++) {
+        if (el.fixZ[s] == 1 && Zin[s] == 2) Zin[s] = 1;
+        el.Z[s] = Zin[s];
+        el.isGB[s] = (Bin[s] != 0);
+      }
+      vector<mat> Qs(6);
+      Qs[0] = bpp.submat;
+      Qs[1] = el.getRate(bpp.submat, sc, 0);
+      Qs[2] = el.getRate(bpp.submat, sn, 0);
+      Qs[3] = el.getRate(bpp.submat, 0, gb);
+      Qs[4] = el.getRate(bpp.submat, sc, gb);
+      Qs[5] = el.getRate(bpp.submat, sn, gb);
+      el.init_cache_TM(Qs);
+      for (int s = bpp.S; s < N; s++)
+        for (int g = 0; g < el.GG; g++) el.lambda[g][s].fill(0);
+      vector<bool> visited(N, false);
+      for (int g = 0; g < el.GG; g++) el.Update_Tg(g, visited, bpp, false);
+      for (size_t k = 0; k < el.nodes.size(); k++) el.posterior_Tg_next[el.nodes[k]].fill(0);
+      for (int g = 0; g < el.GG; g++) el.Update_Tg(g, visited, bpp, true);
+      el.posterior_Tg = el.posterior_Tg_next;
+      const double elbo = el.initial_prob_back(bpp);
+      printf("integ %d elbo %a loglik %a\n", resZ, elbo, el.log_prob_back[el.root][0]);
+      printf("Zused");
+      for (int s = 0; s < N; s++) printf(" %d", el.Z[s]);
+      printf("\nfixZ");
+      for (int s = 0; s < N; s++) printf(" %d", el.fixZ[s]);
+      printf("\n");
+      for (size_t k = 0; k + 1 < el.nodes.size(); k++) {
+        const int s = el.nodes[k];
+        printf("post %d", s);
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) printf(" %a", el.posterior_Tg[s](i, j));  // row: child base, column: parent base
+        printf("\nemis %d", s);
+        for (int i = 0; i < 6; i++) printf(" %a", el.log_emission[s][i]);
+        printf("\ntmint %d", s);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) printf(" %a", el.log_TM_Int[s](i, j));
+        printf("\n");
+      }
+      printf("rootback");
+      for (int i = 0; i < 6; i++) printf(" %a", el.log_prob_back[el.root][i]);
+      printf("\nconsts %a %a %a\n", bpp.nGBprior_c, bpp.consToMis, bpp.nconsToMis);
     }
   }
   cout.rdbuf(old_cout);

@@ -81,6 +81,10 @@ class PaHyper(C.Structure):
         return {k: float(getattr(self, k)) for k, _ in self._fields_}
 
 
+class PaGbgcConsts(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("grate", "lrate", "prior_gb", "cons_to_mis", "ncons_to_mis")]
+
+
 class PaCounters(C.Structure):
     _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
                 ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
@@ -94,7 +98,7 @@ EXPORTS = [
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
-    "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay",
+    "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
 ]
 
 _lib = None
@@ -151,6 +155,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
     lib.pa_run_from_config.argtypes = [C.c_char_p]
     lib.pa_device_fp64_peak.argtypes = [C.c_int, C.c_int, _f64p]
+    lib.pa_engine_gbgc_integrate.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _i8p, _f64p, _f64p, _f64p, C.POINTER(PaGbgcConsts), _f64p, _f64p, _f64p]
     lib.pa_engine_gbgc_replay.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _f64p, _f64p, _f64p, _f64p]
     lib.pa_gbgc_transition.argtypes = [C.c_int, C.POINTER(PaSubst), C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p]
     _lib = lib
@@ -414,6 +419,21 @@ class Engine:
                                                sel_n.ctypes.data_as(_f64p), sel_c.ctypes.data_as(_f64p), gbc.ctypes.data_as(_f64p),
                                                out.ctypes.data_as(_f64p)))
         return out
+
+    def gbgc_integrate(self, elem, Z, B, fixZ, sel_n, sel_c, gbc, grate=0.8, lrate=0.1, prior_gb=0.2, cons_to_mis=0.01, ncons_to_mis=0.1):
+        """PhyloAcc-ST-GBGC groundwork (pa_engine_gbgc_integrate): expected (child, parent) base pairs [n, N, 4, 4], the six (Z, B)
+        emissions [n, N, 6] and [n, 8] = log_prob_back[root][0..5], ELBO term, upward log-likelihood."""
+        elem = np.ascontiguousarray(elem, dtype=np.int32)
+        n = len(elem)
+        Z, B, fixZ = (np.ascontiguousarray(x, dtype=np.int8).reshape(n, self.N) for x in (Z, B, fixZ))
+        sel_n, sel_c, gbc = (np.ascontiguousarray(x, dtype=np.float64) for x in (sel_n, sel_c, gbc))
+        k = PaGbgcConsts(grate, lrate, prior_gb, cons_to_mis, ncons_to_mis)
+        post, emis, rootv = np.zeros((n, self.N, 4, 4)), np.zeros((n, self.N, 6)), np.zeros((n, 8))
+        _check(self._lib.pa_engine_gbgc_integrate(self._h, n, elem.ctypes.data_as(_i32p), Z.ctypes.data_as(_i8p), B.ctypes.data_as(_i8p),
+                                                  fixZ.ctypes.data_as(_i8p), sel_n.ctypes.data_as(_f64p), sel_c.ctypes.data_as(_f64p),
+                                                  gbc.ctypes.data_as(_f64p), C.byref(k), post.ctypes.data_as(_f64p), emis.ctypes.data_as(_f64p),
+                                                  rootv.ctypes.data_as(_f64p)))
+        return post, emis, rootv
 
     def trace(self, i: int, model: int):
         p = self.params()

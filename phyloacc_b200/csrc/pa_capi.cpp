@@ -242,6 +242,16 @@ int pa_engine_gbgc_replay(pa_engine* e, int32_t n_states, const int32_t* elem, c
   return guarded([&]() { return e->eng.gbgc_replay(n_states, elem, Z, B, sel_n, sel_c, gbc, loglik_out); });
 }
 
+int pa_engine_gbgc_integrate(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ,
+                             const double* sel_n, const double* sel_c, const double* gbc, const pa_gbgc_consts* consts, double* post_out,
+                             double* emis_out, double* root_out) {
+  if (!e || !consts || (n_states > 0 && (!elem || !Z || !B || !fixZ || !sel_n || !sel_c || !gbc || !post_out || !emis_out || !root_out))) {
+    g_last = "null argument";
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.gbgc_integrate(n_states, elem, Z, B, fixZ, sel_n, sel_c, gbc, consts, post_out, emis_out, root_out); });
+}
+
 int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
   if (!e || !out10) return PA_ERR_ARG;
   for (int k = 0; k < 10; k++) out10[k] = e->eng.phase_cycles[k];

@@ -394,6 +394,30 @@ int Engine::gbgc_replay(int32_t n_states, const int32_t* elem, const int8_t* Z, 
   return PA_OK;
 }
 
+int Engine::gbgc_integrate(int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ, const double* sel_n, const double* sel_c,
+                           const double* gbc, const pa_gbgc_consts* k, double* post_out, double* emis_out, double* root_out) {
+  if (!loaded) {
+    set_error("pa_engine_gbgc_integrate called before pa_engine_load_alignment");
+    return PA_ERR_STATE;
+  }
+  if (device < 0) {
+    set_error("no CUDA device bound to this engine (there is no CPU fallback)");
+    return PA_ERR_CUDA;
+  }
+  const int N = model.tree.N;
+  std::vector<int8_t> upper((size_t)std::max(n_states, 0) * N, 0);
+  for (int i = 0; i < n_states; i++) {
+    if (elem[i] < 0 || elem[i] >= (int)plans.size()) {
+      set_error("element id out of range");
+      return PA_ERR_ARG;
+    }
+    // the outgroup's ancestors within the element's pruned tree keep conserved -> conserved with probability 1 (GBGC/SRC/bpp.hpp:312-316)
+    for (int32_t v : plans[elem[i]].upper_c) upper[(size_t)i * N + v] = 1;
+  }
+  return pa::gbgc_integrate(device, stream, d_blobs, d_blob_off, N, n_max, slots_max, P_max, model.tree.pi, model.tree.Q, n_states, elem, Z, B, fixZ,
+                            upper.data(), sel_n, sel_c, gbc, k->grate, k->lrate, k->prior_gb, k->cons_to_mis, k->ncons_to_mis, post_out, emis_out, root_out);
+}
+
 // ------------------------------------------------------------------------------------------ FP64 FMA peak
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

@@ -8,6 +8,8 @@
 
 #include <stdint.h>
 
+#include <cuda_runtime.h>
+
 #include <string>
 #include <vector>
 
@@ -151,6 +153,10 @@ std::vector<int32_t> species_ids(const Tree& t, const std::string& semicolon_lis
 bool build_model(const Tree& t, const pa_params& prm, Model& out);
 bool eigen_real4(const double Q[16], double eval[4], double V[16], double Vinv[16]);
 int gbgc_transition(int device, const double* Q0, int n, const double* sel, const double* bias, const double* t, double* rate_out, double* P_out);  // pa_gbgc.cu
+int gbgc_integrate(int device, cudaStream_t stream, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max, const double* pi,
+                   const double* Q0, int n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ, const int8_t* upper,
+                   const double* sel_n, const double* sel_c, const double* gbc, double grate, double lrate, double prior_gb, double cons_to_mis,
+                   double ncons_to_mis, double* post_out, double* emis_out, double* root_out);  // pa_gbgc.cu
 void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, int32_t len, int elem_id, ElemPlan& out);
 
 }  // namespace pa

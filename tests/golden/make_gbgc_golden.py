@@ -47,6 +47,14 @@ def main():
             sc, sn, gb = float(np.round(rng.uniform(-3, -0.5), 6)), float(np.round(rng.uniform(-1, 0.5), 6)), float(np.round(rng.uniform(0, 5), 6))
             script.append(f"state {sc!r} {sn!r} {gb!r} " + " ".join(map(str, Z)) + " " + " ".join(map(str, B)))
             requests.append(dict(c=c, sel_c=sc, sel_n=sn, gbc=gb, Z=Z.tolist(), B=B.tolist()))
+        # the random-number-free evaluations of one Gibbs iteration (expected base pairs, emissions, 6-state messages, ELBO) under each
+        # model's own fixZ: M0 (resZ 0), M1 (resZ 2), M2 (resZ 1)
+        for resZ in (0, 2, 1):
+            Z = rng.integers(0, 3, size=N)
+            B = rng.integers(0, 2, size=N)
+            sc, sn, gb = float(np.round(rng.uniform(-3, -0.5), 6)), float(np.round(rng.uniform(-1, 0.5), 6)), float(np.round(rng.uniform(0, 5), 6))
+            script.append(f"integ {resZ} {sc!r} {sn!r} {gb!r} " + " ".join(map(str, Z)) + " " + " ".join(map(str, B)))
+            requests.append(dict(c=c, integ=resZ, sel_c=sc, sel_n=sn, gbc=gb, B=B.tolist()))
     sp = os.path.join(work, "script.txt")
     with open(sp, "w") as f:
         f.write("\n".join(script) + "\n")

@@ -76,11 +76,68 @@ def _replay_case():
     case = Case("gbgc43")
     gdir = os.path.dirname(GOLD)
     with open(os.path.join(gdir, "requests.json")) as f:
-        reqs = json.load(f)
+        reqs = [r for r in json.load(f) if "integ" not in r]
     with open(GOLD) as f:
         want = gbgc.parse_logliks(f.read())
     assert len(reqs) == len(want) == 24
     return case, reqs, want
+
+
+def _integ_case():
+    import json
+
+    from tests._util import Case
+
+    case = Case("gbgc43")
+    with open(os.path.join(os.path.dirname(GOLD), "requests.json")) as f:
+        reqs = [r for r in json.load(f) if "integ" in r]
+    with open(GOLD) as f:
+        dumps = gbgc.parse_integ(f.read())
+    assert len(reqs) == len(dumps) == 12
+    return case, reqs, dumps
+
+
+def _class_log_tables(Q0, el, r):
+    """log P^T ((child, parent) layout) of the six (Z, B) classes of every branch: k = Z + 3 B."""
+    out = {}
+    for s in el.nodes[:-1]:
+        t = float(el.distances2[s])
+        out[s] = [np.log(gbgc.transition_uniformised(Q0, (0.0, r["sel_c"], r["sel_n"])[k % 3], r["gbc"] if k >= 3 else 0.0, t)).T for k in range(6)]
+    return out
+
+
+def test_expected_pairs_and_zb_integration_match_reference():
+    """The random-number-free half of a GBGC iteration at given states, under each model's own fixZ: expected (child, parent) base pairs per
+    branch (Update_Tg(.,.,.,true)), the six (Z, B) emissions, the 6-state upward messages, log_prob_back[root][0] and the ELBO term."""
+    case, reqs, dumps = _integ_case()
+    Q0, _ = _load()
+    pi = np.asarray(case.tree.pi)
+    for r, d in zip(reqs, dumps):
+        assert d["resZ"] == r["integ"]
+        el = case.element(r["c"])
+        post = gbgc.expected_pairs(Q0, pi, el, d["Z"], r["B"], r["sel_c"], r["sel_n"], r["gbc"])
+        for s, want in d["post"].items():
+            assert np.allclose(post[s], want, rtol=1e-9, atol=1e-12), (r["c"], d["resZ"], s)
+            assert abs(post[s].sum() - el.GG) < 1e-8  # every column contributes one (child, parent) pair per branch
+        tabs = _class_log_tables(Q0, el, r)
+        emis, rootback = gbgc.integrate_zb(post, tabs, el, d["fixZ"], d["tmint"], d["consts"])
+        for s, want in d["emis"].items():
+            fin = np.isfinite(want)
+            assert np.array_equal(fin, np.isfinite(emis[s])) and np.allclose(emis[s][fin], want[fin], rtol=1e-10, atol=1e-9), (r["c"], d["resZ"], s)
+        fin = np.isfinite(d["rootback"])
+        assert np.allclose(rootback[fin], d["rootback"][fin], rtol=1e-10, atol=1e-8)
+        assert abs(rootback[0] - d["loglik"]) <= 1e-10 * abs(d["loglik"])
+        # ELBO term: the emission of every branch's CURRENT class, without the prior constants (bpp_c2.cpp:386)
+        elbo = 0.0
+        for s in el.nodes[:-1]:
+            if el.missing[s]:
+                continue
+            k = d["Z"][s] + 3 * r["B"][s]
+            if d["fixZ"][s] == 1 and k % 3 == 2:
+                continue
+            elbo += float(np.where(post[s] == 0, 0.0, tabs[s][k] * post[s]).sum())
+        assert abs(elbo - d["elbo"]) <= 1e-10 * abs(d["elbo"])
+    case.close()
 
 
 def test_replayed_gbgc_likelihoods_match_reference():
@@ -115,5 +172,31 @@ def test_cuda_gbgc_replay_matches_reference(native_lib):
     a = eng.gbgc_replay([0], Z, Z, [0.0], [0.0], [0.0])[0]
     b = eng.loglik_replay([0], Z, [1.0], [1.0])[0]
     assert abs(a - b) <= 1e-10 * abs(b)
+    eng.close()
+    case.close()
+
+
+@pytest.mark.gpu
+def test_cuda_gbgc_integrate_matches_reference(native_lib):
+    """pa_engine_gbgc_integrate (gbgc_integrate_kernel: upward pass, downward pass of expected base pairs over compressed site patterns,
+    six-class emissions, 6-state messages) against the reference's dumps at twelve states under the three models' own fixZ."""
+    import phyloacc_b200 as pab
+
+    case, reqs, dumps = _integ_case()
+    eng = pab.Engine.from_config(case.cfg, device=0)
+    post, emis, rootv = eng.gbgc_integrate([r["c"] for r in reqs], [d["Z"] for d in dumps], [r["B"] for r in reqs], [d["fixZ"] for d in dumps],
+                                           [r["sel_n"] for r in reqs], [r["sel_c"] for r in reqs], [r["gbc"] for r in reqs],
+                                           grate=0.8, lrate=0.1, prior_gb=dumps[0]["consts"][0], cons_to_mis=dumps[0]["consts"][1],
+                                           ncons_to_mis=dumps[0]["consts"][2])
+    for k, (r, d) in enumerate(zip(reqs, dumps)):
+        for s, want in d["post"].items():
+            assert np.allclose(post[k, s], want, rtol=1e-9, atol=1e-12), (k, s)
+        for s, want in d["emis"].items():
+            fin = np.isfinite(want)
+            assert np.array_equal(fin, np.isfinite(emis[k, s])) and np.allclose(emis[k, s][fin], want[fin], rtol=1e-10, atol=1e-9), (k, s)
+        fin = np.isfinite(d["rootback"])
+        assert np.allclose(rootv[k, :6][fin], d["rootback"][fin], rtol=1e-10, atol=1e-8), k
+        assert abs(rootv[k, 0] - d["loglik"]) <= 1e-10 * abs(d["loglik"])
+        assert abs(rootv[k, 6] - d["elbo"]) <= 1e-10 * abs(d["elbo"])
     eng.close()
     case.close()
