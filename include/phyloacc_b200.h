@@ -226,6 +226,46 @@ int pa_engine_gbgc_integrate(pa_engine* e, int32_t n_states, const int32_t* elem
                              const double* sel_n, const double* sel_c, const double* gbc, const pa_gbgc_consts* consts, double* post_out,
                              double* emis_out, double* root_out);
 
+/* PhyloAcc-ST-GBGC: the chain itself.  BPP_C::Gibbs of src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:259-345 for the listed elements
+ * under M0 / M1 / M2 (the reference's resZ 0 / 2 / 1; main.cpp:395-412), followed by the variant's own Eval2 (variational bound,
+ * bpp_c2.cpp:29-285) and Output_init summaries (bpp_c2.cpp:603-650).  Scalars = LoadParams' GBGC keys and constructor constants
+ * (GBGC/SRC/main.cpp:50-86,108-193; bpp.hpp:201; bpp.cpp:217-219; bpp_c.hpp:358-361). */
+typedef struct pa_gbgc_params {
+  double sel_c0, sel_n0, gbc0;                    /* CONSERVE_RATE (-2), ACCE_RATE (0), initial gBGC bias (3) */
+  double cprior_a, cprior_b;                      /* CONSERVE_PRIOR_A / B: Gamma prior of -sel_c */
+  double nprior_a, nprior_b, nprior_c;            /* ACCE_PRIOR_A / B and the shift (2): Gamma prior of sel_n + shift */
+  double gbprior_a, gbprior_b, gbprior_c;         /* Gamma prior of the bias; prior probability that gBGC acts on a branch */
+  double cons_to_mis, ncons_to_mis;               /* CONSTOMIS and its non-conserved counterpart (0.01, 0.1) */
+  double grate, lrate;                            /* PREP_GRATE, PREP_LRATE (0.8, 0.1) */
+  double prop_c, prop_n, prop_gb;                 /* proposal widths (1.2, 1.2, 0.2; not adapted inside Gibbs: update_rates(.., false)) */
+  int32_t num_burn, num_mcmc;                     /* BURNIN, MCMC */
+  uint32_t seed;
+  int32_t pad_;
+} pa_gbgc_params;
+void pa_gbgc_params_default(pa_gbgc_params* p);
+
+/* Caller-allocated outputs; model index 0 / 1 / 2 = M0 / M1 / M2.  Optional arrays may be NULL. */
+typedef struct pa_gbgc_results {
+  int32_t n_ids, N, T;
+  uint8_t* filtered;   /* [n_ids] */
+  double* loglik;      /* [n_ids][3]  Eval2's estimate of log P(X | model): loglik_NUll, loglik_RES, loglik_all */
+  double* loglik_max;  /* [n_ids][3]  max over post-burn-in iterations of log P(X, Z, B, r) */
+  double* med;         /* [n_ids][3][3]  n_rate, c_rate, gBC as Output_init takes them (element T/2 of the trace with its tail sorted) */
+  double* post_b;      /* [n_ids][3][N]  P(B = 1) per node */
+  double* post_z;      /* [n_ids][3][N][4]  P(Z = -1, 0, 1, 2) per node */
+  int8_t* max_z;       /* [n_ids][3][N]  Z at the arg-max, -1 for pruned nodes */
+  int8_t* max_b;       /* [n_ids][3][N] */
+  int32_t* accept;     /* [n_ids][3][2]  iterations with an accepted rate move / accepted (Z, B) update */
+  double* trace;       /* optional [n_ids][3][5][T]: log P(X | Z, B, r), log P(X, Z, B, r), c_rate, n_rate, gBC */
+  int8_t* trace_z;     /* optional [n_ids][3][T][N] */
+  int8_t* trace_b;     /* optional [n_ids][3][T][N] */
+  double kernel_ms;    /* duration of the chain kernel (CUDA events) */
+  uint64_t node_pattern_updates, chain_iterations;
+} pa_gbgc_results;
+/* targets: node ids of TARGETSPECIES (the only tips free to accelerate under M1).  model_mask: bit m set = run model m. */
+int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,
+                       int model_mask, pa_gbgc_results* out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

@@ -85,6 +85,19 @@ class PaGbgcConsts(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("grate", "lrate", "prior_gb", "cons_to_mis", "ncons_to_mis")]
 
 
+class PaGbgcParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("sel_c0", "sel_n0", "gbc0", "cprior_a", "cprior_b", "nprior_a", "nprior_b", "nprior_c", "gbprior_a",
+                                          "gbprior_b", "gbprior_c", "cons_to_mis", "ncons_to_mis", "grate", "lrate", "prop_c", "prop_n",
+                                          "prop_gb")] + [("num_burn", C.c_int32), ("num_mcmc", C.c_int32), ("seed", C.c_uint32), ("pad_", C.c_int32)]
+
+
+class PaGbgcResults(C.Structure):
+    _fields_ = [("n_ids", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("filtered", _u8p), ("loglik", _f64p), ("loglik_max", _f64p),
+                ("med", _f64p), ("post_b", _f64p), ("post_z", _f64p), ("max_z", _i8p), ("max_b", _i8p), ("accept", _i32p),
+                ("trace", _f64p), ("trace_z", _i8p), ("trace_b", _i8p), ("kernel_ms", C.c_double),
+                ("node_pattern_updates", C.c_uint64), ("chain_iterations", C.c_uint64)]
+
+
 class PaCounters(C.Structure):
     _fields_ = [("node_pattern_updates", C.c_uint64), ("root_evals", C.c_uint64), ("pt_builds", C.c_uint64),
                 ("history_draws", C.c_uint64), ("chain_iterations", C.c_uint64), ("kernel_launches", C.c_uint64),
@@ -99,6 +112,7 @@ EXPORTS = [
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
     "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
+    "pa_gbgc_params_default", "pa_engine_gbgc_run",
 ]
 
 _lib = None
@@ -158,6 +172,9 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_gbgc_integrate.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _i8p, _f64p, _f64p, _f64p, C.POINTER(PaGbgcConsts), _f64p, _f64p, _f64p]
     lib.pa_engine_gbgc_replay.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _f64p, _f64p, _f64p, _f64p]
     lib.pa_gbgc_transition.argtypes = [C.c_int, C.POINTER(PaSubst), C.c_int32, _f64p, _f64p, _f64p, _f64p, _f64p]
+    lib.pa_gbgc_params_default.argtypes = [C.POINTER(PaGbgcParams)]
+    lib.pa_gbgc_params_default.restype = None
+    lib.pa_engine_gbgc_run.argtypes = [C.c_void_p, _i32p, C.c_int32, _i32p, C.c_int32, C.POINTER(PaGbgcParams), C.c_int, C.POINTER(PaGbgcResults)]
     _lib = lib
     return lib
 
@@ -434,6 +451,36 @@ class Engine:
                                                   gbc.ctypes.data_as(_f64p), C.byref(k), post.ctypes.data_as(_f64p), emis.ctypes.data_as(_f64p),
                                                   rootv.ctypes.data_as(_f64p)))
         return post, emis, rootv
+
+    def gbgc_run(self, ids, targets, traces: bool = False, model_mask: int = 7, **params) -> dict:
+        """The PhyloAcc-ST-GBGC chain (pa_engine_gbgc_run): M0 / M1 / M2 for the listed elements.  `targets` = node ids of TARGETSPECIES;
+        keyword arguments override pa_gbgc_params_default (num_burn, num_mcmc, seed, sel_c0, ...).  Returns a dict of arrays indexed
+        [element, model, ...] (loglik, loglik_max, med = (n_rate, c_rate, gBC), post_b, post_z, max_z, max_b, accept, filtered), with
+        trace [.., 5, T], trace_z / trace_b [.., T, N] when traces=True, and kernel_ms / node_pattern_updates / chain_iterations."""
+        prm = PaGbgcParams()
+        self._lib.pa_gbgc_params_default(C.byref(prm))
+        for k, v in params.items():
+            if not hasattr(prm, k):
+                raise KeyError(k)
+            setattr(prm, k, v)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        targets = np.ascontiguousarray(targets, dtype=np.int32)
+        n, N, T = len(ids), self.N, prm.num_burn + prm.num_mcmc
+        out = dict(filtered=np.zeros(n, np.uint8), loglik=np.zeros((n, 3)), loglik_max=np.zeros((n, 3)), med=np.zeros((n, 3, 3)),
+                   post_b=np.zeros((n, 3, N)), post_z=np.zeros((n, 3, N, 4)), max_z=np.zeros((n, 3, N), np.int8), max_b=np.zeros((n, 3, N), np.int8),
+                   accept=np.zeros((n, 3, 2), np.int32))
+        if traces:
+            out.update(trace=np.zeros((n, 3, 5, T)), trace_z=np.zeros((n, 3, T, N), np.int8), trace_b=np.zeros((n, 3, T, N), np.int8))
+        r = PaGbgcResults()
+        r.n_ids, r.N, r.T = n, N, T
+        for k, t in (("filtered", _u8p), ("loglik", _f64p), ("loglik_max", _f64p), ("med", _f64p), ("post_b", _f64p), ("post_z", _f64p),
+                     ("max_z", _i8p), ("max_b", _i8p), ("accept", _i32p), ("trace", _f64p), ("trace_z", _i8p), ("trace_b", _i8p)):
+            if k in out:
+                setattr(r, k, out[k].ctypes.data_as(t))
+        _check(self._lib.pa_engine_gbgc_run(self._h, ids.ctypes.data_as(_i32p), n, targets.ctypes.data_as(_i32p), len(targets), C.byref(prm),
+                                            model_mask, C.byref(r)))
+        out.update(kernel_ms=float(r.kernel_ms), node_pattern_updates=int(r.node_pattern_updates), chain_iterations=int(r.chain_iterations))
+        return out
 
     def trace(self, i: int, model: int):
         p = self.params()

@@ -252,6 +252,15 @@ int pa_engine_gbgc_integrate(pa_engine* e, int32_t n_states, const int32_t* elem
   return guarded([&]() { return e->eng.gbgc_integrate(n_states, elem, Z, B, fixZ, sel_n, sel_c, gbc, consts, post_out, emis_out, root_out); });
 }
 
+int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,
+                       int model_mask, pa_gbgc_results* out) {
+  if (!e || !prm || !out || (n_targets > 0 && !targets)) {
+    pa::set_error("pa_engine_gbgc_run: null argument");
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.gbgc_run(ids, n_ids, targets, n_targets, prm, model_mask, out); });
+}
+
 int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10) {
   if (!e || !out10) return PA_ERR_ARG;
   for (int k = 0; k < 10; k++) out10[k] = e->eng.phase_cycles[k];

@@ -1,0 +1,697 @@
+// pa_gbgc_chain.cu -- the PhyloAcc-ST-GBGC chain on the device: BPP_C::Gibbs of src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:259-345.
+//
+// One CTA (128 threads) per (element, model) chain, persistent grid pulling chains from an atomic queue.  Unlike PhyloAcc-ST the GC-biased
+// sampler draws no substitution histories: an iteration works on the EXPECTED (child base, parent base) pairs of every branch
+//   1. MonitorChain                                                                      bpp_c.cpp:598-652
+//   2. expected pairs at the current state (downward pass over compressed site patterns)  Update_Tg(g,.,.,true)   :530-583
+//   3. six (Z, B) emissions per branch + 6-state upward messages + the ELBO term          initial_prob_back       bpp_c2.cpp:354-407
+//   4. three joint MH moves on (gBGC bias, accelerated selection, conserved selection)    sample_rates            bpp_c.cpp:881-958
+//      with (Z, B) integrated out: five new rate matrices Q o f(s + b B), P(t) of every
+//      branch under each (uniformisation + squaring, pa_gbgc.cuh), emissions, messages    integrate_ZB            :1765-1795
+//   5. top-down draws of (Z, B), the exact likelihood at the drawn state (upward pass),
+//      ELBO at the new state, one MH decision for the whole iteration                     update_rates, Update_ZB :1079-1131, 1667-1763
+// Random numbers: Philox4x32-10 keyed by (seed, element number * 4 + model), counter (index, sub, iteration, PA_ST_GBGC); sub 0 = the
+// three rate moves (index = move; words = bias / accelerated / conserved proposal, acceptance), sub 1 = the (Z, B) draw of node `index`,
+// sub 2 = the iteration's final acceptance.  oracle/gbgc.py (GbgcChain) restates the chain on the same schedule.
+// Layout: P(t) logs of the five rate-dependent classes live in three rotating per-CTA buffers in global memory (committed / working /
+// proposal: accepting a move is a pointer swap), class 0 (background, no gBGC) is computed once per chain; partials [node][pattern][4] in
+// the CTA's scratch; everything else in shared memory.  fp64 throughout.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "pa_device.cuh"
+#include "pa_gbgc.cuh"
+#include "pa_internal.h"
+
+namespace pa {
+
+namespace {
+
+constexpr int kCBD = 128;
+#define PA_ST_GBGC 4u
+
+struct GbgcChainLaunch {
+  const uint8_t* blobs; const int64_t* blob_off;
+  int n_chains, N, n_max, slots_max, P_max, T;
+  const int32_t* chain_elem;  // element index in the engine's batch
+  const int32_t* chain_resz;  // the reference's resZ: 0 = M0, 2 = M1, 1 = M2
+  const int8_t* fixZ;         // [n_chains][N] original numbering (1: class 2 forbidden)
+  const int8_t* upper;        // [n_chains][N] outgroup lineage: conserved stays conserved
+  pa_gbgc_params prm;
+  double pi[4];
+  double Q0[16];
+  unsigned char* scratch; size_t stride;  // per resident CTA
+  int* queue;
+  double* tr;       // [n_chains][5][T]: log P(X | Z, B, r), log P(X, Z, B, r), conserved / accelerated selection, gBGC bias
+  uint8_t* tr_zb;   // [n_chains][T][n_max] local node order: Z | B << 2
+  double* head;     // [n_chains][8]: log P(constraints), accepted rate sweeps, accepted iterations
+  unsigned long long* counters;  // [4]: node-pattern updates, P(t) builds, chain iterations
+};
+
+// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | per-warp pair accumulators [4][n_max][16]
+__host__ __device__ inline size_t uni_doubles(int n_max, int slots_max) {
+  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = (size_t)4 * n_max * 16;
+  return a > b ? a : b;
+}
+
+struct Sh {  // shared-memory views of one chain
+  double *Pm, *uni, *red, *emis, *emis_t, *back, *Qc, *scal;
+  int* stack_sc;
+  int16_t *child, *tiprow, *su, *intidx, *parent, *up_nodes, *up_off, *down_nodes, *down_off;
+  uint8_t *flags, *fix, *upr;
+  int8_t *slot, *Z, *B, *Zn, *Bn;
+};
+
+enum { SC_LG0 = 0, SC_LG1, SC_LL0, SC_LL1, SC_SELC, SC_SELN, SC_GBC, SC_PSELC, SC_PSELN, SC_PGBC, SC_LOGLIK, SC_LOGLIK_OLD, SC_ELBO_OLD, SC_LOGPZ,
+       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_N };
+
+// log TM_Int (child class a, parent class j) of a branch (GBGC/SRC/bpp.hpp:284-316): (0,0) = 1-g, (1,0) = g, (1,1) = 1-l, (2,1) = l, (2,2) = 1;
+// on the outgroup lineage (1,1) = 1 and (2,1) = 0
+__device__ __forceinline__ double lt_val(const double* scal, int a, int j, bool up) {
+  if (j == 0) return a == 0 ? scal[SC_LG0] : (a == 1 ? scal[SC_LG1] : -CUDART_INF);
+  if (j == 1) return a == 1 ? (up ? 0.0 : scal[SC_LL0]) : (a == 2 ? (up ? -CUDART_INF : scal[SC_LL1]) : -CUDART_INF);
+  return a == 2 ? 0.0 : -CUDART_INF;
+}
+
+// message of child c to its parent's class j: log sum_k exp(lt[k % 3][j] + back[c][k]) with ONE maximum over the whole 6 x 3 table
+// (BPP::log_multi, GBGC/SRC/bpp.hpp)
+__device__ __forceinline__ double child_msg(const Sh& s, int c, int j) {
+  const bool up = s.upr[c] != 0;
+  double mx = -CUDART_INF;
+  for (int k = 0; k < 6; k++) {
+    const double b = s.back[c * 6 + k];
+#pragma unroll
+    for (int jj = 0; jj < 3; jj++) mx = fmax(mx, lt_val(s.scal, k % 3, jj, up) + b);
+  }
+  if (!(mx > -CUDART_INF)) return -CUDART_INF;
+  double sum = 0.0;
+  for (int k = 0; k < 6; k++) sum += exp(lt_val(s.scal, k % 3, j, up) + s.back[c * 6 + k] - mx);
+  return log(sum) + mx;
+}
+
+// 6-state upward messages by height levels; src = emissions [n][6] (the root's row is taken as zero); result in s.back
+__device__ void messages(const Sh& s, const double* src, int n, int n_up, bool init_pass, int tid) {
+  for (int t = tid; t < n * 6; t += kCBD) s.back[t] = (t >= (n - 1) * 6) ? 0.0 : src[t];
+  __syncthreads();
+  for (int h = 1; h < n_up; h++) {
+    const int lo = s.up_off[h], cnt = s.up_off[h + 1] - lo;
+    for (int t = tid; t < cnt * 3; t += kCBD) {
+      const int p = s.up_nodes[lo + t / 3], j = t % 3;
+      const int c0 = s.child[2 * p], c1 = s.child[2 * p + 1];
+      if (c0 < 0) continue;
+      double m0 = child_msg(s, c0, j), m1 = child_msg(s, c1, j);
+      if (init_pass) { m0 -= 0.69314718055994530942; m1 -= 0.69314718055994530942; }
+      s.back[p * 6 + j] = (s.back[p * 6 + j] + m0) + m1;
+      s.back[p * 6 + 3 + j] = (s.back[p * 6 + 3 + j] + m0) + m1;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ const double* class_log(const double* P0, const double* buf, int i, int k) {
+  return k == 0 ? P0 + (size_t)i * 16 : buf + ((size_t)i * 5 + (k - 1)) * 16;
+}
+
+__device__ __forceinline__ double pair_dot(const double* __restrict__ lp, const double* __restrict__ post) {
+  double sum = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const double c = post[a * 4 + b];
+      if (c != 0.0) sum += lp[b * 4 + a] * c;  // log P(parent b -> child a) x expected pairs (child a, parent b)
+    }
+  return sum;
+}
+
+// emissions of classes k_lo..5 of every branch into dst; class 0 (and missing branches) are copied from `base` when k_lo == 1
+__device__ void emissions(const Sh& s, const GbgcChainLaunch& L, double* dst, const double* base, const double* P0, const double* buf,
+                          const double* post, int n, int k_lo, int tid) {
+  const double l_b0 = log(1.0 - L.prm.gbprior_c), l_b1 = log(L.prm.gbprior_c), l_c = log(1.0 - L.prm.cons_to_mis), l_n = log(1.0 - L.prm.ncons_to_mis);
+  for (int t = tid; t < 6 * (n - 1); t += kCBD) {
+    const int i = t / 6, k = t - 6 * i;
+    const bool fix1 = s.fix[i] == 1;
+    double e;
+    if (s.flags[i] & PA_F_MISSING) {
+      if (base) e = base[t];
+      else {
+        e = 0.0;
+        if (!(s.flags[s.parent[i]] & PA_F_MISSING)) e = (k % 3 == 1) ? log(L.prm.cons_to_mis) : log(L.prm.ncons_to_mis);
+        if (fix1 && k % 3 == 2) e = -CUDART_INF;
+      }
+    } else if (fix1 && k % 3 == 2) {
+      e = -CUDART_INF;
+    } else if (k < k_lo) {
+      e = base[t];
+    } else {
+      e = pair_dot(class_log(P0, buf, i, k), post + (size_t)i * 16) + (k < 3 ? l_b0 : l_b1) + (k % 3 == 1 ? l_c : l_n);
+    }
+    dst[t] = e;
+  }
+}
+
+// sum over the non-missing branches of <log P of the branch's class, expected pairs>  (BPP_C::ELBO, GBGC/SRC/bpp_c.cpp:840-878)
+__device__ double elbo_term(const Sh& s, const int8_t* Z, const int8_t* B, const double* P0, const double* buf, const double* post, int n, int tid) {
+  double acc = 0.0;
+  for (int i = tid; i < n - 1; i += kCBD)
+    if (!(s.flags[i] & PA_F_MISSING)) acc += pair_dot(class_log(P0, buf, i, Z[i] + 3 * B[i]), post + (size_t)i * 16);
+  return block_sum(acc, s.red, tid, kCBD);
+}
+
+// log P(t) of classes k_lo..5 of every branch at (sel_c, sel_n, gbc) into P0 (class 0) / buf (classes 1..5); row-major P(i -> j)
+__device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView& ev, double* P0, double* buf, double sel_c, double sel_n, double gbc, int n,
+                           int k_lo, int tid) {
+  if (tid >= k_lo && tid < 6) {
+    double Q[16];
+    gbgc_rate(L.Q0, tid % 3 == 0 ? 0.0 : (tid % 3 == 1 ? sel_c : sel_n), tid >= 3 ? gbc : 0.0, Q);
+#pragma unroll
+    for (int e = 0; e < 16; e++) s.Qc[tid * 16 + e] = Q[e];
+  }
+  __syncthreads();
+  const int nk = 6 - k_lo;
+  for (int t = tid; t < nk * (n - 1); t += kCBD) {
+    const int i = t / nk, k = k_lo + (t - nk * i);
+    if (s.flags[i] & PA_F_MISSING) continue;
+    if (s.fix[i] == 1 && k % 3 == 2) continue;  // never read (update_cache_TM's own skip, GBGC/SRC/bpp_c.cpp:1655)
+    double Q[16], P16[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) Q[e] = s.Qc[k * 16 + e];
+    expm_uniformised(Q, ev.dist[i], P16);
+    double* dst = k == 0 ? P0 + (size_t)i * 16 : buf + ((size_t)i * 5 + (k - 1)) * 16;
+#pragma unroll
+    for (int e = 0; e < 16; e++) dst[e] = log(P16[e]);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int categorical_n(const double* w, int K, double u) {
+  double tot = 0.0;
+  for (int k = 0; k < K; k++) tot += w[k];
+  const double x = u * tot;
+  double acc = 0.0;
+  for (int k = 0; k < K; k++) {
+    acc += w[k];
+    if (x < acc) return k;
+  }
+  for (int k = K - 1; k >= 0; k--)
+    if (w[k] > 0.0) return k;
+  return -1;
+}
+
+// deterministic sum over warp 0 (values of the other warps are ignored): returns the total on every lane of warp 0
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_chain, s_flag, s_bufA, s_bufW;
+  __shared__ double s_pi[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_max = L.n_max, slots_max = L.slots_max, N = L.N, T = L.T;
+  Sh s;
+  {
+    double* d = reinterpret_cast<double*>(smem_raw);
+    s.Pm = d; d += (size_t)n_max * 16;
+    s.uni = d;  // pruning stack [slots][4][BD] + scale counts | per-warp pair accumulators [4][n_max][16]
+    const size_t uni_d = uni_doubles(n_max, slots_max);
+    s.stack_sc = reinterpret_cast<int*>(d + (size_t)slots_max * 4 * kCBD);
+    d += uni_d;
+    s.red = d; d += 34;
+    s.emis = d; d += (size_t)n_max * 6;
+    s.emis_t = d; d += (size_t)n_max * 6;
+    s.back = d; d += (size_t)n_max * 6;
+    s.Qc = d; d += 96;
+    s.scal = d; d += SC_N;
+    int16_t* h16 = reinterpret_cast<int16_t*>(d);
+    s.child = h16; h16 += 2 * n_max;
+    s.tiprow = h16; h16 += n_max;
+    s.su = h16; h16 += n_max;
+    s.intidx = h16; h16 += n_max;
+    s.parent = h16; h16 += n_max;
+    s.up_nodes = h16; h16 += n_max;
+    s.up_off = h16; h16 += n_max + 2;
+    s.down_nodes = h16; h16 += n_max;
+    s.down_off = h16; h16 += n_max + 2;
+    uint8_t* b8 = reinterpret_cast<uint8_t*>(h16);
+    s.flags = b8; b8 += n_max;
+    s.fix = b8; b8 += n_max;
+    s.upr = b8; b8 += n_max;
+    s.slot = reinterpret_cast<int8_t*>(b8); b8 += n_max;
+    s.Z = reinterpret_cast<int8_t*>(b8); b8 += n_max;
+    s.B = reinterpret_cast<int8_t*>(b8); b8 += n_max;
+    s.Zn = reinterpret_cast<int8_t*>(b8); b8 += n_max;
+    s.Bn = reinterpret_cast<int8_t*>(b8); b8 += n_max;
+  }
+  // per-CTA scratch
+  unsigned char* sc = L.scratch + (size_t)blockIdx.x * L.stride;
+  double* P0 = reinterpret_cast<double*>(sc);                     // [n_max][16]
+  double* bufs = P0 + (size_t)n_max * 16;                         // [3][n_max][5][16]
+  const size_t buf_d = (size_t)n_max * 80;
+  double* postb = bufs + 3 * buf_d;                               // [2][n_max][16]
+  double* gpart = postb + (size_t)2 * n_max * 16;                 // [n_max][P_max][4]
+  int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)n_max * L.P_max * 4);
+  const pa_gbgc_params& pr = L.prm;
+  if (tid < 4) s_pi[tid] = L.pi[tid];
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_chain = atomicAdd(L.queue, 1);
+    __syncthreads();
+    const int ch = s_chain;
+    if (ch >= L.n_chains) break;
+    const int64_t off = L.blob_off[L.chain_elem[ch]];
+    if (off < 0) continue;  // filtered element
+    const ElemView ev = make_view(L.blobs + off);
+    const ElemHeader* h = ev.h;
+    const int n = h->n, ni = h->ni, root = n - 1, n_up = h->n_up, n_down = h->n_down, P = h->P, Ppad = h->Ppad;
+    const int resz = L.chain_resz[ch];
+    const uint32_t key = (uint32_t)h->elem_id * 4u + (uint32_t)resz;
+    double* tr = L.tr + (size_t)ch * 5 * T;
+    uint8_t* trzb = L.tr_zb + (size_t)ch * T * n_max;
+    for (int i = tid; i < n; i += kCBD) {
+      s.child[2 * i] = ev.child[2 * i];
+      s.child[2 * i + 1] = ev.child[2 * i + 1];
+      s.tiprow[i] = ev.tiprow[i];
+      s.intidx[i] = ev.intidx[i];
+      s.parent[i] = ev.parent[i];
+      s.flags[i] = ev.flags[i];
+      s.slot[i] = ev.slot[i];
+      s.up_nodes[i] = ev.up_nodes[i];
+      s.down_nodes[i] = ev.down_nodes[i];
+      const int o = ev.orig[i];
+      s.fix[i] = (uint8_t)(L.fixZ[(size_t)ch * N + o] == 1 ? 1 : 0);
+      s.upr[i] = (uint8_t)(L.upper[(size_t)ch * N + o] ? 1 : 0);
+      s.Z[i] = 0; s.B[i] = 0; s.Zn[i] = 0; s.Bn[i] = 0;
+    }
+    for (int i = tid; i < ni; i += kCBD) s.su[i] = ev.su[i];
+    for (int i = tid; i <= n_up; i += kCBD) s.up_off[i] = ev.up_off[i];
+    for (int i = tid; i <= n_down; i += kCBD) s.down_off[i] = ev.down_off[i];
+    if (tid == 0) {
+      s.scal[SC_LG0] = log(1.0 - pr.grate); s.scal[SC_LG1] = log(pr.grate);
+      s.scal[SC_LL0] = log(1.0 - pr.lrate); s.scal[SC_LL1] = log(pr.lrate);
+      s.scal[SC_SELC] = pr.sel_c0; s.scal[SC_SELN] = pr.sel_n0; s.scal[SC_GBC] = pr.gbc0;
+      s_bufA = 0; s_bufW = 0;
+    }
+    __syncthreads();
+    TreeSmem ts{s.child, s.flags, s.tiprow, s.su, s.slot, s.intidx};
+    double* stack = s.uni;
+    // log P(constraints): the 6-state pass of initMCMC with "- log 2" per message (GBGC/SRC/bpp_c.cpp:232-254)
+    for (int t = tid; t < n * 6; t += kCBD) s.emis_t[t] = (s.fix[t / 6] == 1 && (t % 3) == 2) ? -CUDART_INF : 0.0;
+    __syncthreads();
+    messages(s, s.emis_t, n, n_up, true, tid);
+    if (tid == 0) s.scal[SC_LOGPZC] = s.back[root * 6];
+    // the six classes' log P(t) at the initial rates; P(t) of the initial classes (Z = 0, B = 0 everywhere)
+    build_logs(s, L, ev, P0, bufs, pr.sel_c0, pr.sel_n0, pr.gbc0, n, 0, tid);
+    auto load_Pm = [&](const int8_t* Zs, const int8_t* Bs, const double* buf) {
+      for (int t = tid; t < (n - 1) * 16; t += kCBD) {
+        const int i = t >> 4;
+        if (s.flags[i] & PA_F_MISSING) continue;
+        s.Pm[t] = exp(class_log(P0, buf, i, Zs[i] + 3 * Bs[i])[t & 15]);
+      }
+      __syncthreads();
+    };
+    auto upward = [&]() -> double {
+      double acc = 0.0;
+      for (int p = tid; p < Ppad; p += kCBD)
+        if (p < P) acc += (double)ev.weights[p] * prune_pattern<false, true>(h, ts, ev.codes, s.Pm, nullptr, stack, s.stack_sc, gpart, gsc, s_pi, p, kCBD, tid);
+      const double v = block_sum(acc, s.red, tid, kCBD);
+      __syncthreads();
+      return v;
+    };
+    load_Pm(s.Z, s.B, bufs);
+    {
+      const double ll0 = upward();
+      if (tid == 0) {
+        s.scal[SC_LOGLIK] = ll0;
+        double pz = 0.0;
+        for (int i = n - 2; i >= 0; i--) pz += lt_val(s.scal, 0, 0, s.upr[i] != 0);
+        s.scal[SC_LOGPZ] = pz - s.scal[SC_LOGPZC];
+        s.scal[SC_FULL] = 0.0;
+      }
+    }
+    __syncthreads();
+    bool move = true;
+    int cur = 0, nxt = 0;  // expected-pair buffers: post_cur / post_next
+    int acc_rates = 0, acc_zb = 0;
+    for (int m = 0; m < T; m++) {
+      // ---- 1. MonitorChain
+      if (warp == 0) {
+        if (move) {
+          int c0 = 0, c1 = 0, c2 = 0, c3 = 0, gb = 0, ungb = 0;
+          for (int i = lane; i < n - 1; i += 32) {
+            if (s.flags[s.parent[i]] & PA_F_MISSING) continue;
+            const bool mis = (s.flags[i] & PA_F_MISSING) != 0;
+            const int idx = 2 * (mis ? 1 : 0) + (s.Z[i] == 1 ? 1 : 0);
+            c0 += idx == 0; c1 += idx == 1; c2 += idx == 2; c3 += idx == 3;
+            if (!mis) { gb += s.B[i] ? 1 : 0; ungb += s.B[i] ? 0 : 1; }
+          }
+          c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1); c2 = __reduce_add_sync(0xffffffffu, c2);
+          c3 = __reduce_add_sync(0xffffffffu, c3); gb = __reduce_add_sync(0xffffffffu, gb); ungb = __reduce_add_sync(0xffffffffu, ungb);
+          if (lane == 0) {
+            double v = s.scal[SC_LOGLIK] + s.scal[SC_LOGPZ];
+            v += log_gamma_pdf(-s.scal[SC_SELC], pr.cprior_a, pr.cprior_b);
+            if (resz != 0) v += log_gamma_pdf(s.scal[SC_SELN] + pr.nprior_c, pr.nprior_a, pr.nprior_b);
+            v += log(1.0 - pr.ncons_to_mis) * c0 + log(1.0 - pr.cons_to_mis) * c1 + log(pr.ncons_to_mis) * c2 + log(pr.cons_to_mis) * c3;
+            v += log(1.0 - pr.gbprior_c) * ungb + log_gamma_pdf(s.scal[SC_GBC], pr.gbprior_a, pr.gbprior_b) + log(pr.gbprior_c) * gb;
+            s.scal[SC_FULL] = v;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tr[m] = s.scal[SC_LOGLIK];
+          tr[T + m] = s.scal[SC_FULL];
+          tr[2 * T + m] = s.scal[SC_SELC];
+          tr[3 * T + m] = s.scal[SC_SELN];
+          tr[4 * T + m] = s.scal[SC_GBC];
+        }
+      }
+      for (int i = tid; i < n; i += kCBD) trzb[(size_t)m * n_max + i] = (uint8_t)(s.Z[i] | (s.B[i] << 2));
+      if (m == T - 1) break;
+      // ---- 2. expected (child, parent) pairs at the current state (only when the state moved): parents before children, an internal
+      //         node's partial is overwritten by the posterior of its base; per-warp accumulators, no block barrier inside the pass
+      if (move) {
+        nxt = (m == 0) ? 0 : 1 - cur;
+        double* pw = s.uni + (size_t)warp * n_max * 16;
+        for (int t = lane; t < n * 16; t += 32) pw[t] = 0.0;
+        __syncwarp();
+        const int half = Ppad >> 1;
+        for (int p0 = 0; p0 < Ppad; p0 += kCBD) {
+          const int p = p0 + tid;
+          const bool act = p < P;
+          const double w = act ? (double)ev.weights[p] : 0.0;
+          if (act) {
+            double* g = gpart + ((size_t)s.intidx[root] * Ppad + p) * 4;
+            const double r0 = s_pi[0] * g[0], r1 = s_pi[1] * g[1], r2 = s_pi[2] * g[2], r3 = s_pi[3] * g[3];
+            const double tot = ((r0 + r1) + r2) + r3;
+            g[0] = r0 / tot; g[1] = r1 / tot; g[2] = r2 / tot; g[3] = r3 / tot;
+          }
+          for (int i = n - 2; i >= 0; i--) {
+            if (s.flags[i] & PA_F_MISSING) continue;  // uniform over the CTA
+            double J[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) J[e] = 0.0;
+            if (act) {
+              double Lv[4];
+              double* gi = nullptr;
+              if (s.flags[i] & PA_F_TIP) {
+                const uint32_t byte = __ldg(ev.codes + (size_t)s.tiprow[i] * half + (p >> 1));
+                const uint32_t code = (byte >> ((p & 1) * 4)) & 15u;
+#pragma unroll
+                for (int a = 0; a < 4; a++) Lv[a] = ((code >> a) & 1u) ? 1.0 : 0.0;
+              } else {
+                gi = gpart + ((size_t)s.intidx[i] * Ppad + p) * 4;
+#pragma unroll
+                for (int a = 0; a < 4; a++) Lv[a] = gi[a];
+              }
+              const double* Pi = s.Pm + i * 16;
+              const double* qp = gpart + ((size_t)s.intidx[s.parent[i]] * Ppad + p) * 4;
+              double qi[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const double mm = ((Pi[b * 4] * Lv[0] + Pi[b * 4 + 1] * Lv[1]) + Pi[b * 4 + 2] * Lv[2]) + Pi[b * 4 + 3] * Lv[3];
+                const double ratio = (mm > 0.0) ? qp[b] / mm : 0.0;
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                  const double j = ratio * Pi[b * 4 + a] * Lv[a];
+                  J[a * 4 + b] = j * w;  // [child base a][parent base b], weighted by the pattern's column count
+                  qi[a] += j;
+                }
+              }
+              if (gi) {
+#pragma unroll
+                for (int a = 0; a < 4; a++) gi[a] = qi[a];
+              }
+            }
+            // transposing butterfly: 16 values x 32 lanes -> one total per even lane in 16 shuffles (deterministic order)
+            double v8[8], v4[4], v2[2], v1;
+            {
+              const bool hi = (lane & 16) != 0;
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                const double keep = hi ? J[e + 8] : J[e], send = hi ? J[e] : J[e + 8];
+                v8[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+            }
+            {
+              const bool hi = (lane & 8) != 0;
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                const double keep = hi ? v8[e + 4] : v8[e], send = hi ? v8[e] : v8[e + 4];
+                v4[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+            }
+            {
+              const bool hi = (lane & 4) != 0;
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const double keep = hi ? v4[e + 2] : v4[e], send = hi ? v4[e] : v4[e + 2];
+                v2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+            }
+            {
+              const bool hi = (lane & 2) != 0;
+              const double keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
+              v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+            if (!(lane & 1)) pw[i * 16 + (lane >> 1)] += v1;  // pair index = 8 b4 + 4 b3 + 2 b2 + b1 of the lane = lane >> 1
+          }
+        }
+        __syncthreads();
+        double* pn = postb + (size_t)nxt * n_max * 16;
+        for (int t = tid; t < (n - 1) * 16; t += kCBD)
+          pn[t] = ((s.uni[t] + s.uni[(size_t)n_max * 16 + t]) + s.uni[(size_t)2 * n_max * 16 + t]) + s.uni[(size_t)3 * n_max * 16 + t];
+        __syncthreads();
+      }
+      if (m == 0) cur = nxt;
+      const double* post = postb + (size_t)cur * n_max * 16;
+      // ---- 3. initial_prob_back: emissions of the six classes, messages, ELBO at the current classes
+      const double* bufA = bufs + (size_t)s_bufA * buf_d;
+      emissions(s, L, s.emis, nullptr, P0, bufA, post, n, 0, tid);
+      __syncthreads();
+      messages(s, s.emis, n, n_up, false, tid);
+      const double elbo_old = elbo_term(s, s.Z, s.B, P0, bufA, post, n, tid);
+      if (tid == 0) {
+        s.scal[SC_LOGLIK_OLD] = s.back[root * 6];
+        s.scal[SC_ELBO_OLD] = elbo_old;
+        s.scal[SC_PSELC] = s.scal[SC_SELC]; s.scal[SC_PSELN] = s.scal[SC_SELN]; s.scal[SC_PGBC] = s.scal[SC_GBC];  // cur_* of sample_rates
+        s_bufW = s_bufA;
+      }
+      __syncthreads();
+      // ---- 4. sample_rates: three joint moves with (Z, B) integrated out
+      bool any_moved = false;
+      for (int mm = 0; mm < 3; mm++) {
+        const uint4 w4 = philox4(pr.seed, key, (uint32_t)mm, 0u, (uint32_t)m, PA_ST_GBGC);
+        const double cur_c = s.scal[SC_PSELC], cur_n = s.scal[SC_PSELN], cur_g = s.scal[SC_PGBC];
+        double new_g = cur_g + (u01(w4.x) - 0.5) * pr.prop_gb * 2;
+        if (new_g < 0.01) new_g = cur_g;
+        double new_n = cur_n;
+        if (resz != 0) {
+          const double u = u01(w4.y) * (pr.prop_n - 1 / pr.prop_n) + 1 / pr.prop_n;
+          new_n = (cur_n + pr.nprior_c) * u - pr.nprior_c;
+        }
+        const double new_c = cur_c * (u01(w4.z) * (pr.prop_c - 1 / pr.prop_c) + 1 / pr.prop_c);
+        const int bA = s_bufA, bW = s_bufW;
+        const int bP = (bA != 0 && bW != 0) ? 0 : ((bA != 1 && bW != 1) ? 1 : 2);
+        double* bufP = bufs + (size_t)bP * buf_d;
+        __syncthreads();
+        build_logs(s, L, ev, P0, bufP, new_c, new_n, new_g, n, 1, tid);
+        emissions(s, L, s.emis_t, s.emis, P0, bufP, post, n, 1, tid);
+        __syncthreads();
+        messages(s, s.emis_t, n, n_up, false, tid);
+        if (tid == 0) {
+          const double ll_p = s.back[root * 6];
+          double ratio = ll_p - s.scal[SC_LOGLIK_OLD] + log_gamma_pdf(new_g, pr.gbprior_a, pr.gbprior_b) - log_gamma_pdf(cur_g, pr.gbprior_a, pr.gbprior_b);
+          if (resz != 0)
+            ratio += log_gamma_pdf(new_n + pr.nprior_c, pr.nprior_a, pr.nprior_b) - log_gamma_pdf(cur_n + pr.nprior_c, pr.nprior_a, pr.nprior_b);
+          ratio += log_gamma_pdf(-new_c, pr.cprior_a, pr.cprior_b) - log_gamma_pdf(-cur_c, pr.cprior_a, pr.cprior_b) - log(-new_c) + log(-cur_c);
+          const bool acc = log(u01(w4.w)) < ratio;
+          s_flag = acc ? 1 : 0;
+          if (acc) {
+            s.scal[SC_PSELC] = new_c; s.scal[SC_PSELN] = new_n; s.scal[SC_PGBC] = new_g;
+            s.scal[SC_LOGLIK_OLD] = ll_p;
+            s_bufW = bP;
+          }
+        }
+        __syncthreads();
+        if (s_flag) {
+          any_moved = true;
+          for (int t = tid; t < (n - 1) * 6; t += kCBD) s.emis[t] = s.emis_t[t];
+        }
+        __syncthreads();
+      }
+      acc_rates += any_moved ? 1 : 0;
+      // ---- 5. Update_ZB + update_rates
+      const double* bufW = bufs + (size_t)s_bufW * buf_d;
+      messages(s, s.emis, n, n_up, false, tid);
+      for (int d = 1; d < n_down; d++) {
+        const int lo = s.down_off[d], cnt = s.down_off[d + 1] - lo;
+        for (int t = tid; t < cnt; t += kCBD) {
+          const int i = s.down_nodes[lo + t], par = s.parent[i];
+          const int zp = s.Zn[par];
+          const double u = u01(philox4(pr.seed, key, (uint32_t)i, 1u, (uint32_t)m, PA_ST_GBGC).x);
+          const bool mis = (s.flags[i] & PA_F_MISSING) != 0;
+          const bool up = s.upr[i] != 0;
+          int zn = s.Z[i], bn = s.B[i];
+          if (zp != 2) {
+            double lw[6], mx = -CUDART_INF;
+            for (int k = 0; k < 6; k++) {
+              lw[k] = lt_val(s.scal, k % 3, zp, up) + s.back[i * 6 + k];
+              mx = fmax(mx, lw[k]);
+            }
+            for (int k = 0; k < 6; k++) lw[k] = exp(lw[k] - mx);
+            const int nn = categorical_n(lw, 6, u);
+            if (nn >= 0) {
+              zn = nn % 3;
+              if (!mis) bn = nn > 2 ? 1 : 0;
+            }
+          } else {
+            zn = 2;
+            double lw[2] = {s.back[i * 6 + 2], s.back[i * 6 + 5]};
+            const double mx = fmax(lw[0], lw[1]);
+            lw[0] = exp(lw[0] - mx); lw[1] = exp(lw[1] - mx);
+            const int nn = categorical_n(lw, 2, u);
+            if (nn >= 0 && !mis) bn = nn > 0 ? 1 : 0;
+          }
+          s.Zn[i] = (int8_t)zn;
+          s.Bn[i] = (int8_t)bn;
+        }
+        __syncthreads();
+      }
+      load_Pm(s.Zn, s.Bn, bufW);
+      const double ll_new = upward();
+      const double elbo_new = elbo_term(s, s.Zn, s.Bn, P0, bufW, post, n, tid);
+      if (tid == 0) {
+        const double ratio = ll_new - s.scal[SC_LOGLIK] + s.scal[SC_ELBO_OLD] - elbo_new;
+        const bool acc = log(u01(philox4(pr.seed, key, 0u, 2u, (uint32_t)m, PA_ST_GBGC).x)) < ratio;
+        s_flag = acc ? 1 : 0;
+        if (acc) {
+          s.scal[SC_LOGLIK] = ll_new;
+          s.scal[SC_SELC] = s.scal[SC_PSELC]; s.scal[SC_SELN] = s.scal[SC_PSELN]; s.scal[SC_GBC] = s.scal[SC_PGBC];
+          s_bufA = s_bufW;
+        }
+      }
+      __syncthreads();
+      move = s_flag != 0;
+      if (move) {
+        acc_zb++;
+        for (int i = tid; i < n; i += kCBD) { s.Z[i] = s.Zn[i]; s.B[i] = s.Bn[i]; }
+        __syncthreads();
+        if (warp == 0) {  // prior_Z (GBGC/SRC/bpp_c2.cpp:484-498)
+          double pz = 0.0;
+          for (int i = lane; i < n - 1; i += 32) pz += lt_val(s.scal, s.Z[i], s.Z[s.parent[i]], s.upr[i] != 0);
+          pz = warp_sum(pz);
+          if (lane == 0) s.scal[SC_LOGPZ] = pz - s.scal[SC_LOGPZC];
+        }
+      } else {
+        for (int i = tid; i < n; i += kCBD) { s.Zn[i] = s.Z[i]; s.Bn[i] = s.B[i]; }
+        // the partials in the arena now belong to the rejected state; they are not read again before the next accepted state rewrites them
+      }
+      __syncthreads();
+      cur = nxt;
+      if (tid == 0 && L.counters) {
+        atomicAdd(&L.counters[0], (unsigned long long)ni * (unsigned long long)P);
+        atomicAdd(&L.counters[2], 1ull);
+      }
+    }
+    if (tid == 0) {
+      double* hd = L.head + (size_t)ch * 8;
+      hd[0] = s.scal[SC_LOGPZC];
+      hd[1] = (double)acc_rates;
+      hd[2] = (double)acc_zb;
+    }
+  }
+}
+
+size_t chain_smem_bytes(int n_max, int slots_max) {
+  const size_t uni_d = uni_doubles(n_max, slots_max);
+  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N) * 8;
+  b += ((size_t)n_max * 10 + 4) * 2 + (size_t)n_max * 8;  // ten int16 arrays (two with 2 spare entries), eight byte arrays
+  return (b + 63) & ~size_t(63);
+}
+
+}  // namespace
+
+size_t gbgc_chain_scratch_stride(int n_max, int P_max) {
+  const size_t d = (size_t)n_max * 16 + 3 * (size_t)n_max * 80 + 2 * (size_t)n_max * 16 + (size_t)n_max * P_max * 4;
+  return ((d * 8 + (size_t)n_max * P_max * 2) + 255) & ~size_t(255);
+}
+
+// Runs n_chains chains to completion.  Host arrays in, host arrays out (traces [n_chains][5][T], states [n_chains][T][n_max] in the local
+// node order of each element, heads [n_chains][8]); kernel_ms (optional) = the kernel's duration from CUDA events on `stream`.
+int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max,
+                const double* pi, const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
+                const pa_gbgc_params* prm, double* tr_out, uint8_t* zb_out, double* head_out, float* kernel_ms, unsigned long long* counters_out) {
+  if (n_chains <= 0) return PA_OK;
+  cudaError_t err = cudaSetDevice(device);
+  const size_t nc = (size_t)n_chains;
+  const int T = prm->num_burn + prm->num_mcmc;
+  const size_t smem = chain_smem_bytes(n_max, slots_max);
+  int per_sm = 0;
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(gbgc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gbgc_chain_kernel, kCBD, smem);
+  if (err == cudaSuccess && per_sm < 1) {
+    set_error("gbgc_chains: the tree does not fit the chain kernel's shared memory");
+    return PA_ERR_ARG;
+  }
+  const int grid = (int)std::min<size_t>(nc, (size_t)std::max(1, num_sms) * std::max(1, per_sm));
+  const size_t stride = gbgc_chain_scratch_stride(n_max, P_max);
+  const size_t b_in = nc * 8 + 2 * nc * N + 64, b_tr = nc * 5 * T * 8, b_zb = nc * T * n_max, b_head = nc * 8 * 8;
+  unsigned char *d_in = nullptr, *d_scr = nullptr, *d_out = nullptr;
+  if (err == cudaSuccess) err = cudaMalloc(&d_in, b_in);
+  if (err == cudaSuccess) err = cudaMalloc(&d_scr, stride * grid);
+  if (err == cudaSuccess) err = cudaMalloc(&d_out, b_tr + b_head + b_zb + 64);
+  GbgcChainLaunch L;
+  L.blobs = d_blobs; L.blob_off = d_blob_off; L.n_chains = n_chains; L.N = N; L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T;
+  int32_t* di = reinterpret_cast<int32_t*>(d_in);
+  L.chain_elem = di; L.chain_resz = di + nc;
+  int8_t* d8 = reinterpret_cast<int8_t*>(di + 2 * nc);
+  L.fixZ = d8; L.upper = d8 + nc * N;
+  L.prm = *prm;
+  for (int k = 0; k < 4; k++) L.pi[k] = pi[k];
+  for (int k = 0; k < 16; k++) L.Q0[k] = Q0[k];
+  L.scratch = d_scr; L.stride = stride;
+  L.tr = reinterpret_cast<double*>(d_out);
+  L.head = L.tr + nc * 5 * T;
+  L.counters = reinterpret_cast<unsigned long long*>(L.head + nc * 8);
+  L.queue = reinterpret_cast<int*>(L.counters + 4);
+  L.tr_zb = reinterpret_cast<uint8_t*>(L.counters + 8);
+  auto up = [&](const void* dst, const void* src, size_t bytes) {
+    if (err == cudaSuccess) err = cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, stream);
+  };
+  up(L.chain_elem, chain_elem, nc * 4); up(L.chain_resz, chain_resz, nc * 4); up(L.fixZ, fixZ, nc * N); up(L.upper, upper, nc * N);
+  if (err == cudaSuccess) err = cudaMemsetAsync(d_out, 0, b_tr + b_head + 64, stream);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (err == cudaSuccess) err = cudaEventCreate(&e0);
+  if (err == cudaSuccess) err = cudaEventCreate(&e1);
+  if (err == cudaSuccess) {
+    cudaEventRecord(e0, stream);
+    gbgc_chain_kernel<<<grid, kCBD, smem, stream>>>(L);
+    err = cudaGetLastError();
+    cudaEventRecord(e1, stream);
+  }
+  if (err == cudaSuccess) err = cudaMemcpyAsync(tr_out, L.tr, b_tr, cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(head_out, L.head, b_head, cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(zb_out, L.tr_zb, b_zb, cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess && counters_out) err = cudaMemcpyAsync(counters_out, L.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
+  if (err == cudaSuccess && kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (d_in) cudaFree(d_in);
+  if (d_scr) cudaFree(d_scr);
+  if (d_out) cudaFree(d_out);
+  if (err != cudaSuccess) {
+    set_error(std::string("gbgc_chains: ") + cudaGetErrorString(err));
+    return PA_ERR_CUDA;
+  }
+  return PA_OK;
+}
+
+}  // namespace pa

@@ -157,6 +157,9 @@ int gbgc_integrate(int device, cudaStream_t stream, const uint8_t* d_blobs, cons
                    const double* Q0, int n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ, const int8_t* upper,
                    const double* sel_n, const double* sel_c, const double* gbc, double grate, double lrate, double prior_gb, double cons_to_mis,
                    double ncons_to_mis, double* post_out, double* emis_out, double* root_out);  // pa_gbgc.cu
+int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max,
+                const double* pi, const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
+                const pa_gbgc_params* prm, double* tr_out, uint8_t* zb_out, double* head_out, float* kernel_ms, unsigned long long* counters_out);  // pa_gbgc_chain.cu
 void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, int32_t len, int elem_id, ElemPlan& out);
 
 }  // namespace pa
