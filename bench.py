@@ -2,7 +2,7 @@
 """bench.py -- throughput of the PhyloAcc-ST hot path (per-element MCMC) on B200, BASELINE.json's metric:
 element x MCMC-iterations / second.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3] [--full-run]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3|cfg4] [--full-run]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workloads (BASELINE.json configs[0..2]; `config.workload` names the one that ran, cfg2 is the default / headline):
@@ -10,6 +10,9 @@ Workloads (BASELINE.json configs[0..2]; `config.workload` names 
   cfg2  ratite-genome scale: 43 taxa, element lengths lognormal(median 150, sigma 0.8) clipped to [50, 2000] bp, 2048 elements
         resident per GPU per step
   cfg3  240-taxon Zoonomia-shaped tree x 200 bp (deep-tree layout), 592 elements resident per GPU per step
+  cfg4  PhyloAcc-ST-GBGC: 43 taxa x 200 bp simulated with a gBGC bias ~ Gamma(4, 0.8) on 20 % of the branches,
+        2048 elements resident per GPU per step, M0 + M1 + M2 x (200 + 800) iterations (the variant's defaults) through
+        pa_engine_gbgc_run; reference = the unmodified GBGC sources (oracle/_ref/PhyloAcc-GBGC-ref)
 A "step" is one pass of the hot path over one resident batch: every element runs its M0, M1 and M2 chains for BURNIN + MCMC = 1500
 iterations on the device.
 value   = elements x 3 x 1500 / device time of the chain kernel, inputs resident in HBM (CUDA events on the launching stream);
@@ -45,6 +48,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "element×MCMC-iter/sec (PhyloAcc-ST)"
+METRIC_GBGC = "element×MCMC-iter/sec (PhyloAcc-ST-GBGC)"
 UNIT = "element-iterations/s"
 BURNIN, MCMC = 500, 1000  # driver defaults (params.py:130-131 of the reference)
 
@@ -55,7 +59,10 @@ WORKLOADS = {
                  taxa=43, length="cfg2", elems=int(os.environ.get("PA_BENCH_ELEMS", "2048")), ref_elems_per_core=8, ref_chain=(20, 40)),
     "cfg3": dict(name="cfg3: PhyloAcc-ST on a 240-taxon Zoonomia-shaped tree, elements x 200 bp, M0+M1+M2 x (500+1000) iterations",
                  taxa=240, length=200, elems=592, ref_elems_per_core=4, ref_chain=(10, 20)),
+    "cfg4": dict(name="cfg4: PhyloAcc-ST-GBGC, 43 taxa, elements x 200 bp, gBGC bias ~ Gamma(4,0.8) on 20% of the branches, M0+M1+M2 x (200+800) iterations",
+                 taxa=43, length=200, elems=int(os.environ.get("PA_BENCH_ELEMS", "2048")), ref_elems_per_core=3, ref_chain=(20, 40), gbgc=True),
 }
+GBGC_BURNIN, GBGC_MCMC = 200, 800  # defaults of the GBGC binary (GBGC/SRC/main.cpp:52-53)
 FULL_RUN_ELEMS = 280000  # BASELINE.json configs[1]
 
 
@@ -177,6 +184,210 @@ def reference_step(wl, tree, cores, slice_index, n_slices, shape):
         return value, dt, n_done, what
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def gbgc_reference_step(wl, tree, cores, slice_index):
+    """One bounded sample of cfg4 through the unmodified PhyloAcc-ST-GBGC binary (shim build): `cores` concurrent single-thread
+    processes, each with its own ids of one shared input.  Returns (element-iterations/s, seconds, elements done, description)."""
+    from phyloacc_b200 import synth
+
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-GBGC-ref")
+    burn, mc = wl["ref_chain"]
+    n_el = max(8, wl["ref_elems_per_core"] * cores)
+    batch = synth.simulate(tree, C=n_el, length=wl["length"], seed=5150 + slice_index, gbgc={})
+    tmp = tempfile.mkdtemp(prefix="pa_bench_gbgc_")
+    try:
+        if not os.path.exists(ref_bin):
+            return _gbgc_port_step(wl, tree, batch, burn, mc)
+        prm = dict(BURNIN=burn, MCMC=mc, CHAIN=1, ADAPT_FREQ=100, SEED=1 + slice_index, GAPCHAR="-", VERBOSE=0, NUM_THREAD=1)
+        cfgs = []
+        for b in range(cores):
+            ids = list(range(b, n_el, cores))
+            if ids:
+                cfgs.append(synth.write_files(batch, os.path.join(tmp, f"b{b}"), prefix="ref", ids=ids, params=prm))
+        t0 = time.time()
+        procs = []
+        for b, cfg in enumerate(cfgs):
+            lf = open(os.path.join(os.path.dirname(cfg), "log.txt"), "w")
+            procs.append((subprocess.Popen([ref_bin, cfg], stdout=lf, stderr=subprocess.STDOUT), lf))
+        for p, lf in procs:
+            p.wait()
+            lf.close()
+        dt = time.time() - t0
+        n_done = sum(_count_done(os.path.join(os.path.dirname(cfg), "out", "ref_rate_postZ_1.txt")) for cfg in cfgs)
+        what = (f"{n_done} cfg4 elements (43 taxa x {wl['length']} bp, simulated with gBGC) x 3 models x ({burn}+{mc}) iterations, {len(cfgs)} concurrent "
+                f"single-thread processes, {dt:.1f} s wall (unmodified PhyloAcc-ST-GBGC sources + Armadillo/GSL compat shim, g++ -O2)")
+        return n_done * 3 * (burn + mc) / dt, dt, n_done, what
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _gbgc_port_step(wl, tree, batch, burn, mc):
+    """No GBGC reference binary on this box: time the numpy restatement of the chain on one core (cpu_baseline.kind = "port")."""
+    from oracle import frontend as fe, gbgc  # cpu_baseline leg only
+    from phyloacc_b200 import synth
+
+    tmp = tempfile.mkdtemp(prefix="pa_bench_gbgc_port_")
+    try:
+        cfg = synth.write_files(batch, tmp, prefix="ref", params=dict(BURNIN=burn, MCMC=mc, CHAIN=1, GAPCHAR="-"))
+        P = fe.load_params(cfg)
+        otree = fe.parse_mod(P.PHYTREE_FILE)
+        names, X = fe.load_fasta(P.ALIGN_FILE)
+        _, pos = fe.load_bed(P.SEG_FILE)
+        starts, lens = fe.element_layout(pos)
+        model = fe.build_model(otree, P)
+        X = fe.reorder_alignment(otree, names, X)
+        par = gbgc.GbgcParams(num_burn=burn, num_mcmc=mc)
+        t0 = time.time()
+        n_done = 0
+        for c in range(min(batch.C, 2)):
+            el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
+            if el.filter:
+                continue
+            for resZ in (0, 2, 1):
+                gbgc.GbgcChain(np.asarray(otree.Q).reshape(4, 4), otree.pi, el, otree.N, otree.S, resZ, tree.targets, model.upper, par, 1, c * 4 + resZ).run()
+            n_done += 1
+        dt = time.time() - t0
+        return n_done * 3 * (burn + mc) / dt, dt, n_done, f"numpy port of the GBGC chain, {n_done} elements x 3 models x ({burn}+{mc}) iterations on 1 core, {dt:.1f} s"
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def gbgc_cpu_baseline(wl, tree, cores, slices=(1, 2)):
+    have_bin = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-GBGC-ref"))
+    units, secs, what = 0.0, 0.0, ""
+    for sl in slices:
+        v, dt, _, what = gbgc_reference_step(wl, tree, cores, sl)
+        units += v * dt
+        secs += dt
+    return dict(value=units / secs, unit=UNIT, cores=cores if have_bin else 1, kind="reference" if have_bin else "port", shape="procs",
+                sample=f"{len(slices)} samples; last: {what}")
+
+
+def run_gbgc_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    tree = make_workload_tree(wl)
+    cores = os.cpu_count() or 1
+    have_bin = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "PhyloAcc-GBGC-ref"))
+    for k in range(args.warmup):
+        gbgc_reference_step(wl, tree, cores, k)
+    units, secs, what = 0.0, 0.0, ""
+    for k in range(args.steps):
+        v, dt, _, what = gbgc_reference_step(wl, tree, cores, args.warmup + k)
+        units += v * dt
+        secs += dt
+    v = units / secs
+    base = dict(value=v, unit=UNIT, cores=cores if have_bin else 1, kind="reference" if have_bin else "port", shape="procs",
+                sample=f"{args.steps} distinct samples ({args.steps + args.warmup} incl. warm-up); last: {what}")
+    line = {"impl": "reference", "metric": METRIC_GBGC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": secs * 1e3 / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": wl["name"], "sample": base["sample"]}, "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main_gbgc(args, wl, rank, local_rank, world):
+    """cfg4: the PhyloAcc-ST-GBGC chain (pa_engine_gbgc_run).  Same contract as the ST workloads: `value` from the chain kernel's CUDA
+    events (inputs resident), `e2e` = pa_engine_load_alignment + pa_engine_gbgc_run with host buffers, wall clock."""
+    import torch
+    import torch.distributed as dist
+
+    import phyloacc_b200 as pab
+    from phyloacc_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tree = make_workload_tree(wl)
+    batch = synth.simulate(tree, C=wl["elems"], length=wl["length"], seed=4000 + rank, gbgc={})
+    prm = pab.default_params()
+    prm.num_thread = max(1, (os.cpu_count() or 1) // max(world, 1))
+    eng = pab.Engine.create(tree.parent, tree.children, tree.dist, tree.pi, tree.Q, params=prm, outgroup=tree.outgroup, conserve=tree.conserve,
+                            device=local_rank)
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    Xn = torch.from_numpy(batch.X).pin_memory().numpy()
+    eng.load_alignment(Xn, batch.elem_start, batch.elem_len)
+    ids = np.arange(batch.C, dtype=np.int32)
+    T = GBGC_BURNIN + GBGC_MCMC
+    kw = dict(num_burn=GBGC_BURNIN, num_mcmc=GBGC_MCMC, seed=1 + rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks, stop = [], threading.Event()
+    out = None
+    for _ in range(args.warmup):
+        out = eng.gbgc_run(ids, tree.targets, **kw)
+    n_active = int((out["filtered"] == 0).sum())
+    units_per_step = n_active * 3 * T
+    sampler = threading.Thread(target=_clock_sampler, args=(stop, clocks, local_rank), daemon=True)
+    sampler.start()
+    barrier()
+    kern_ms = []
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(k)
+        torch.cuda.synchronize()
+        out = eng.gbgc_run(ids, tree.targets, **kw)  # kernel_ms: CUDA events around the chain kernel on the engine's stream
+        kern_ms.append(out["kernel_ms"])
+    barrier()
+    ms_step = float(np.mean(kern_ms))
+    barrier()
+    t0 = time.time()
+    for k in range(args.steps):
+        eng.load_alignment(Xn, batch.elem_start, batch.elem_len)
+        out = eng.gbgc_run(ids, tree.targets, **kw)
+    barrier()
+    e2e_ms = (time.time() - t0) * 1e3 / args.steps
+    stop.set()
+    sampler.join(timeout=2)
+    t_ms = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+    units = torch.tensor([float(units_per_step)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+        summ = torch.from_numpy(np.ascontiguousarray(out["loglik"])).cuda()
+        gathered = [torch.empty_like(summ) for _ in range(world)]
+        dist.all_gather(gathered, summ)
+    value = float(units[0]) / (float(t_ms[0]) * 1e-3)
+    e2e_value = float(units[0]) / (float(t_ms[1]) * 1e-3)
+    if rank == 0:
+        # algorithmic FMA of one step: 36 per (internal node, pattern) of an upward pass, 48 per (branch, pattern) of a downward pass
+        # (16 message + 16 joint + 16 weighted accumulation), 96 per (branch, class) matrix (80 for P(t) as in §8d + its 16-term emission)
+        fma = 36.0 * out["node_pattern_updates"] + 48.0 * out["branch_pattern_updates"] + 96.0 * out["pt_builds"]
+        achieved = 2.0 * fma / (ms_step * 1e-3) / 1e12
+        peak = pab.fp64_peak_tflops(local_rank, 400)
+        its = max(1, out["chain_iterations"])
+        names = "setup monitor downward init_emissions init_messages pt_builds emissions messages zb_draws upward elbo_mh commit".split()
+        sm_clock = (_clock_summary(clocks)["sm_mhz"] or 1965) * 1e6
+        lr = np.asarray(out["loglik"])
+        line = {"metric": METRIC_GBGC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(t_ms[0]), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "elements_per_gpu_per_step": wl["elems"], "active_elements_rank0": n_active, "iterations_per_chain": T,
+                           "models": 3, "l2": "flushed between timed steps (256 MiB write)",
+                           "parallelism": f"elements sharded over {world} GPU(s), no data-path collective, one all_gather of summaries"},
+                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                             "peak_source": "measured live: register-resident DFMA micro-benchmark (pa_device_fp64_peak)",
+                             "peak_theoretical": 148 * 64 * 2 * sm_clock / 1e12, "algorithmic_fma_per_step": fma, "kernel": "gbgc_chain_kernel",
+                             "phase_kcycles_per_chain_iteration": {n: round(c / its / 1e3, 1) for n, c in zip(names, out["phase_cycles"])}},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.X.nbytes), "d2h_bytes_per_step": int(out["d2h_bytes"]), "steps": args.steps},
+                "gpu_launches": args.steps, "clocks": _clock_summary(clocks),
+                "work": {k: int(out[k]) for k in ("node_pattern_updates", "branch_pattern_updates", "pt_builds", "chain_iterations")},
+                "accelerated_calls_rank0": int(np.sum((lr[:, 1] - lr[:, 0] > 5) & (lr[:, 1] - lr[:, 2] > 5) & (out["filtered"] == 0)))}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = gbgc_cpu_baseline(wl, tree, os.cpu_count() or 1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def _port_step(wl, tree, batch, burn, mc, tmp):
@@ -303,6 +514,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if wl.get("gbgc"):
+        if args.impl == "reference":
+            run_gbgc_reference_arm(args, wl, rank)
+        else:
+            main_gbgc(args, wl, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference_arm(args, wl, rank)
         return

@@ -260,7 +260,11 @@ typedef struct pa_gbgc_results {
   int8_t* trace_z;     /* optional [n_ids][3][T][N] */
   int8_t* trace_b;     /* optional [n_ids][3][T][N] */
   double kernel_ms;    /* duration of the chain kernel (CUDA events) */
-  uint64_t node_pattern_updates, chain_iterations;
+  uint64_t node_pattern_updates, chain_iterations; /* upward passes: internal nodes x patterns; iterations over all chains */
+  uint64_t pt_builds, branch_pattern_updates;      /* (branch, class) P(t) matrices built; downward passes: branches x patterns */
+  uint64_t d2h_bytes;                              /* bytes copied device -> host by this call */
+  uint64_t phase_cycles[12]; /* SM cycles per kernel phase, thread 0 of every CTA summed (setup, monitor, downward pass, emissions, messages,
+                                P(t) builds, proposal emissions, proposal messages, (Z, B) draws, upward pass, ELBO + MH, commit) */
 } pa_gbgc_results;
 /* targets: node ids of TARGETSPECIES (the only tips free to accelerate under M1).  model_mask: bit m set = run model m. */
 int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,

@@ -95,7 +95,8 @@ class PaGbgcResults(C.Structure):
     _fields_ = [("n_ids", C.c_int32), ("N", C.c_int32), ("T", C.c_int32), ("filtered", _u8p), ("loglik", _f64p), ("loglik_max", _f64p),
                 ("med", _f64p), ("post_b", _f64p), ("post_z", _f64p), ("max_z", _i8p), ("max_b", _i8p), ("accept", _i32p),
                 ("trace", _f64p), ("trace_z", _i8p), ("trace_b", _i8p), ("kernel_ms", C.c_double),
-                ("node_pattern_updates", C.c_uint64), ("chain_iterations", C.c_uint64)]
+                ("node_pattern_updates", C.c_uint64), ("chain_iterations", C.c_uint64), ("pt_builds", C.c_uint64),
+                ("branch_pattern_updates", C.c_uint64), ("d2h_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 12)]
 
 
 class PaCounters(C.Structure):
@@ -479,7 +480,9 @@ class Engine:
                 setattr(r, k, out[k].ctypes.data_as(t))
         _check(self._lib.pa_engine_gbgc_run(self._h, ids.ctypes.data_as(_i32p), n, targets.ctypes.data_as(_i32p), len(targets), C.byref(prm),
                                             model_mask, C.byref(r)))
-        out.update(kernel_ms=float(r.kernel_ms), node_pattern_updates=int(r.node_pattern_updates), chain_iterations=int(r.chain_iterations))
+        out.update(kernel_ms=float(r.kernel_ms), node_pattern_updates=int(r.node_pattern_updates), chain_iterations=int(r.chain_iterations), pt_builds=int(r.pt_builds),
+                   branch_pattern_updates=int(r.branch_pattern_updates), d2h_bytes=int(r.d2h_bytes),
+                   phase_cycles=[int(x) for x in r.phase_cycles])
         return out
 
     def trace(self, i: int, model: int):

@@ -31,6 +31,9 @@ namespace pa {
 namespace {
 
 constexpr int kCBD = 128;
+// phase clock (thread 0): adds the cycles since the previous mark to phase k
+#define PH(k) do { if (tid == 0) { const long long t__ = clock64(); s_ph[k] += t__ - s_t0; s_t0 = t__; } } while (0)
+enum { PH_SETUP = 0, PH_MONITOR, PH_DOWN, PH_INIT_EMIS, PH_INIT_MSG, PH_BUILD, PH_EMIS, PH_MSG, PH_DRAW, PH_UP, PH_ELBO, PH_COMMIT };
 #define PA_ST_GBGC 4u
 
 struct GbgcChainLaunch {
@@ -48,7 +51,8 @@ struct GbgcChainLaunch {
   double* tr;       // [n_chains][5][T]: log P(X | Z, B, r), log P(X, Z, B, r), conserved / accelerated selection, gBGC bias
   uint8_t* tr_zb;   // [n_chains][T][n_max] local node order: Z | B << 2
   double* head;     // [n_chains][8]: log P(constraints), accepted rate sweeps, accepted iterations
-  unsigned long long* counters;  // [4]: node-pattern updates, P(t) builds, chain iterations
+  unsigned long long* counters;  // [16]: node-pattern updates of the upward passes, (branch, class) P(t) builds, chain iterations, branch-pattern updates of the
+                                 // downward passes, then SM cycles per phase (thread 0 of every CTA)
 };
 
 // doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | per-warp pair accumulators [4][n_max][16]
@@ -211,6 +215,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_chain, s_flag, s_bufA, s_bufW;
+  __shared__ long long s_ph[12], s_t0;
+  __shared__ int s_ntask, s_nbranch;
   __shared__ double s_pi[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_max = L.n_max, slots_max = L.slots_max, N = L.N, T = L.T;
@@ -258,6 +264,8 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
   int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)n_max * L.P_max * 4);
   const pa_gbgc_params& pr = L.prm;
   if (tid < 4) s_pi[tid] = L.pi[tid];
+  if (tid < 12) s_ph[tid] = 0;
+  if (tid == 0) s_t0 = clock64();
 
   for (;;) {
     __syncthreads();
@@ -299,6 +307,14 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       s_bufA = 0; s_bufW = 0;
     }
     __syncthreads();
+    if (warp == 0) {  // work counters: (branch, class) matrices per rate move, non-missing branches
+      int nt = 0, nb = 0;
+      for (int i = lane; i < n - 1; i += 32)
+        if (!(s.flags[i] & PA_F_MISSING)) { nb++; nt += s.fix[i] == 1 ? 3 : 5; }
+      nt = __reduce_add_sync(0xffffffffu, nt);
+      nb = __reduce_add_sync(0xffffffffu, nb);
+      if (lane == 0) { s_ntask = nt; s_nbranch = nb; }
+    }
     TreeSmem ts{s.child, s.flags, s.tiprow, s.su, s.slot, s.intidx};
     double* stack = s.uni;
     // log P(constraints): the 6-state pass of initMCMC with "- log 2" per message (GBGC/SRC/bpp_c.cpp:232-254)
@@ -336,6 +352,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       }
     }
     __syncthreads();
+    PH(PH_SETUP);
     bool move = true;
     int cur = 0, nxt = 0;  // expected-pair buffers: post_cur / post_next
     int acc_rates = 0, acc_zb = 0;
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
         }
       }
       for (int i = tid; i < n; i += kCBD) trzb[(size_t)m * n_max + i] = (uint8_t)(s.Z[i] | (s.B[i] << 2));
+      PH(PH_MONITOR);
       if (m == T - 1) break;
       // ---- 2. expected (child, parent) pairs at the current state (only when the state moved): parents before children, an internal
       //         node's partial is overwritten by the posterior of its base; per-warp accumulators, no block barrier inside the pass
@@ -469,13 +487,16 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
           pn[t] = ((s.uni[t] + s.uni[(size_t)n_max * 16 + t]) + s.uni[(size_t)2 * n_max * 16 + t]) + s.uni[(size_t)3 * n_max * 16 + t];
         __syncthreads();
       }
+      PH(PH_DOWN);
       if (m == 0) cur = nxt;
       const double* post = postb + (size_t)cur * n_max * 16;
       // ---- 3. initial_prob_back: emissions of the six classes, messages, ELBO at the current classes
       const double* bufA = bufs + (size_t)s_bufA * buf_d;
       emissions(s, L, s.emis, nullptr, P0, bufA, post, n, 0, tid);
       __syncthreads();
+      PH(PH_INIT_EMIS);
       messages(s, s.emis, n, n_up, false, tid);
+      PH(PH_INIT_MSG);
       const double elbo_old = elbo_term(s, s.Z, s.B, P0, bufA, post, n, tid);
       if (tid == 0) {
         s.scal[SC_LOGLIK_OLD] = s.back[root * 6];
@@ -501,10 +522,14 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
         const int bP = (bA != 0 && bW != 0) ? 0 : ((bA != 1 && bW != 1) ? 1 : 2);
         double* bufP = bufs + (size_t)bP * buf_d;
         __syncthreads();
+        PH(PH_ELBO);
         build_logs(s, L, ev, P0, bufP, new_c, new_n, new_g, n, 1, tid);
+        PH(PH_BUILD);
         emissions(s, L, s.emis_t, s.emis, P0, bufP, post, n, 1, tid);
         __syncthreads();
+        PH(PH_EMIS);
         messages(s, s.emis_t, n, n_up, false, tid);
+        PH(PH_MSG);
         if (tid == 0) {
           const double ll_p = s.back[root * 6];
           double ratio = ll_p - s.scal[SC_LOGLIK_OLD] + log_gamma_pdf(new_g, pr.gbprior_a, pr.gbprior_b) - log_gamma_pdf(cur_g, pr.gbprior_a, pr.gbprior_b);
@@ -529,7 +554,9 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       acc_rates += any_moved ? 1 : 0;
       // ---- 5. Update_ZB + update_rates
       const double* bufW = bufs + (size_t)s_bufW * buf_d;
+      PH(PH_COMMIT);
       messages(s, s.emis, n, n_up, false, tid);
+      PH(PH_MSG);
       for (int d = 1; d < n_down; d++) {
         const int lo = s.down_off[d], cnt = s.down_off[d + 1] - lo;
         for (int t = tid; t < cnt; t += kCBD) {
@@ -564,8 +591,10 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
         }
         __syncthreads();
       }
+      PH(PH_DRAW);
       load_Pm(s.Zn, s.Bn, bufW);
       const double ll_new = upward();
+      PH(PH_UP);
       const double elbo_new = elbo_term(s, s.Zn, s.Bn, P0, bufW, post, n, tid);
       if (tid == 0) {
         const double ratio = ll_new - s.scal[SC_LOGLIK] + s.scal[SC_ELBO_OLD] - elbo_new;
@@ -578,6 +607,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
         }
       }
       __syncthreads();
+      PH(PH_ELBO);
       move = s_flag != 0;
       if (move) {
         acc_zb++;
@@ -595,9 +625,12 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       }
       __syncthreads();
       cur = nxt;
+      PH(PH_COMMIT);
       if (tid == 0 && L.counters) {
         atomicAdd(&L.counters[0], (unsigned long long)ni * (unsigned long long)P);
+        atomicAdd(&L.counters[1], 3ull * (unsigned long long)s_ntask);
         atomicAdd(&L.counters[2], 1ull);
+        if (move) atomicAdd(&L.counters[3], (unsigned long long)s_nbranch * (unsigned long long)P);
       }
     }
     if (tid == 0) {
@@ -607,6 +640,8 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       hd[2] = (double)acc_zb;
     }
   }
+  if (tid == 0 && L.counters)
+    for (int k = 0; k < 12; k++) atomicAdd(&L.counters[4 + k], (unsigned long long)s_ph[k]);
 }
 
 size_t chain_smem_bytes(int n_max, int slots_max) {
@@ -642,11 +677,11 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   }
   const int grid = (int)std::min<size_t>(nc, (size_t)std::max(1, num_sms) * std::max(1, per_sm));
   const size_t stride = gbgc_chain_scratch_stride(n_max, P_max);
-  const size_t b_in = nc * 8 + 2 * nc * N + 64, b_tr = nc * 5 * T * 8, b_zb = nc * T * n_max, b_head = nc * 8 * 8;
+  const size_t b_in = nc * 8 + 2 * nc * N + 64, b_tr = nc * 5 * T * 8, b_zb = nc * T * n_max, b_head = nc * 8 * 8, b_ctr = 18 * 8;
   unsigned char *d_in = nullptr, *d_scr = nullptr, *d_out = nullptr;
   if (err == cudaSuccess) err = cudaMalloc(&d_in, b_in);
   if (err == cudaSuccess) err = cudaMalloc(&d_scr, stride * grid);
-  if (err == cudaSuccess) err = cudaMalloc(&d_out, b_tr + b_head + b_zb + 64);
+  if (err == cudaSuccess) err = cudaMalloc(&d_out, b_tr + b_head + b_ctr + b_zb);
   GbgcChainLaunch L;
   L.blobs = d_blobs; L.blob_off = d_blob_off; L.n_chains = n_chains; L.N = N; L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T;
   int32_t* di = reinterpret_cast<int32_t*>(d_in);
@@ -660,13 +695,13 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   L.tr = reinterpret_cast<double*>(d_out);
   L.head = L.tr + nc * 5 * T;
   L.counters = reinterpret_cast<unsigned long long*>(L.head + nc * 8);
-  L.queue = reinterpret_cast<int*>(L.counters + 4);
-  L.tr_zb = reinterpret_cast<uint8_t*>(L.counters + 8);
+  L.queue = reinterpret_cast<int*>(L.counters + 16);
+  L.tr_zb = reinterpret_cast<uint8_t*>(L.counters + 18);
   auto up = [&](const void* dst, const void* src, size_t bytes) {
     if (err == cudaSuccess) err = cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, stream);
   };
   up(L.chain_elem, chain_elem, nc * 4); up(L.chain_resz, chain_resz, nc * 4); up(L.fixZ, fixZ, nc * N); up(L.upper, upper, nc * N);
-  if (err == cudaSuccess) err = cudaMemsetAsync(d_out, 0, b_tr + b_head + 64, stream);
+  if (err == cudaSuccess) err = cudaMemsetAsync(d_out, 0, b_tr + b_head + b_ctr, stream);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (err == cudaSuccess) err = cudaEventCreate(&e0);
   if (err == cudaSuccess) err = cudaEventCreate(&e1);
@@ -679,7 +714,7 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   if (err == cudaSuccess) err = cudaMemcpyAsync(tr_out, L.tr, b_tr, cudaMemcpyDeviceToHost, stream);
   if (err == cudaSuccess) err = cudaMemcpyAsync(head_out, L.head, b_head, cudaMemcpyDeviceToHost, stream);
   if (err == cudaSuccess) err = cudaMemcpyAsync(zb_out, L.tr_zb, b_zb, cudaMemcpyDeviceToHost, stream);
-  if (err == cudaSuccess && counters_out) err = cudaMemcpyAsync(counters_out, L.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+  if (err == cudaSuccess && counters_out) err = cudaMemcpyAsync(counters_out, L.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
   if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
   if (err == cudaSuccess && kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
   if (e0) cudaEventDestroy(e0);

@@ -242,7 +242,7 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
   std::vector<double> tr((size_t)nc * 5 * T), head((size_t)nc * 8);
   std::vector<uint8_t> zb((size_t)nc * T * n_max);
   float ms = 0;
-  unsigned long long ctr[4] = {0, 0, 0, 0};
+  unsigned long long ctr[16] = {0};
   {
     PA_NVTX_RANGE("gbgc_chains");
     const int rc = gbgc_chains(device, stream, num_sms, d_blobs, d_blob_off, N, n_max, slots_max, P_max, model.tree.pi, model.tree.Q, nc, l_elem.data(),
@@ -252,6 +252,10 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
   out->kernel_ms = ms;
   out->node_pattern_updates = ctr[0];
   out->chain_iterations = ctr[2];
+  out->pt_builds = ctr[1];
+  out->branch_pattern_updates = ctr[3];
+  out->d2h_bytes = (uint64_t)(tr.size() * 8 + head.size() * 8 + zb.size());
+  for (int k = 0; k < 12; k++) out->phase_cycles[k] = ctr[4 + k];
   PA_NVTX_RANGE("gbgc_summaries");
   const int burn = prm->num_burn, mcmc = prm->num_mcmc;
   auto summarise = [&](int k) {

@@ -195,6 +195,25 @@ def _transition_probs(Q: np.ndarray, t: np.ndarray) -> np.ndarray:
     return np.clip(P, 0.0, 1.0)
 
 
+def _gbgc_probs(Q: np.ndarray, sel: np.ndarray, bias: np.ndarray, t: float) -> np.ndarray:
+    """P(t) [c, 4, 4] under the GC-biased model of PhyloAcc-ST-GBGC for per-element selection coefficients and biases: every
+    off-diagonal rate i -> j is multiplied by f(s + B_ij), f(x) = x / (1 - exp(-x)), B = +b for weak -> strong (A, T -> C, G), -b for
+    strong -> weak (BPP_C::getRate, src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:13-30)."""
+    strong = np.array([0, 1, 1, 0])
+    sign = (strong[None, :] - strong[:, None]).astype(np.float64)  # [i, j]: +1 weak -> strong, -1 strong -> weak
+    x = sel[:, None, None] + bias[:, None, None] * sign[None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = np.where(np.abs(x) < 1e-12, 1.0, x / (1.0 - np.exp(-x)))
+    Qs = Q[None] * f
+    idx = np.arange(4)
+    Qs[:, idx, idx] = 0.0
+    Qs[:, idx, idx] = -Qs.sum(axis=2)
+    lam, U = np.linalg.eig(Qs)
+    E = np.exp(lam * t)
+    P = np.einsum("cik,ck,ckj->cij", U, E, np.linalg.inv(U)).real
+    return np.clip(P, 0.0, 1.0)
+
+
 @dataclasses.dataclass
 class SynthBatch:
     tree: SynthTree
@@ -213,9 +232,12 @@ class SynthBatch:
 
 def simulate(tree: SynthTree, C: int = 500, length=200, seed: int = 1, gap_frac: float = 0.01,
              missing_frac: float = 0.03, ambig_frac: float = 0.0, lengths: Optional[Sequence[int]] = None,
-             chunk: int = 20000) -> SynthBatch:
+             chunk: int = 20000, gbgc: Optional[dict] = None) -> SynthBatch:
     """Simulate ``C`` elements.  ``length`` is an int (fixed) or the string ``"cfg2"`` for
-    lognormal(median 150, sigma 0.8) clipped to [50, 2000]."""
+    lognormal(median 150, sigma 0.8) clipped to [50, 2000].
+    ``gbgc`` switches to the GC-biased model: dict(shape=4, scale=0.8, frac=0.2) draws a bias b ~ Gamma(shape, scale)
+    per element acting on a random `frac` of the branches; conserved / accelerated branches then carry SELECTION coefficients
+    (-Gamma(5, 0.4) and Gamma(5, 0.4) - 2, the variant's priors) instead of rate multipliers."""
     rng = np.random.default_rng(seed)
     S, N = tree.S, tree.N
     if lengths is not None:
@@ -261,6 +283,11 @@ def simulate(tree: SynthTree, C: int = 500, length=200, seed: int = 1, gap_frac:
     pick = rng.choice(in_nodes, size=C)
     acc_node[scenario == 2] = pick[scenario == 2]
 
+    if gbgc is not None:
+        g_bias = rng.gamma(gbgc.get("shape", 4.0), gbgc.get("scale", 0.8), size=C)
+        g_on = rng.random((C, N)) < gbgc.get("frac", 0.2)
+        g_selc = -rng.gamma(5.0, 0.4, size=C)
+        g_seln = rng.gamma(5.0, 0.4, size=C) - 2.0
     X = np.empty((S, G), dtype=np.uint8)
     site_elem_all = np.repeat(np.arange(C, dtype=np.int64), elem_len)
     pi_cdf = np.cumsum(tree.pi)
@@ -296,8 +323,11 @@ def simulate(tree: SynthTree, C: int = 500, length=200, seed: int = 1, gap_frac:
                 if cn >= 0 and clade_masks[cn][n]:
                     is_acc |= acc_node[e0:e1] == cn
             rate[is_acc] = n_rate[e0:e1][is_acc]
-            E = np.exp(np.multiply.outer(rate * tree.dist[n], lam))  # [c,4]
-            P = np.einsum("ik,ck,kj->cij", U, E, Uinv).clip(0.0, 1.0)  # [c,4,4] parent i -> child j
+            if gbgc is not None:
+                P = _gbgc_probs(tree.Q, np.where(is_acc, g_seln[e0:e1], g_selc[e0:e1]), np.where(g_on[e0:e1, n], g_bias[e0:e1], 0.0), float(tree.dist[n]))
+            else:
+                E = np.exp(np.multiply.outer(rate * tree.dist[n], lam))  # [c,4]
+                P = np.einsum("ik,ck,kj->cij", U, E, Uinv).clip(0.0, 1.0)  # [c,4,4] parent i -> child j
             cdf = np.cumsum(P, axis=2)
             row = cdf[site_elem, states[par]]  # [ng,4]
             u = rng.random(ng) * row[:, 3]

@@ -26,4 +26,6 @@ out = eng.gbgc_run(list(range(C)), tree.targets, num_burn=burn, num_mcmc=mcmc, s
 dt = time.time() - t
 its = out["chain_iterations"]
 print(f"chains {3 * C} iterations {its} kernel {out['kernel_ms']:.1f} ms  wall {dt:.2f} s  -> {its / 3 / (out['kernel_ms'] / 1e3):.0f} element-iterations/s (kernel)")
+names = "setup monitor down init_emis init_msg build emis msg draw up elbo commit".split()
+print("cycles per chain-iteration:", ", ".join(f"{n} {c / max(its, 1) / 1e3:.1f} k" for n, c in zip(names, out["phase_cycles"])), "| total %.1f k" % (sum(out["phase_cycles"]) / max(its, 1) / 1e3))
 print("loglik", out["loglik"][:2], "med", out["med"][0], "accept", out["accept"][0])
