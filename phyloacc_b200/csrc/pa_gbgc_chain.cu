@@ -55,22 +55,23 @@ struct GbgcChainLaunch {
                                  // downward passes, then SM cycles per phase (thread 0 of every CTA)
 };
 
-// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | per-warp pair accumulators [4][n_max][16]
+// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | per-warp pair accumulators [4][n_max][16] |
+// power basis of the P(t) builds [6][20][16]
 __host__ __device__ inline size_t uni_doubles(int n_max, int slots_max) {
-  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = (size_t)4 * n_max * 16;
-  return a > b ? a : b;
+  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = (size_t)4 * n_max * 16, c = 6 * 20 * 16;
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 struct Sh {  // shared-memory views of one chain
-  double *Pm, *uni, *red, *emis, *emis_t, *back, *Qc, *scal;
-  int* stack_sc;
+  double *Pm, *uni, *red, *emis, *emis_t, *back, *Qc, *scal, *msg, *lsum, *pw, *mu;
+  int *stack_sc, *msc;
   int16_t *child, *tiprow, *su, *intidx, *parent, *up_nodes, *up_off, *down_nodes, *down_off;
   uint8_t *flags, *fix, *upr;
   int8_t *slot, *Z, *B, *Zn, *Bn;
 };
 
 enum { SC_LG0 = 0, SC_LG1, SC_LL0, SC_LL1, SC_SELC, SC_SELN, SC_GBC, SC_PSELC, SC_PSELN, SC_PGBC, SC_LOGLIK, SC_LOGLIK_OLD, SC_ELBO_OLD, SC_LOGPZ,
-       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_N };
+       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_G, SC_L, SC_KC, SC_KN, SC_KG, SC_N };
 
 // log TM_Int (child class a, parent class j) of a branch (GBGC/SRC/bpp.hpp:284-316): (0,0) = 1-g, (1,0) = g, (1,1) = 1-l, (2,1) = l, (2,2) = 1;
 // on the outgroup lineage (1,1) = 1 and (2,1) = 0
@@ -113,6 +114,88 @@ __device__ void messages(const Sh& s, const double* src, int n, int n_up, bool i
     }
     __syncthreads();
   }
+}
+
+// linear T of a branch: j = parent class
+__device__ __forceinline__ double lt_lin(const double* scal, int a, int j, bool up) {
+  if (j == 0) return a == 0 ? 1.0 - scal[SC_G] : (a == 1 ? scal[SC_G] : 0.0);
+  if (j == 1) return a == 1 ? (up ? 1.0 : 1.0 - scal[SC_L]) : (a == 2 ? (up ? 0.0 : scal[SC_L]) : 0.0);
+  return a == 2 ? 1.0 : 0.0;
+}
+
+// The same 6-state upward pass in LINEAR space: per node the six class weights exp(emission - max) times the children's messages,
+// renormalised by a power of two; the log of the total travels as (sum of the maxima) + (sum of the exponents) ln 2.  No transcendental
+// inside the level loop (6 exp per node up front, in parallel; one log at the root), the levels run on one warp without block barriers.
+// s.back receives the LINEAR weights w[node][6] (what the top-down draws need), *ll = log_prob_back[root][0].
+// Returns false when a finite emission underflows against its node's maximum (> 700 nats apart) or the root's class 0 vanishes: the
+// caller then repeats the pass in log space (messages()).
+__device__ bool messages_lin(const Sh& s, const double* src, int n, int n_up, int tid, double* ll) {
+  bool bad = false;
+  for (int i = tid; i < n; i += kCBD) {
+    double e[6], mE = -CUDART_INF;
+    const bool is_root = i == n - 1;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { e[k] = is_root ? 0.0 : src[i * 6 + k]; mE = fmax(mE, e[k]); }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const double d = e[k] - mE;
+      if (d < -700.0 && e[k] > -CUDART_INF) bad = true;
+      e[k] = exp(d);
+      s.back[i * 6 + k] = e[k];
+    }
+    if (!(mE > -CUDART_INF)) bad = true;
+    s.lsum[i] = mE;
+    s.msc[i] = 0;
+    if (s.child[2 * i] < 0) {  // tips: their messages are final
+      const bool up = s.upr[i] != 0;
+      const double a0 = e[0] + e[3], a1 = e[1] + e[4], a2 = e[2] + e[5];
+      s.msg[i * 3] = lt_lin(s.scal, 0, 0, up) * a0 + lt_lin(s.scal, 1, 0, up) * a1;
+      s.msg[i * 3 + 1] = lt_lin(s.scal, 1, 1, up) * a1 + lt_lin(s.scal, 2, 1, up) * a2;
+      s.msg[i * 3 + 2] = a2;
+    }
+  }
+  if (__syncthreads_or(bad ? 1 : 0)) return false;
+  int bad_w = 0;
+  if (tid < 32) {
+    for (int h = 1; h < n_up; h++) {
+      const int lo = s.up_off[h], cnt = s.up_off[h + 1] - lo;
+      for (int t = tid; t < cnt; t += 32) {
+        const int i = s.up_nodes[lo + t];
+        const int c0 = s.child[2 * i], c1 = s.child[2 * i + 1];
+        if (c0 < 0) continue;
+        double w[6], mx = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          w[k] = (s.back[i * 6 + k] * s.msg[c0 * 3 + k % 3]) * s.msg[c1 * 3 + k % 3];
+          mx = fmax(mx, w[k]);
+        }
+        int ex = 0;
+        if (mx > 0.0) {
+          ex = ilogb(mx);
+#pragma unroll
+          for (int k = 0; k < 6; k++) w[k] = scalbn(w[k], -ex);
+        } else {
+          bad_w = 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) s.back[i * 6 + k] = w[k];
+        s.msc[i] = (ex + s.msc[c0]) + s.msc[c1];
+        s.lsum[i] = (s.lsum[i] + s.lsum[c0]) + s.lsum[c1];
+        const bool up = s.upr[i] != 0;
+        const double a0 = w[0] + w[3], a1 = w[1] + w[4], a2 = w[2] + w[5];
+        s.msg[i * 3] = lt_lin(s.scal, 0, 0, up) * a0 + lt_lin(s.scal, 1, 0, up) * a1;
+        s.msg[i * 3 + 1] = lt_lin(s.scal, 1, 1, up) * a1 + lt_lin(s.scal, 2, 1, up) * a2;
+        s.msg[i * 3 + 2] = a2;
+      }
+      __syncwarp();
+    }
+    if (tid == 0) {
+      const int r = n - 1;
+      if (!(s.back[r * 6] > 0.0)) bad_w = 1;
+      else *ll = (log(s.back[r * 6]) + (double)s.msc[r] * 0.69314718055994530942) + s.lsum[r];
+    }
+  }
+  return !__syncthreads_or(bad_w);
 }
 
 __device__ __forceinline__ const double* class_log(const double* P0, const double* buf, int i, int k) {
@@ -165,14 +248,44 @@ __device__ double elbo_term(const Sh& s, const int8_t* Z, const int8_t* B, const
   return block_sum(acc, s.red, tid, kCBD);
 }
 
-// log P(t) of classes k_lo..5 of every branch at (sel_c, sel_n, gbc) into P0 (class 0) / buf (classes 1..5); row-major P(i -> j)
+// log P(t) of classes k_lo..5 of every branch at (sel_c, sel_n, gbc) into P0 (class 0) / buf (classes 1..5); row-major P(i -> j).
+// Uniformisation with a power basis SHARED by the branches of a class: with mu = max |Q_ii| and A = I + Q / mu (stochastic), the powers
+// A^1..A^19 are built once per class (16 lanes per class, one entry each), and a branch of length t is
+//   P(t) = [ sum_j Poisson(j; x) A^j ]^(2^q),  x = mu t / 2^q <= 1/2,
+// i.e. a linear combination of the stored powers (16 FMA per term, as many terms as the Poisson tail needs) and q squarings -- against
+// 19 + q matrix products per branch before.  Every term is non-negative: no cancellation, nothing depends on the spectrum.
+constexpr int kPow = 19;
+// emis_dst != nullptr: the emissions of the built classes are taken from the matrices while they are in registers (the proposal's
+// getEmission_update), every other entry (class 0, missing branches, forbidden classes) is copied from emis_base.
 __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView& ev, double* P0, double* buf, double sel_c, double sel_n, double gbc, int n,
-                           int k_lo, int tid) {
+                           int k_lo, int tid, double* emis_dst = nullptr, const double* emis_base = nullptr, const double* post = nullptr) {
+  if (emis_dst)
+    for (int t = tid; t < 6 * (n - 1); t += kCBD) {
+      const int i = t / 6, k = t - 6 * i;
+      if ((s.flags[i] & PA_F_MISSING) || k < k_lo) emis_dst[t] = emis_base[t];
+      else if (s.fix[i] == 1 && k % 3 == 2) emis_dst[t] = -CUDART_INF;
+    }
+  const double l_b0 = log(1.0 - L.prm.gbprior_c), l_b1 = log(L.prm.gbprior_c), l_c = log(1.0 - L.prm.cons_to_mis), l_n = log(1.0 - L.prm.ncons_to_mis);
   if (tid >= k_lo && tid < 6) {
     double Q[16];
     gbgc_rate(L.Q0, tid % 3 == 0 ? 0.0 : (tid % 3 == 1 ? sel_c : sel_n), tid >= 3 ? gbc : 0.0, Q);
+    const double mu = fmax(fmax(-Q[0], -Q[5]), fmax(-Q[10], -Q[15]));
+    s.mu[tid] = mu;
 #pragma unroll
-    for (int e = 0; e < 16; e++) s.Qc[tid * 16 + e] = Q[e];
+    for (int e = 0; e < 16; e++) s.pw[(tid * (kPow + 1) + 1) * 16 + e] = (mu > 0.0 ? Q[e] / mu : 0.0) + (((e >> 2) == (e & 3)) ? 1.0 : 0.0);  // A^1
+  }
+  __syncthreads();
+  if (tid < 96) {  // 16 lanes per class: lane (r, c) owns entry [r][c] of every power
+    const int k = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
+    const double* A = s.pw + (k * (kPow + 1) + 1) * 16;
+    const double a0 = A[c], a1 = A[4 + c], a2 = A[8 + c], a3 = A[12 + c];
+    for (int j = 2; j <= kPow; j++) {
+      if (k >= k_lo) {
+        const double* prev = s.pw + (k * (kPow + 1) + j - 1) * 16 + r * 4;
+        s.pw[(k * (kPow + 1) + j) * 16 + e] = ((prev[0] * a0 + prev[1] * a1) + prev[2] * a2) + prev[3] * a3;
+      }
+      __syncwarp();
+    }
   }
   __syncthreads();
   const int nk = 6 - k_lo;
@@ -180,15 +293,45 @@ __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView
     const int i = t / nk, k = k_lo + (t - nk * i);
     if (s.flags[i] & PA_F_MISSING) continue;
     if (s.fix[i] == 1 && k % 3 == 2) continue;  // never read (update_cache_TM's own skip, GBGC/SRC/bpp_c.cpp:1655)
-    double Q[16], P16[16];
+    double P16[16];
+    const double mu = s.mu[k], tt = ev.dist[i];
+    if (!(mu > 0.0) || !(tt > 0.0)) {
 #pragma unroll
-    for (int e = 0; e < 16; e++) Q[e] = s.Qc[k * 16 + e];
-    expm_uniformised(Q, ev.dist[i], P16);
+      for (int e = 0; e < 16; e++) P16[e] = ((e >> 2) == (e & 3)) ? 1.0 : 0.0;
+    } else {
+      int ksq = 0;
+      double x = mu * tt;
+      while (x > 0.5 && ksq < 60) { x *= 0.5; ksq++; }
+      double wgt = exp(-x);
+#pragma unroll
+      for (int e = 0; e < 16; e++) P16[e] = ((e >> 2) == (e & 3)) ? wgt : 0.0;
+      const double* pw = s.pw + (size_t)k * (kPow + 1) * 16;
+      for (int j = 1; j <= kPow; j++) {
+        wgt *= x / j;
+        const double* Aj = pw + j * 16;
+#pragma unroll
+        for (int e = 0; e < 16; e++) P16[e] += wgt * Aj[e];
+        if (wgt < 1e-19) break;  // x <= 1/2: the remaining Poisson tail is below 1e-19 of a row sum
+      }
+      double nxt[16];
+      for (int q = 0; q < ksq; q++) {
+        matmul4(P16, P16, nxt);
+#pragma unroll
+        for (int e = 0; e < 16; e++) P16[e] = nxt[e];
+      }
+    }
     double* dst = k == 0 ? P0 + (size_t)i * 16 : buf + ((size_t)i * 5 + (k - 1)) * 16;
 #pragma unroll
-    for (int e = 0; e < 16; e++) dst[e] = log(P16[e]);
+    for (int e = 0; e < 16; e++) { P16[e] = log(P16[e]); dst[e] = P16[e]; }
+    if (emis_dst) emis_dst[i * 6 + k] = pair_dot(P16, post + (size_t)i * 16) + (k < 3 ? l_b0 : l_b1) + (k % 3 == 1 ? l_c : l_n);
   }
   __syncthreads();
+}
+
+// log of the Gamma(a, scale b) density at x with K = lgamma(a) + log(b) precomputed (the reference takes log(gsl_ran_gamma_pdf(x, a, b)))
+__device__ __forceinline__ double lgp(double x, double a, double b, double K) {
+  if (!(x > 0.0)) return (x == 0.0 && a == 1.0) ? -K : -CUDART_INF;
+  return (a == 1.0 ? 0.0 : (a - 1.0) * log(x / b)) - x / b - K;
 }
 
 __device__ __forceinline__ int categorical_n(const double* w, int K, double u) {
@@ -234,6 +377,11 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
     s.back = d; d += (size_t)n_max * 6;
     s.Qc = d; d += 96;
     s.scal = d; d += SC_N;
+    s.msg = d; d += (size_t)n_max * 3;
+    s.lsum = d; d += n_max;
+    s.pw = s.uni;  // the power basis of build_logs lives in the phase-shared region (no pruning pass runs during the rate moves)
+    s.mu = d; d += 6;
+    s.msc = reinterpret_cast<int*>(d); d += (n_max + 1) / 2;
     int16_t* h16 = reinterpret_cast<int16_t*>(d);
     s.child = h16; h16 += 2 * n_max;
     s.tiprow = h16; h16 += n_max;
@@ -304,6 +452,10 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       s.scal[SC_LG0] = log(1.0 - pr.grate); s.scal[SC_LG1] = log(pr.grate);
       s.scal[SC_LL0] = log(1.0 - pr.lrate); s.scal[SC_LL1] = log(pr.lrate);
       s.scal[SC_SELC] = pr.sel_c0; s.scal[SC_SELN] = pr.sel_n0; s.scal[SC_GBC] = pr.gbc0;
+      s.scal[SC_G] = pr.grate; s.scal[SC_L] = pr.lrate;
+      // constants of the three log Gamma densities: lgamma(a) + log(b)
+      s.scal[SC_KC] = lgamma(pr.cprior_a) + log(pr.cprior_b); s.scal[SC_KN] = lgamma(pr.nprior_a) + log(pr.nprior_b);
+      s.scal[SC_KG] = lgamma(pr.gbprior_a) + log(pr.gbprior_b);
       s_bufA = 0; s_bufW = 0;
     }
     __syncthreads();
@@ -340,6 +492,16 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       __syncthreads();
       return v;
     };
+    // (Z, B) integrated out: log_prob_back[root][0] into s.scal[SC_LL_PROP]; true = s.back holds LINEAR class weights, false = logs
+    auto integrate = [&](const double* src) -> bool {
+      const bool lin = messages_lin(s, src, n, n_up, tid, &s.scal[SC_LL_PROP]);
+      if (!lin) {
+        messages(s, src, n, n_up, false, tid);
+        if (tid == 0) s.scal[SC_LL_PROP] = s.back[root * 6];
+        __syncthreads();
+      }
+      return lin;
+    };
     load_Pm(s.Z, s.B, bufs);
     {
       const double ll0 = upward();
@@ -372,10 +534,10 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
           c3 = __reduce_add_sync(0xffffffffu, c3); gb = __reduce_add_sync(0xffffffffu, gb); ungb = __reduce_add_sync(0xffffffffu, ungb);
           if (lane == 0) {
             double v = s.scal[SC_LOGLIK] + s.scal[SC_LOGPZ];
-            v += log_gamma_pdf(-s.scal[SC_SELC], pr.cprior_a, pr.cprior_b);
-            if (resz != 0) v += log_gamma_pdf(s.scal[SC_SELN] + pr.nprior_c, pr.nprior_a, pr.nprior_b);
+            v += lgp(-s.scal[SC_SELC], pr.cprior_a, pr.cprior_b, s.scal[SC_KC]);
+            if (resz != 0) v += lgp(s.scal[SC_SELN] + pr.nprior_c, pr.nprior_a, pr.nprior_b, s.scal[SC_KN]);
             v += log(1.0 - pr.ncons_to_mis) * c0 + log(1.0 - pr.cons_to_mis) * c1 + log(pr.ncons_to_mis) * c2 + log(pr.cons_to_mis) * c3;
-            v += log(1.0 - pr.gbprior_c) * ungb + log_gamma_pdf(s.scal[SC_GBC], pr.gbprior_a, pr.gbprior_b) + log(pr.gbprior_c) * gb;
+            v += log(1.0 - pr.gbprior_c) * ungb + lgp(s.scal[SC_GBC], pr.gbprior_a, pr.gbprior_b, s.scal[SC_KG]) + log(pr.gbprior_c) * gb;
             s.scal[SC_FULL] = v;
           }
         }
@@ -495,11 +657,11 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       emissions(s, L, s.emis, nullptr, P0, bufA, post, n, 0, tid);
       __syncthreads();
       PH(PH_INIT_EMIS);
-      messages(s, s.emis, n, n_up, false, tid);
+      integrate(s.emis);
       PH(PH_INIT_MSG);
       const double elbo_old = elbo_term(s, s.Z, s.B, P0, bufA, post, n, tid);
       if (tid == 0) {
-        s.scal[SC_LOGLIK_OLD] = s.back[root * 6];
+        s.scal[SC_LOGLIK_OLD] = s.scal[SC_LL_PROP];
         s.scal[SC_ELBO_OLD] = elbo_old;
         s.scal[SC_PSELC] = s.scal[SC_SELC]; s.scal[SC_PSELN] = s.scal[SC_SELN]; s.scal[SC_PGBC] = s.scal[SC_GBC];  // cur_* of sample_rates
         s_bufW = s_bufA;
@@ -523,19 +685,16 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
         double* bufP = bufs + (size_t)bP * buf_d;
         __syncthreads();
         PH(PH_ELBO);
-        build_logs(s, L, ev, P0, bufP, new_c, new_n, new_g, n, 1, tid);
+        build_logs(s, L, ev, P0, bufP, new_c, new_n, new_g, n, 1, tid, s.emis_t, s.emis, post);
         PH(PH_BUILD);
-        emissions(s, L, s.emis_t, s.emis, P0, bufP, post, n, 1, tid);
-        __syncthreads();
-        PH(PH_EMIS);
-        messages(s, s.emis_t, n, n_up, false, tid);
+        integrate(s.emis_t);
         PH(PH_MSG);
         if (tid == 0) {
-          const double ll_p = s.back[root * 6];
-          double ratio = ll_p - s.scal[SC_LOGLIK_OLD] + log_gamma_pdf(new_g, pr.gbprior_a, pr.gbprior_b) - log_gamma_pdf(cur_g, pr.gbprior_a, pr.gbprior_b);
+          const double ll_p = s.scal[SC_LL_PROP];
+          double ratio = ll_p - s.scal[SC_LOGLIK_OLD] + lgp(new_g, pr.gbprior_a, pr.gbprior_b, s.scal[SC_KG]) - lgp(cur_g, pr.gbprior_a, pr.gbprior_b, s.scal[SC_KG]);
           if (resz != 0)
-            ratio += log_gamma_pdf(new_n + pr.nprior_c, pr.nprior_a, pr.nprior_b) - log_gamma_pdf(cur_n + pr.nprior_c, pr.nprior_a, pr.nprior_b);
-          ratio += log_gamma_pdf(-new_c, pr.cprior_a, pr.cprior_b) - log_gamma_pdf(-cur_c, pr.cprior_a, pr.cprior_b) - log(-new_c) + log(-cur_c);
+            ratio += lgp(new_n + pr.nprior_c, pr.nprior_a, pr.nprior_b, s.scal[SC_KN]) - lgp(cur_n + pr.nprior_c, pr.nprior_a, pr.nprior_b, s.scal[SC_KN]);
+          ratio += lgp(-new_c, pr.cprior_a, pr.cprior_b, s.scal[SC_KC]) - lgp(-cur_c, pr.cprior_a, pr.cprior_b, s.scal[SC_KC]) - log(-new_c) + log(-cur_c);
           const bool acc = log(u01(w4.w)) < ratio;
           s_flag = acc ? 1 : 0;
           if (acc) {
@@ -555,7 +714,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       // ---- 5. Update_ZB + update_rates
       const double* bufW = bufs + (size_t)s_bufW * buf_d;
       PH(PH_COMMIT);
-      messages(s, s.emis, n, n_up, false, tid);
+      const bool lin = integrate(s.emis);
       PH(PH_MSG);
       for (int d = 1; d < n_down; d++) {
         const int lo = s.down_off[d], cnt = s.down_off[d + 1] - lo;
@@ -567,12 +726,17 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
           const bool up = s.upr[i] != 0;
           int zn = s.Z[i], bn = s.B[i];
           if (zp != 2) {
-            double lw[6], mx = -CUDART_INF;
-            for (int k = 0; k < 6; k++) {
-              lw[k] = lt_val(s.scal, k % 3, zp, up) + s.back[i * 6 + k];
-              mx = fmax(mx, lw[k]);
+            double lw[6];
+            if (lin) {
+              for (int k = 0; k < 6; k++) lw[k] = lt_lin(s.scal, k % 3, zp, up) * s.back[i * 6 + k];
+            } else {
+              double mx = -CUDART_INF;
+              for (int k = 0; k < 6; k++) {
+                lw[k] = lt_val(s.scal, k % 3, zp, up) + s.back[i * 6 + k];
+                mx = fmax(mx, lw[k]);
+              }
+              for (int k = 0; k < 6; k++) lw[k] = exp(lw[k] - mx);
             }
-            for (int k = 0; k < 6; k++) lw[k] = exp(lw[k] - mx);
             const int nn = categorical_n(lw, 6, u);
             if (nn >= 0) {
               zn = nn % 3;
@@ -581,8 +745,10 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
           } else {
             zn = 2;
             double lw[2] = {s.back[i * 6 + 2], s.back[i * 6 + 5]};
-            const double mx = fmax(lw[0], lw[1]);
-            lw[0] = exp(lw[0] - mx); lw[1] = exp(lw[1] - mx);
+            if (!lin) {
+              const double mx = fmax(lw[0], lw[1]);
+              lw[0] = exp(lw[0] - mx); lw[1] = exp(lw[1] - mx);
+            }
             const int nn = categorical_n(lw, 2, u);
             if (nn >= 0 && !mis) bn = nn > 0 ? 1 : 0;
           }
@@ -646,7 +812,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
 
 size_t chain_smem_bytes(int n_max, int slots_max) {
   const size_t uni_d = uni_doubles(n_max, slots_max);
-  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N) * 8;
+  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N + (size_t)n_max * 4 + 6 + (n_max + 1) / 2) * 8;
   b += ((size_t)n_max * 10 + 4) * 2 + (size_t)n_max * 8;  // ten int16 arrays (two with 2 spare entries), eight byte arrays
   return (b + 63) & ~size_t(63);
 }
