@@ -224,7 +224,8 @@ struct TreeSmem {   // per-chain tree arrays in shared memory
   int16_t* intidx;  // [n]
 };
 
-template <bool READ_G, bool WRITE_G>
+// LDG_CODES = false: `codes` may point to shared memory (a staged copy), so it is read with a plain generic load
+template <bool READ_G, bool WRITE_G, bool LDG_CODES = true>
 __device__ __forceinline__ double prune_pattern(const ElemHeader* h, const TreeSmem& ts, const uint8_t* __restrict__ codes, const double* __restrict__ Pm,
                                                 const uint8_t* __restrict__ dirty, double* __restrict__ stack, int* __restrict__ stack_sc,
                                                 double* __restrict__ gpart, int16_t* __restrict__ gsc, const double* __restrict__ pi, int p, int BD,
@@ -246,7 +247,8 @@ __device__ __forceinline__ double prune_pattern(const ElemHeader* h, const TreeS
       if (f & PA_F_MISSING) continue;  // bpp_c.cpp:660
       const double* Pc = Pm + ch * 16;
       if (f & PA_F_TIP) {
-        const uint32_t byte = __ldg(codes + (size_t)ts.tiprow[ch] * half + (p >> 1));
+        const uint8_t* cp = codes + (size_t)ts.tiprow[ch] * half + (p >> 1);
+        const uint32_t byte = LDG_CODES ? __ldg(cp) : *cp;
         const uint32_t code = (byte >> ((p & 1) * 4)) & 15u;
         if (code == 15u) continue;  // gap / N: Tg >= num_base (bpp_c.cpp:660)
         if ((code & (code - 1)) == 0) {

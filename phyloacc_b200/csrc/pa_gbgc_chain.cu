@@ -39,6 +39,7 @@ enum { PH_SETUP = 0, PH_MONITOR, PH_DOWN, PH_INIT_EMIS, PH_INIT_MSG, PH_BUILD, P
 struct GbgcChainLaunch {
   const uint8_t* blobs; const int64_t* blob_off;
   int n_chains, N, n_max, slots_max, P_max, T;
+  int codes_cap;              // bytes of shared memory for a staged copy of an element's packed tip codes (0: always read them from the blob)
   const int32_t* chain_elem;  // element index in the engine's batch
   const int32_t* chain_resz;  // the reference's resZ: 0 = M0, 2 = M1, 1 = M2
   const int8_t* fixZ;         // [n_chains][N] original numbering (1: class 2 forbidden)
@@ -55,18 +56,24 @@ struct GbgcChainLaunch {
                                  // downward passes, then SM cycles per phase (thread 0 of every CTA)
 };
 
-// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | per-warp pair accumulators [4][n_max][16] |
+constexpr int kPow = 19;
+constexpr int kPwStride = (kPow + 1) * 16 + 2;  // doubles between the power tables of two classes: the lanes of a warp read up to six classes at the same
+                                                 // (power, entry) -- a stride of 320 would put them all in one bank
+__constant__ double c_inv[kPow + 1] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
+                                       1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19};
+
+// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | transposition tiles of the downward pass [4][16][33] |
 // power basis of the P(t) builds [6][20][16]
 __host__ __device__ inline size_t uni_doubles(int n_max, int slots_max) {
-  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = (size_t)4 * n_max * 16, c = 6 * 20 * 16;
+  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = 4 * 16 * 33, c = 6 * ((kPow + 1) * 16 + 2);
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
 struct Sh {  // shared-memory views of one chain
   double *Pm, *uni, *red, *emis, *emis_t, *back, *Qc, *scal, *msg, *lsum, *pw, *mu;
   int *stack_sc, *msc;
-  int16_t *child, *tiprow, *su, *intidx, *parent, *up_nodes, *up_off, *down_nodes, *down_off;
-  uint8_t *flags, *fix, *upr;
+  int16_t *child, *tiprow, *su, *intidx, *parent, *up_nodes, *up_off, *down_nodes, *down_off, *dn_node, *dn_src, *dn_par;
+  uint8_t *flags, *fix, *upr, *codes_s;
   int8_t *slot, *Z, *B, *Zn, *Bn;
 };
 
@@ -98,7 +105,7 @@ __device__ __forceinline__ double child_msg(const Sh& s, int c, int j) {
 }
 
 // 6-state upward messages by height levels; src = emissions [n][6] (the root's row is taken as zero); result in s.back
-__device__ void messages(const Sh& s, const double* src, int n, int n_up, bool init_pass, int tid) {
+__device__ __noinline__ void messages(const Sh& s, const double* src, int n, int n_up, bool init_pass, int tid) {
   for (int t = tid; t < n * 6; t += kCBD) s.back[t] = (t >= (n - 1) * 6) ? 0.0 : src[t];
   __syncthreads();
   for (int h = 1; h < n_up; h++) {
@@ -198,6 +205,20 @@ __device__ bool messages_lin(const Sh& s, const double* src, int n, int n_up, in
   return !__syncthreads_or(bad_w);
 }
 
+// log P(X | Z, B, r): the upward pass at the matrices in s.Pm over the element's site patterns (thread = pattern, partials on a shared-memory
+// stack, every internal node's partial also written to the arena for the downward pass)
+__device__ double upward_pass(const Sh& s, const ElemHeader* h, const uint8_t* codes, const uint16_t* weights, double* gpart, int16_t* gsc,
+                                           const double* pi, int tid) {
+  const TreeSmem ts{s.child, s.flags, s.tiprow, s.su, s.slot, s.intidx};
+  const int P = h->P, Ppad = h->Ppad;
+  double acc = 0.0;
+  for (int p = tid; p < Ppad; p += kCBD)
+    if (p < P) acc += (double)weights[p] * prune_pattern<false, true, false>(h, ts, codes, s.Pm, nullptr, s.uni, s.stack_sc, gpart, gsc, pi, p, kCBD, tid);
+  const double v = block_sum(acc, s.red, tid, kCBD);
+  __syncthreads();
+  return v;
+}
+
 __device__ __forceinline__ const double* class_log(const double* P0, const double* buf, int i, int k) {
   return k == 0 ? P0 + (size_t)i * 16 : buf + ((size_t)i * 5 + (k - 1)) * 16;
 }
@@ -254,7 +275,6 @@ __device__ double elbo_term(const Sh& s, const int8_t* Z, const int8_t* B, const
 //   P(t) = [ sum_j Poisson(j; x) A^j ]^(2^q),  x = mu t / 2^q <= 1/2,
 // i.e. a linear combination of the stored powers (16 FMA per term, as many terms as the Poisson tail needs) and q squarings -- against
 // 19 + q matrix products per branch before.  Every term is non-negative: no cancellation, nothing depends on the spectrum.
-constexpr int kPow = 19;
 // emis_dst != nullptr: the emissions of the built classes are taken from the matrices while they are in registers (the proposal's
 // getEmission_update), every other entry (class 0, missing branches, forbidden classes) is copied from emis_base.
 __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView& ev, double* P0, double* buf, double sel_c, double sel_n, double gbc, int n,
@@ -272,17 +292,17 @@ __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView
     const double mu = fmax(fmax(-Q[0], -Q[5]), fmax(-Q[10], -Q[15]));
     s.mu[tid] = mu;
 #pragma unroll
-    for (int e = 0; e < 16; e++) s.pw[(tid * (kPow + 1) + 1) * 16 + e] = (mu > 0.0 ? Q[e] / mu : 0.0) + (((e >> 2) == (e & 3)) ? 1.0 : 0.0);  // A^1
+    for (int e = 0; e < 16; e++) s.pw[tid * kPwStride + 16 + e] = (mu > 0.0 ? Q[e] / mu : 0.0) + (((e >> 2) == (e & 3)) ? 1.0 : 0.0);  // A^1
   }
   __syncthreads();
   if (tid < 96) {  // 16 lanes per class: lane (r, c) owns entry [r][c] of every power
     const int k = tid >> 4, e = tid & 15, r = e >> 2, c = e & 3;
-    const double* A = s.pw + (k * (kPow + 1) + 1) * 16;
+    const double* A = s.pw + k * kPwStride + 16;
     const double a0 = A[c], a1 = A[4 + c], a2 = A[8 + c], a3 = A[12 + c];
     for (int j = 2; j <= kPow; j++) {
       if (k >= k_lo) {
-        const double* prev = s.pw + (k * (kPow + 1) + j - 1) * 16 + r * 4;
-        s.pw[(k * (kPow + 1) + j) * 16 + e] = ((prev[0] * a0 + prev[1] * a1) + prev[2] * a2) + prev[3] * a3;
+        const double* prev = s.pw + k * kPwStride + (j - 1) * 16 + r * 4;
+        s.pw[k * kPwStride + j * 16 + e] = ((prev[0] * a0 + prev[1] * a1) + prev[2] * a2) + prev[3] * a3;
       }
       __syncwarp();
     }
@@ -305,9 +325,9 @@ __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView
       double wgt = exp(-x);
 #pragma unroll
       for (int e = 0; e < 16; e++) P16[e] = ((e >> 2) == (e & 3)) ? wgt : 0.0;
-      const double* pw = s.pw + (size_t)k * (kPow + 1) * 16;
+      const double* pw = s.pw + k * kPwStride;
       for (int j = 1; j <= kPow; j++) {
-        wgt *= x / j;
+        wgt *= x * c_inv[j];
         const double* Aj = pw + j * 16;
 #pragma unroll
         for (int e = 0; e < 16; e++) P16[e] += wgt * Aj[e];
@@ -322,7 +342,7 @@ __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView
     }
     double* dst = k == 0 ? P0 + (size_t)i * 16 : buf + ((size_t)i * 5 + (k - 1)) * 16;
 #pragma unroll
-    for (int e = 0; e < 16; e++) { P16[e] = log(P16[e]); dst[e] = P16[e]; }
+    for (int e = 0; e < 16; e++) { P16[e] = log_fast(P16[e]); dst[e] = P16[e]; }
     if (emis_dst) emis_dst[i * 6 + k] = pair_dot(P16, post + (size_t)i * 16) + (k < 3 ? l_b0 : l_b1) + (k % 3 == 1 ? l_c : l_n);
   }
   __syncthreads();
@@ -355,11 +375,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) {
+#ifndef PA_GBGC_CTAS
+#define PA_GBGC_CTAS 3
+#endif
+__global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChainLaunch L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_chain, s_flag, s_bufA, s_bufW;
   __shared__ long long s_ph[12], s_t0;
-  __shared__ int s_ntask, s_nbranch;
+  __shared__ int s_ntask, s_nbranch, s_ndown;
   __shared__ double s_pi[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_max = L.n_max, slots_max = L.slots_max, N = L.N, T = L.T;
@@ -367,7 +390,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
   {
     double* d = reinterpret_cast<double*>(smem_raw);
     s.Pm = d; d += (size_t)n_max * 16;
-    s.uni = d;  // pruning stack [slots][4][BD] + scale counts | per-warp pair accumulators [4][n_max][16]
+    s.uni = d;  // pruning stack [slots][4][BD] + scale counts | power basis of the P(t) builds
     const size_t uni_d = uni_doubles(n_max, slots_max);
     s.stack_sc = reinterpret_cast<int*>(d + (size_t)slots_max * 4 * kCBD);
     d += uni_d;
@@ -382,6 +405,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
     s.pw = s.uni;  // the power basis of build_logs lives in the phase-shared region (no pruning pass runs during the rate moves)
     s.mu = d; d += 6;
     s.msc = reinterpret_cast<int*>(d); d += (n_max + 1) / 2;
+    s.codes_s = reinterpret_cast<uint8_t*>(d); d += (L.codes_cap + 7) / 8;
     int16_t* h16 = reinterpret_cast<int16_t*>(d);
     s.child = h16; h16 += 2 * n_max;
     s.tiprow = h16; h16 += n_max;
@@ -392,6 +416,9 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
     s.up_off = h16; h16 += n_max + 2;
     s.down_nodes = h16; h16 += n_max;
     s.down_off = h16; h16 += n_max + 2;
+    s.dn_node = h16; h16 += n_max;
+    s.dn_src = h16; h16 += n_max;
+    s.dn_par = h16; h16 += n_max;
     uint8_t* b8 = reinterpret_cast<uint8_t*>(h16);
     s.flags = b8; b8 += n_max;
     s.fix = b8; b8 += n_max;
@@ -408,7 +435,8 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
   double* bufs = P0 + (size_t)n_max * 16;                         // [3][n_max][5][16]
   const size_t buf_d = (size_t)n_max * 80;
   double* postb = bufs + 3 * buf_d;                               // [2][n_max][16]
-  double* gpart = postb + (size_t)2 * n_max * 16;                 // [n_max][P_max][4]
+  double* gacc = postb + (size_t)2 * n_max * 16;                  // [4 warps][n_max][16] pair sums of each warp's patterns
+  double* gpart = gacc + (size_t)4 * n_max * 16;                  // [n_max][P_max][4]
   int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)n_max * L.P_max * 4);
   const pa_gbgc_params& pr = L.prm;
   if (tid < 4) s_pi[tid] = L.pi[tid];
@@ -467,8 +495,30 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       nb = __reduce_add_sync(0xffffffffu, nb);
       if (lane == 0) { s_ntask = nt; s_nbranch = nb; }
     }
-    TreeSmem ts{s.child, s.flags, s.tiprow, s.su, s.slot, s.intidx};
-    double* stack = s.uni;
+    // the packed tip codes never change during a chain: staged once in shared memory when they fit (rows of Ppad / 2 bytes, a multiple of 16)
+    const int half = Ppad >> 1;
+    const bool staged = (size_t)h->S * half <= (size_t)L.codes_cap;
+    if (staged) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(ev.codes);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s.codes_s);
+      for (int t = tid; t < (h->S * half) >> 2; t += kCBD) dst[t] = __ldg(src + t);
+    }
+    const uint8_t* codes = staged ? s.codes_s : ev.codes;
+    // program of the downward pass: the non-missing branches, parents before children; source of the branch's own upward partial
+    // (tip row as -(row + 1), or the internal node's arena index) and of its parent's posterior (-1: the parent is the branch of the
+    // previous step, its posterior is still in registers)
+    if (tid == 0) {
+      int k = 0, prev = root;
+      for (int i = n - 2; i >= 0; i--) {
+        if (s.flags[i] & PA_F_MISSING) continue;
+        s.dn_node[k] = (int16_t)i;
+        s.dn_src[k] = (s.flags[i] & PA_F_TIP) ? (int16_t)(-(s.tiprow[i] + 1)) : s.intidx[i];
+        s.dn_par[k] = (s.parent[i] == prev) ? (int16_t)-1 : s.intidx[s.parent[i]];
+        prev = i;
+        k++;
+      }
+      s_ndown = k;
+    }
     // log P(constraints): the 6-state pass of initMCMC with "- log 2" per message (GBGC/SRC/bpp_c.cpp:232-254)
     for (int t = tid; t < n * 6; t += kCBD) s.emis_t[t] = (s.fix[t / 6] == 1 && (t % 3) == 2) ? -CUDART_INF : 0.0;
     __syncthreads();
@@ -484,14 +534,7 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       }
       __syncthreads();
     };
-    auto upward = [&]() -> double {
-      double acc = 0.0;
-      for (int p = tid; p < Ppad; p += kCBD)
-        if (p < P) acc += (double)ev.weights[p] * prune_pattern<false, true>(h, ts, ev.codes, s.Pm, nullptr, stack, s.stack_sc, gpart, gsc, s_pi, p, kCBD, tid);
-      const double v = block_sum(acc, s.red, tid, kCBD);
-      __syncthreads();
-      return v;
-    };
+    auto upward = [&]() -> double { return upward_pass(s, h, codes, ev.weights, gpart, gsc, s_pi, tid); };
     // (Z, B) integrated out: log_prob_back[root][0] into s.scal[SC_LL_PROP]; true = s.back holds LINEAR class weights, false = logs
     auto integrate = [&](const double* src) -> bool {
       const bool lin = messages_lin(s, src, n, n_up, tid, &s.scal[SC_LL_PROP]);
@@ -554,99 +597,113 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
       PH(PH_MONITOR);
       if (m == T - 1) break;
       // ---- 2. expected (child, parent) pairs at the current state (only when the state moved): parents before children, an internal
-      //         node's partial is overwritten by the posterior of its base; per-warp accumulators, no block barrier inside the pass
+      //         node's partial is overwritten by the posterior of its base.  Thread = pattern; the step of branch k + 1 has its operands
+      //         (its own upward partial or tip code, its parent's posterior) requested before branch k is computed, and a parent that was
+      //         the previous step hands its posterior over in registers: the global-memory latency is off the dependent chain.  The 16
+      //         pair sums of a warp's 32 patterns go to that warp's own slice of `gacc` (no block barrier inside the pass).
       if (move) {
         nxt = (m == 0) ? 0 : 1 - cur;
-        double* pw = s.uni + (size_t)warp * n_max * 16;
-        for (int t = lane; t < n * 16; t += 32) pw[t] = 0.0;
-        __syncwarp();
-        const int half = Ppad >> 1;
-        for (int p0 = 0; p0 < Ppad; p0 += kCBD) {
+        double* ga = gacc + (size_t)warp * n_max * 16;
+        double* rt = s.uni + warp * (16 * 33);  // the pruning stack is idle during this pass
+        const int nd = s_ndown;
+        int tile = 0;
+        for (int p0 = 0; p0 < Ppad; p0 += kCBD, tile++) {
+          if (p0 + warp * 32 >= P) break;  // none of this warp's patterns in this tile or a later one
           const int p = p0 + tid;
           const bool act = p < P;
           const double w = act ? (double)ev.weights[p] : 0.0;
+          double qprev[4] = {0.0, 0.0, 0.0, 0.0};
           if (act) {
             double* g = gpart + ((size_t)s.intidx[root] * Ppad + p) * 4;
             const double r0 = s_pi[0] * g[0], r1 = s_pi[1] * g[1], r2 = s_pi[2] * g[2], r3 = s_pi[3] * g[3];
             const double tot = ((r0 + r1) + r2) + r3;
-            g[0] = r0 / tot; g[1] = r1 / tot; g[2] = r2 / tot; g[3] = r3 / tot;
+            qprev[0] = r0 / tot; qprev[1] = r1 / tot; qprev[2] = r2 / tot; qprev[3] = r3 / tot;
+            g[0] = qprev[0]; g[1] = qprev[1]; g[2] = qprev[2]; g[3] = qprev[3];
           }
-          for (int i = n - 2; i >= 0; i--) {
-            if (s.flags[i] & PA_F_MISSING) continue;  // uniform over the CTA
-            double J[16];
-#pragma unroll
-            for (int e = 0; e < 16; e++) J[e] = 0.0;
+          double LvN[4] = {0.0, 0.0, 0.0, 0.0}, qpN[4] = {0.0, 0.0, 0.0, 0.0};
+          int nodeN = 0, srcN = 0, parN = -1;
+          auto fetch = [&](int k) {
+            nodeN = s.dn_node[k]; srcN = s.dn_src[k]; parN = s.dn_par[k];
             if (act) {
-              double Lv[4];
-              double* gi = nullptr;
-              if (s.flags[i] & PA_F_TIP) {
-                const uint32_t byte = __ldg(ev.codes + (size_t)s.tiprow[i] * half + (p >> 1));
+              if (srcN < 0) {
+                const uint32_t byte = codes[(size_t)(-srcN - 1) * half + (p >> 1)];
                 const uint32_t code = (byte >> ((p & 1) * 4)) & 15u;
 #pragma unroll
-                for (int a = 0; a < 4; a++) Lv[a] = ((code >> a) & 1u) ? 1.0 : 0.0;
+                for (int a = 0; a < 4; a++) LvN[a] = ((code >> a) & 1u) ? 1.0 : 0.0;
               } else {
-                gi = gpart + ((size_t)s.intidx[i] * Ppad + p) * 4;
-#pragma unroll
-                for (int a = 0; a < 4; a++) Lv[a] = gi[a];
+                const double2* g2 = reinterpret_cast<const double2*>(gpart + ((size_t)srcN * Ppad + p) * 4);
+                const double2 x = g2[0], y = g2[1];
+                LvN[0] = x.x; LvN[1] = x.y; LvN[2] = y.x; LvN[3] = y.y;
               }
+              if (parN >= 0) {
+                const double2* q2 = reinterpret_cast<const double2*>(gpart + ((size_t)parN * Ppad + p) * 4);
+                const double2 x = q2[0], y = q2[1];
+                qpN[0] = x.x; qpN[1] = x.y; qpN[2] = y.x; qpN[3] = y.y;
+              }
+            }
+          };
+          if (nd > 0) fetch(0);
+          for (int k = 0; k < nd; k++) {
+            const int i = nodeN, src = srcN;
+            const bool fwd = parN < 0;
+            double Lv[4], qp[4];
+#pragma unroll
+            for (int a = 0; a < 4; a++) { Lv[a] = LvN[a]; qp[a] = fwd ? qprev[a] : qpN[a]; }
+            double old = 0.0;
+            if (tile > 0 && lane < 16) old = ga[i * 16 + lane];
+            if (k + 1 < nd) fetch(k + 1);
+            // 16 weighted pairs of this pattern into the warp's transposition tile [16][33], then lane (e, h) adds up element e of the patterns
+            // 16 h .. 16 h + 15 in order and the two halves meet in one shuffle: 16 STS + 16 LDS + 16 DADD instead of a 31-shuffle butterfly
+            if (act) {
               const double* Pi = s.Pm + i * 16;
-              const double* qp = gpart + ((size_t)s.intidx[s.parent[i]] * Ppad + p) * 4;
-              double qi[4] = {0.0, 0.0, 0.0, 0.0};
+              double PL[16], ratio[4];
+#pragma unroll
+              for (int e = 0; e < 16; e++) PL[e] = Pi[e] * Lv[e & 3];  // [parent base b][child base a]
 #pragma unroll
               for (int b = 0; b < 4; b++) {
-                const double mm = ((Pi[b * 4] * Lv[0] + Pi[b * 4 + 1] * Lv[1]) + Pi[b * 4 + 2] * Lv[2]) + Pi[b * 4 + 3] * Lv[3];
-                const double ratio = (mm > 0.0) ? qp[b] / mm : 0.0;
-#pragma unroll
-                for (int a = 0; a < 4; a++) {
-                  const double j = ratio * Pi[b * 4 + a] * Lv[a];
-                  J[a * 4 + b] = j * w;  // [child base a][parent base b], weighted by the pattern's column count
-                  qi[a] += j;
-                }
+                const double mm = ((PL[b * 4] + PL[b * 4 + 1]) + PL[b * 4 + 2]) + PL[b * 4 + 3];
+                ratio[b] = (mm > 0.0) ? div_fast(qp[b], mm) : 0.0;
               }
-              if (gi) {
 #pragma unroll
-                for (int a = 0; a < 4; a++) gi[a] = qi[a];
+              for (int a = 0; a < 4; a++) qprev[a] = ((ratio[0] * PL[a] + ratio[1] * PL[4 + a]) + ratio[2] * PL[8 + a]) + ratio[3] * PL[12 + a];
+              if (src >= 0) {
+                double2* g2 = reinterpret_cast<double2*>(gpart + ((size_t)src * Ppad + p) * 4);
+                g2[0] = make_double2(qprev[0], qprev[1]);
+                g2[1] = make_double2(qprev[2], qprev[3]);
               }
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const double rw = ratio[b] * w;  // weighted by the pattern's column count
+#pragma unroll
+                for (int a = 0; a < 4; a++) rt[(a * 4 + b) * 33 + lane] = rw * PL[b * 4 + a];  // [child base a][parent base b]
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e++) rt[e * 33 + lane] = 0.0;
             }
-            // transposing butterfly: 16 values x 32 lanes -> one total per even lane in 16 shuffles (deterministic order)
-            double v8[8], v4[4], v2[2], v1;
+            __syncwarp();
+            double v1 = 0.0;
             {
-              const bool hi = (lane & 16) != 0;
+              const double* col = rt + (lane & 15) * 33 + (lane & 16);
 #pragma unroll
-              for (int e = 0; e < 8; e++) {
-                const double keep = hi ? J[e + 8] : J[e], send = hi ? J[e] : J[e + 8];
-                v8[e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
+              for (int q = 0; q < 16; q++) v1 += col[q];
             }
-            {
-              const bool hi = (lane & 8) != 0;
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                const double keep = hi ? v8[e + 4] : v8[e], send = hi ? v8[e] : v8[e + 4];
-                v4[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-            }
-            {
-              const bool hi = (lane & 4) != 0;
-#pragma unroll
-              for (int e = 0; e < 2; e++) {
-                const double keep = hi ? v4[e + 2] : v4[e], send = hi ? v4[e] : v4[e + 2];
-                v2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-            }
-            {
-              const bool hi = (lane & 2) != 0;
-              const double keep = hi ? v2[1] : v2[0], send = hi ? v2[0] : v2[1];
-              v1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-            if (!(lane & 1)) pw[i * 16 + (lane >> 1)] += v1;  // pair index = 8 b4 + 4 b3 + 2 b2 + b1 of the lane = lane >> 1
+            v1 += __shfl_xor_sync(0xffffffffu, v1, 16);
+            if (lane < 16) ga[i * 16 + lane] = old + v1;
+            __syncwarp();
           }
         }
         __syncthreads();
         double* pn = postb + (size_t)nxt * n_max * 16;
-        for (int t = tid; t < (n - 1) * 16; t += kCBD)
-          pn[t] = ((s.uni[t] + s.uni[(size_t)n_max * 16 + t]) + s.uni[(size_t)2 * n_max * 16 + t]) + s.uni[(size_t)3 * n_max * 16 + t];
+        const int nw = min(4, (P + 31) >> 5);  // warps that own patterns, in fixed order
+        for (int t = tid; t < (n - 1) * 16; t += kCBD) {
+          double v = 0.0;
+          if (!(s.flags[t >> 4] & PA_F_MISSING)) {
+            v = gacc[t];
+            for (int ww = 1; ww < nw; ww++) v += gacc[(size_t)ww * n_max * 16 + t];
+          }
+          pn[t] = v;
+        }
         __syncthreads();
       }
       PH(PH_DOWN);
@@ -810,17 +867,17 @@ __global__ void __launch_bounds__(kCBD, 3) gbgc_chain_kernel(GbgcChainLaunch L) 
     for (int k = 0; k < 12; k++) atomicAdd(&L.counters[4 + k], (unsigned long long)s_ph[k]);
 }
 
-size_t chain_smem_bytes(int n_max, int slots_max) {
+size_t chain_smem_bytes(int n_max, int slots_max, int codes_cap) {
   const size_t uni_d = uni_doubles(n_max, slots_max);
-  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N + (size_t)n_max * 4 + 6 + (n_max + 1) / 2) * 8;
-  b += ((size_t)n_max * 10 + 4) * 2 + (size_t)n_max * 8;  // ten int16 arrays (two with 2 spare entries), eight byte arrays
+  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N + (size_t)n_max * 4 + 6 + (n_max + 1) / 2 + (codes_cap + 7) / 8) * 8;
+  b += ((size_t)n_max * 13 + 4) * 2 + (size_t)n_max * 8;  // thirteen int16 arrays (two with 2 spare entries), eight byte arrays
   return (b + 63) & ~size_t(63);
 }
 
 }  // namespace
 
 size_t gbgc_chain_scratch_stride(int n_max, int P_max) {
-  const size_t d = (size_t)n_max * 16 + 3 * (size_t)n_max * 80 + 2 * (size_t)n_max * 16 + (size_t)n_max * P_max * 4;
+  const size_t d = (size_t)n_max * 16 + 3 * (size_t)n_max * 80 + 2 * (size_t)n_max * 16 + 4 * (size_t)n_max * 16 + (size_t)n_max * P_max * 4;
   return ((d * 8 + (size_t)n_max * P_max * 2) + 255) & ~size_t(255);
 }
 
@@ -833,7 +890,9 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   cudaError_t err = cudaSetDevice(device);
   const size_t nc = (size_t)n_chains;
   const int T = prm->num_burn + prm->num_mcmc;
-  const size_t smem = chain_smem_bytes(n_max, slots_max);
+  // tip codes of one element: at most (n_max + 1) / 2 rows of P_max / 2 bytes; staged in shared memory up to 12 KB
+  const int codes_cap = (int)std::min<size_t>(12288, ((size_t)((n_max + 1) / 2) * (size_t)(P_max / 2) + 15) & ~size_t(15));
+  const size_t smem = chain_smem_bytes(n_max, slots_max, codes_cap);
   int per_sm = 0;
   if (err == cudaSuccess) err = cudaFuncSetAttribute(gbgc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err == cudaSuccess) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gbgc_chain_kernel, kCBD, smem);
@@ -850,6 +909,7 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   if (err == cudaSuccess) err = cudaMalloc(&d_out, b_tr + b_head + b_ctr + b_zb);
   GbgcChainLaunch L;
   L.blobs = d_blobs; L.blob_off = d_blob_off; L.n_chains = n_chains; L.N = N; L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T;
+  L.codes_cap = codes_cap;
   int32_t* di = reinterpret_cast<int32_t*>(d_in);
   L.chain_elem = di; L.chain_resz = di + nc;
   int8_t* d8 = reinterpret_cast<int8_t*>(di + 2 * nc);

@@ -14,7 +14,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, obj, ksub, n_iter = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv[4])
 title = sys.argv[5] if len(sys.argv) > 5 else os.path.basename(rep)
-SRC = os.path.join(ROOT, "phyloacc_b200", "csrc", "pa_chain.cu")
+SRC = os.path.join(ROOT, "phyloacc_b200", "csrc", os.environ.get("PA_NCU_SRC", "pa_chain.cu"))  # PA_NCU_SRC=pa_gbgc_chain.cu for the GBGC chain
 
 
 def ncu_csv(page):
@@ -61,7 +61,7 @@ for l in sass.splitlines():
 src_lines = open(SRC).read().split("\n")
 marks = []  # (line, label) from the phase comments of the source
 for i, l in enumerate(src_lines, 1):
-    m = re.match(r"\s*// -{8,} (.*)", l)
+    m = re.match(r"\s*// -{4,} (.*)", l)
     if m:
         marks.append((i, m.group(1)[:60]))
     m = re.match(r"(?:template.*\n)?__device__ .*? (\w+)\(", l)
@@ -104,6 +104,6 @@ print("instructions / stall samples by phase (library code attributed to the pha
 for k, x in agg.most_common(16):
     print(f"  {100 * x / T:5.1f}%i {x / n_iter:9.0f} instr/iter {100 * smp[k] / TS:5.1f}%s  static {stat[k]:6d}  {k}")
 print("hottest source lines (share of executed warp-instructions):")
-for (f, ln), x in line_agg.most_common(14):
+for (f, ln), x in line_agg.most_common(int(os.environ.get("PA_NCU_TOP", "14"))):
     text = src_lines[ln - 1].strip()[:110] if f == os.path.basename(SRC) and 0 < ln <= len(src_lines) else ""
     print(f"  {100 * x / T:5.1f}%  {f}:{ln}  {text}")
