@@ -285,6 +285,13 @@ int pa_engine_get_params(const pa_engine* e, pa_params* out);
  * optional _mcmc_trace_M*_*.txt) and the "time used:" log line. */
 int pa_run_from_config(const char* cfg_path);
 
+/* Whole-program entry of the PhyloAcc-ST-GBGC variant = main() of src/PhyloAcc-ST-GBGC/SRC/main.cpp:240-445: the variant's parameter file
+ * (LoadParams, main.cpp:89-212: CONSERVE_RATE, ACCE_RATE, PREP_LRATE, PREP_GRATE, GAPCHAR '*', VERBOSE 1 by default ...) in, result files out:
+ * <prefix>_hyper.txt, _species_names.txt, _rate_postZ_{0,1,2}.txt (n_rate, c_rate, gBC, P(B) and P(Z = -1..2) per node; file index = resZ),
+ * _elem_lik.txt (loglik_NUll, loglik_RES, loglik_all, log_ratio, loglik_Max1..3), _1_elem_Z.txt and, with VERBOSE, _mcmc_trace_{resZ}_{c}.txt
+ * (bpp_c2.cpp:567-650, bpp.cpp:536-574).  SAMPLE_HYPER 1 is rejected (exit code 1).  Returns the process exit code. */
+int pa_gbgc_run_from_config(const char* cfg_path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ from . import build as _build
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PA_LIB", _build.LIB)  # PA_LIB: load an alternative build of the same library (A/B timing)
 BIN_PATH = _build.BIN
+BIN_GBGC_PATH = _build.BIN_GBGC
 
 PA_OK = 0
 M0, M1, M2 = 0, 1, 2
@@ -110,7 +111,7 @@ EXPORTS = [
     "pa_engine_load_alignment", "pa_engine_num_elements", "pa_engine_element_info", "pa_engine_loglik_replay",
     "pa_engine_sample", "pa_engine_collect", "pa_engine_run", "pa_engine_get_trace", "pa_engine_counters", "pa_engine_phase_cycles",
     "pa_engine_create_from_config", "pa_engine_get_tree", "pa_engine_node_name", "pa_engine_element_name",
-    "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_device_fp64_peak",
+    "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_gbgc_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
     "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
     "pa_gbgc_params_default", "pa_engine_gbgc_run",
@@ -169,6 +170,7 @@ def load_library(build_if_missing: bool = True):
     lib.pa_engine_get_ids.argtypes = [C.c_void_p, C.POINTER(_i32p), _i32p]
     lib.pa_engine_get_params.argtypes = [C.c_void_p, C.POINTER(PaParams)]
     lib.pa_run_from_config.argtypes = [C.c_char_p]
+    lib.pa_gbgc_run_from_config.argtypes = [C.c_char_p]
     lib.pa_device_fp64_peak.argtypes = [C.c_int, C.c_int, _f64p]
     lib.pa_engine_gbgc_integrate.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _i8p, _f64p, _f64p, _f64p, C.POINTER(PaGbgcConsts), _f64p, _f64p, _f64p]
     lib.pa_engine_gbgc_replay.argtypes = [C.c_void_p, C.c_int32, _i32p, _i8p, _i8p, _f64p, _f64p, _f64p, _f64p]

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PA_LIB_OUT", os.path.join(HERE, "libphyloacc_b200.so"))  # PA_LIB_OUT: build an A/B variant next to the product library
 BIN = os.path.join(HERE, "PhyloAcc-ST-b200")
-LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu", "pa_summary.cu", "pa_gbgc.cu", "pa_gbgc_chain.cu", "pa_gbgc_host.cpp"]
+BIN_GBGC = os.path.join(HERE, "PhyloAcc-GBGC-b200")  # drop-in for the PhyloAcc-ST-GBGC binary (same source, -DPA_MAIN_GBGC)
+LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu", "pa_summary.cu", "pa_gbgc.cu", "pa_gbgc_chain.cu", "pa_gbgc_host.cpp", "pa_gbgc_app.cpp"]
 NVCC = os.environ.get("PA_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOSTCXX = "/usr/bin/g++"
@@ -55,6 +56,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if os.path.exists(main_src) and not _newer(BIN, [main_src, LIB]):
         # the binary dlopen()s the library only after argument checking (zero-argument probe must not touch CUDA)
         subprocess.run([HOSTCXX, "-O2", "-std=c++17", main_src, "-o", BIN, "-ldl"], check=True)
+    if os.path.exists(main_src) and not _newer(BIN_GBGC, [main_src, LIB]):
+        subprocess.run([HOSTCXX, "-O2", "-std=c++17", "-DPA_MAIN_GBGC", main_src, "-o", BIN_GBGC, "-ldl"], check=True)
     return LIB
 
 

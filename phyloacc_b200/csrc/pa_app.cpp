@@ -13,6 +13,7 @@
 
 #include <cuda_runtime.h>
 
+#include "pa_app.h"
 #include "pa_engine.h"
 #include "pa_nvtx.h"
 #include "pa_internal.h"
@@ -20,7 +21,7 @@
 namespace pa {
 void set_last_error(const std::string& s);
 
-static bool directory_exists(const std::string& p) {  // main.cpp:291-307
+bool directory_exists(const std::string& p) {  // main.cpp:291-307
   if (p == "") return false;
   DIR* d = opendir(p.c_str());
   if (d) {
@@ -30,25 +31,16 @@ static bool directory_exists(const std::string& p) {  // main.cpp:291-307
   return false;
 }
 
-// what the parsers produce: LoadParams + LoadPhyloProfiles + LoadPhyloTree + id selection (main.cpp:331-358,406-439)
-struct ConfigInputs {
-  Params P;
-  Tree tree;
-  std::vector<std::string> element_names;
-  std::vector<int64_t> elem_start;
-  std::vector<int32_t> elem_len;
-  std::vector<int32_t> og, cg;  // OUTGROUP / CONSERVE as leaf ids
-  std::vector<int> ids;
-  std::vector<uint8_t> X;       // [S][G]
-  int64_t G = 0;
-  int C = 0;
-};
-
 static int load_config_inputs(const char* cfg_path, ConfigInputs& in) {
-  Params& P = in.P;
   std::cout << "Loading program configurations from " << cfg_path << "......" << std::endl;
+  if (!load_params(cfg_path, in.P)) return PA_ERR_ARG;
+  return load_inputs(in);
+}
+
+// LoadPhyloProfiles + LoadPhyloTree + id selection for parameters already in in.P (shared by the ST and GBGC front doors)
+int load_inputs(ConfigInputs& in) {
+  Params& P = in.P;
   Alignment aln;
-  if (!load_params(cfg_path, P)) return PA_ERR_ARG;
   if (!load_alignment_files(P.align_path, P.segment_path, aln)) return PA_ERR_IO;
   std::cout << "Loading phylogenetic tree from " << P.phytree_path << "......" << std::endl;
   if (!load_tree(P.phytree_path, in.tree)) return PA_ERR_IO;
@@ -85,7 +77,7 @@ static int load_config_inputs(const char* cfg_path, ConfigInputs& in) {
 }
 
 // BPP::BPP on one device (bpp.hpp:173-404): an engine handle with the batch model; the alignment is loaded by the caller
-static int make_engine(const ConfigInputs& in, int device, int num_thread, pa_engine** out) {
+int make_engine(const ConfigInputs& in, int device, int num_thread, pa_engine** out) {
   pa_engine* e = new pa_engine();
   e->from_config = true;
   e->params = in.P;
@@ -130,7 +122,7 @@ static int create_from_config(const char* cfg_path, int device, pa_engine** out)
 // GPUs of this process the run is spread over: all visible ones unless PA_DEVICES=<count> says fewer or PA_DEVICE_LIST=<a,b,...> names
 // them (an ordinal may repeat: several shards on one GPU, used by the tests), and never more than one shard per
 // PA_MIN_ELEMS_PER_DEVICE (default 128) elements -- the driver's 50-locus batches stay on one GPU, genome-scale id files use the box
-static std::vector<int> pick_devices(int n_elems) {
+std::vector<int> pick_devices(int n_elems) {
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) return {0};  // the engine reports the missing device itself
   std::vector<int> devs;
