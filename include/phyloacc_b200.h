@@ -270,6 +270,36 @@ typedef struct pa_gbgc_results {
 int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,
                        int model_mask, pa_gbgc_results* out);
 
+/* PhyloAcc-GT groundwork (no GT sampler yet): what the gene-tree variant evaluates for an element at a given GENE tree
+ * embedded in the species tree, for n_states states at once --
+ *   loglik_out: log P(X | gene tree, Z, rates), the upward half of GTree::Update_Tg (src/PhyloAcc-GT/genetree.cpp:1330-1418) summed over the
+ *               columns as BPP_C::Gibbs does (bpp_c.cpp:423-432); fp64 pruning on the device over the element's compressed site patterns;
+ *   prior_out:  the multispecies-coalescent density of the tree, GTree::priorTree (genetree.cpp:560-585);
+ *   logpz_out:  log P(missing | Z, tree), GTree::get_logpZ1 (genetree.cpp:1156-1190).
+ * The gene tree is passed as GTree holds it (genetree.hpp:28-45): children_gene / heights_gene / missing_gene over the N node slots of the
+ * species tree (tips = species), its root, and parent_gene2 flattened -- for every species branch the gene lineages inside it and where each
+ * goes (itself: it leaves the branch uncoalesced; another node: it coalesces into that node inside the branch; N: the root's own entry).
+ * A gene-tree branch evolves piecewise at the rate of the species branches it crosses (1 / c_rate / n_rate by Z).  Output arrays may be NULL. */
+typedef struct pa_gt_states {
+  int32_t n_states, N;
+  const int32_t* elem;         /* [n_states] element of the loaded batch */
+  const int32_t* gchild;       /* [n_states][N][2] children_gene, -1 = none */
+  const int32_t* groot;        /* [n_states] */
+  const uint8_t* gmissing;     /* [n_states][N] missing_gene */
+  const double* gheights;      /* [n_states][N] heights_gene (root of the species tree = 0, tips negative) */
+  const int8_t* Z;             /* [n_states][N] latent class of every SPECIES branch */
+  const double* n_rate;        /* [n_states] */
+  const double* c_rate;        /* [n_states] */
+  const int64_t* lin_off;      /* [n_states + 1] range of each state in the three lineage arrays */
+  const int32_t* lin_species;  /* parent_gene2: species branch, */
+  const int32_t* lin_node;     /*               gene lineage inside it, */
+  const int32_t* lin_next;     /*               where the lineage goes */
+  const double* heights;       /* [N] heights of the species nodes (BPP::InitPhyloTree, PhyloAcc-GT/bpp.cpp:81-84) */
+  const double* thetas;        /* [N] population-size parameter of every species branch (main.cpp:376-414) */
+  double cons_to_mis, ncons_to_mis; /* CONSTOMIS and its non-conserved counterpart */
+} pa_gt_states;
+int pa_engine_gt_replay(pa_engine* e, const pa_gt_states* states, double* loglik_out, double* prior_out, double* logpz_out);
+
 /* File-level front door = the first half of the reference's main() (main.cpp:331-358,406-439): LoadParams,
  * LoadPhyloProfiles, LoadPhyloTree, BPP::BPP, InitMCMC, element-id selection, then pa_engine_load_alignment. */
 int pa_engine_create_from_config(const char* cfg_path, int device, pa_engine** out);

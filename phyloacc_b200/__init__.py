@@ -106,6 +106,15 @@ class PaCounters(C.Structure):
                 ("node_site_updates", C.c_uint64), ("d2h_bytes", C.c_uint64), ("host_eval_chains", C.c_uint64)]
 
 
+class PaGtStates(C.Structure):  # pa_gt_states
+    _fields_ = [("n_states", C.c_int32), ("N", C.c_int32), ("elem", C.POINTER(C.c_int32)), ("gchild", C.POINTER(C.c_int32)),
+                ("groot", C.POINTER(C.c_int32)), ("gmissing", C.POINTER(C.c_uint8)), ("gheights", C.POINTER(C.c_double)),
+                ("Z", C.POINTER(C.c_int8)), ("n_rate", C.POINTER(C.c_double)), ("c_rate", C.POINTER(C.c_double)),
+                ("lin_off", C.POINTER(C.c_int64)), ("lin_species", C.POINTER(C.c_int32)), ("lin_node", C.POINTER(C.c_int32)),
+                ("lin_next", C.POINTER(C.c_int32)), ("heights", C.POINTER(C.c_double)), ("thetas", C.POINTER(C.c_double)),
+                ("cons_to_mis", C.c_double), ("ncons_to_mis", C.c_double)]
+
+
 EXPORTS = [
     "pa_last_error", "pa_version", "pa_params_default", "pa_engine_create", "pa_engine_destroy", "pa_engine_set_stream",
     "pa_engine_load_alignment", "pa_engine_num_elements", "pa_engine_element_info", "pa_engine_loglik_replay",
@@ -114,7 +123,7 @@ EXPORTS = [
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_gbgc_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
     "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
-    "pa_gbgc_params_default", "pa_engine_gbgc_run",
+    "pa_gbgc_params_default", "pa_engine_gbgc_run", "pa_engine_gt_replay",
 ]
 
 _lib = None
@@ -427,6 +436,37 @@ class Engine:
     def run(self, ids) -> Results:
         self.sample(ids)
         return self.collect()
+
+    def gt_replay(self, states, heights, thetas, cons_to_mis=0.5, ncons_to_mis=0.5):
+        """PhyloAcc-GT groundwork (pa_engine_gt_replay): for every state -- a dict with elem, gchild [N, 2], root, gmissing [N], gheights [N],
+        Z [N], n_rate, c_rate and `cross` {species: [(gene lineage, where it goes)]} (GTree::parent_gene2) -- the log-likelihood on the gene
+        tree, the coalescent prior of the tree and log P(missing | Z).  Returns three arrays of length len(states)."""
+        n, N = len(states), self.N
+        elem = np.array([st["elem"] for st in states], dtype=np.int32)
+        gchild = np.ascontiguousarray([st["gchild"] for st in states], dtype=np.int32).reshape(n, N, 2)
+        groot = np.array([st["root"] for st in states], dtype=np.int32)
+        gmis = np.ascontiguousarray([st["gmissing"] for st in states], dtype=np.uint8).reshape(n, N)
+        gh = np.ascontiguousarray([st["gheights"] for st in states], dtype=np.float64).reshape(n, N)
+        Z = np.ascontiguousarray([st["Z"] for st in states], dtype=np.int8).reshape(n, N)
+        nr = np.array([st["n_rate"] for st in states], dtype=np.float64)
+        cr = np.array([st["c_rate"] for st in states], dtype=np.float64)
+        off, sp, nd, nx = [0], [], [], []
+        for st in states:
+            for s_, lin in st["cross"].items():
+                for a_, b_ in lin:
+                    sp.append(s_); nd.append(a_); nx.append(b_)
+            off.append(len(sp))
+        off = np.array(off, dtype=np.int64)
+        sp, nd, nx = (np.array(x, dtype=np.int32) for x in (sp, nd, nx))
+        heights = np.ascontiguousarray(heights, dtype=np.float64)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+        gs = PaGtStates(n, N, elem.ctypes.data_as(_i32p), gchild.ctypes.data_as(_i32p), groot.ctypes.data_as(_i32p), gmis.ctypes.data_as(_u8p),
+                        gh.ctypes.data_as(_f64p), Z.ctypes.data_as(_i8p), nr.ctypes.data_as(_f64p), cr.ctypes.data_as(_f64p),
+                        off.ctypes.data_as(C.POINTER(C.c_int64)), sp.ctypes.data_as(_i32p), nd.ctypes.data_as(_i32p), nx.ctypes.data_as(_i32p),
+                        heights.ctypes.data_as(_f64p), thetas.ctypes.data_as(_f64p), cons_to_mis, ncons_to_mis)
+        ll, prior, lpz = np.zeros(n), np.zeros(n), np.zeros(n)
+        _check(self._lib.pa_engine_gt_replay(self._h, C.byref(gs), ll.ctypes.data_as(_f64p), prior.ctypes.data_as(_f64p), lpz.ctypes.data_as(_f64p)))
+        return ll, prior, lpz
 
     def gbgc_replay(self, elem, Z, B, sel_n, sel_c, gbc) -> np.ndarray:
         """PhyloAcc-ST-GBGC groundwork: replayed log-likelihoods under the GC-biased model (see pa_engine_gbgc_replay)."""

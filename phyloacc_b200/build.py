@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("PA_LIB_OUT", os.path.join(HERE, "libphyloacc_b200.so"))  # PA_LIB_OUT: build an A/B variant next to the product library
 BIN = os.path.join(HERE, "PhyloAcc-ST-b200")
 BIN_GBGC = os.path.join(HERE, "PhyloAcc-GBGC-b200")  # drop-in for the PhyloAcc-ST-GBGC binary (same source, -DPA_MAIN_GBGC)
-LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu", "pa_summary.cu", "pa_gbgc.cu", "pa_gbgc_chain.cu", "pa_gbgc_host.cpp", "pa_gbgc_app.cpp"]
+LIB_SOURCES = ["pa_host.cpp", "pa_eval.cpp", "pa_app.cpp", "pa_capi.cpp", "pa_engine.cu", "pa_chain.cu", "pa_summary.cu", "pa_gbgc.cu", "pa_gbgc_chain.cu", "pa_gbgc_host.cpp", "pa_gbgc_app.cpp", "pa_gt.cu"]
 NVCC = os.environ.get("PA_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOSTCXX = "/usr/bin/g++"

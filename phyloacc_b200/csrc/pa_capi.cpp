@@ -252,6 +252,15 @@ int pa_engine_gbgc_integrate(pa_engine* e, int32_t n_states, const int32_t* elem
   return guarded([&]() { return e->eng.gbgc_integrate(n_states, elem, Z, B, fixZ, sel_n, sel_c, gbc, consts, post_out, emis_out, root_out); });
 }
 
+int pa_engine_gt_replay(pa_engine* e, const pa_gt_states* st, double* loglik_out, double* prior_out, double* logpz_out) {
+  if (!e || !st || (st->n_states > 0 && (!st->elem || !st->gchild || !st->groot || !st->gmissing || !st->gheights || !st->Z || !st->n_rate || !st->c_rate ||
+                                         !st->lin_off || !st->lin_species || !st->lin_node || !st->lin_next || !st->heights || !st->thetas))) {
+    pa::set_error("pa_engine_gt_replay: null argument");
+    return PA_ERR_ARG;
+  }
+  return guarded([&]() { return e->eng.gt_replay(st, loglik_out, prior_out, logpz_out); });
+}
+
 int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,
                        int model_mask, pa_gbgc_results* out) {
   if (!e || !prm || !out || (n_targets > 0 && !targets)) {

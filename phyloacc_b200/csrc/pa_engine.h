@@ -90,6 +90,7 @@ struct Engine {
                   double* out);
   int gbgc_integrate(int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ, const double* sel_n, const double* sel_c,
                      const double* gbc, const pa_gbgc_consts* k, double* post_out, double* emis_out, double* root_out);
+  int gt_replay(const pa_gt_states* gs, double* loglik_out, double* prior_out, double* logpz_out);
   int gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm, int model_mask, pa_gbgc_results* out);
   int sample(const int32_t* ids, int32_t n_ids, int model_mask = 7, bool warm_start = false, int chain_iter = 0);
   int sample_hyper(int iter, const int32_t* ids, int32_t n_ids, pa_hyper* out);

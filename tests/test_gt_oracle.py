@@ -1,0 +1,85 @@
+"""PhyloAcc-GT groundwork.  tests/golden/gt12 holds dumps of the UNMODIFIED reference (oracle/_ref/gt_probe, generator
+tests/golden/make_gt_golden.py): 4 elements x 6 states -- gene trees with the species topology and draws from the multispecies coalescent,
+random Z and rates -- each with the embedded gene tree as GTree holds it, the coalescent prior (GTree::priorTree, genetree.cpp:560-585),
+log P(missing | Z) (get_logpZ1, :1156-1190) and the log-likelihood of the upward pass (Update_Tg, :1330-1418).
+  * CPU: oracle/gt.py (numpy restatement; one pruning pass with EFFECTIVE branch lengths) against the dumps: prior and missing-data term
+    to 1e-13, log-likelihood to 1e-12 relative -- which also shows that the ST integer front-end serves the GT variant on these inputs;
+  * GPU: pa_engine_gt_replay (csrc/pa_gt.cu) against the same dumps to 1e-10 (north_star's replay criterion)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gt
+from tests._util import Case
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gt12")
+
+
+def _golden():
+    with open(os.path.join(GOLD, "probe.txt")) as f:
+        return gt.parse_probe(f.read())
+
+
+def test_species_heights_and_thetas():
+    hdr, _ = _golden()
+    case = Case("gt12")
+    # the GT parser keeps branch lengths as doubles, PhyloAcc-ST rounds them through float (newick.cpp): 1e-8 apart, not bit-equal
+    assert np.abs(gt.species_heights(case.tree.parent, case.tree.dist, hdr["N"]) - hdr["heights"]).max() < 1e-7
+    assert np.allclose(hdr["thetas"][hdr["S"]:], 0.01, rtol=1e-4) and (hdr["thetas"][:hdr["S"]] == 0).all()
+    case.close()
+
+
+def test_restatement_matches_reference():
+    hdr, els = _golden()
+    case = Case("gt12")
+    n = 0
+    for e in els:
+        assert not e["filter"]
+        el = case.element(e["c"])
+        assert el.GG == e["GG"]
+        for st in e["states"]:
+            assert abs(gt.prior_tree(st, hdr) - st["prior"]) <= 1e-13 * abs(st["prior"])
+            assert abs(gt.logp_missing(st, hdr) - st["logpz"]) <= 1e-13 * abs(st["logpz"])
+            assert np.array_equal(st["gmissing"][:hdr["S"]], el.missing[:hdr["S"]])
+            ll = gt.replay_loglik(st, hdr, el.masks)
+            assert abs(ll - st["loglik"]) <= 1e-12 * abs(st["loglik"]), (e["c"], ll, st["loglik"])
+            n += 1
+    assert n == 24 and any(st["coal"] for e in els for st in e["states"]) and any(st["gmissing"].any() for e in els for st in e["states"])
+    case.close()
+
+
+def test_coalescent_draws_differ_from_the_species_topology():
+    """The fixture is only worth something if some gene trees are NOT the species tree."""
+    hdr, els = _golden()
+    differ = 0
+    for e in els:
+        ref = e["states"][0]["gchild"]
+        differ += sum(1 for st in e["states"] if st["coal"] and not np.array_equal(np.sort(st["gchild"], axis=1), np.sort(ref, axis=1)))
+    assert differ >= 4
+
+
+@pytest.mark.gpu
+def test_cuda_gt_replay_matches_reference(native_lib):
+    import phyloacc_b200 as pab
+
+    hdr, els = _golden()
+    case = Case("gt12")
+    eng = pab.Engine.from_config(case.cfg, device=0)
+    states, want = [], []
+    for e in els:
+        for st in e["states"]:
+            states.append(dict(st, elem=e["c"]))
+            want.append((st["loglik"], st["prior"], st["logpz"]))
+    want = np.array(want)
+    ll, prior, lpz = eng.gt_replay(states, hdr["heights"], hdr["thetas"], cons_to_mis=states[0]["cons_to_mis"], ncons_to_mis=states[0]["ncons_to_mis"])
+    assert np.all(np.abs(ll - want[:, 0]) <= 1e-10 * np.abs(want[:, 0])), np.abs(ll / want[:, 0] - 1).max()
+    assert np.all(np.abs(prior - want[:, 1]) <= 1e-12 * np.abs(want[:, 1]))
+    assert np.all(np.abs(lpz - want[:, 2]) <= 1e-12 * np.abs(want[:, 2]))
+    # a second call in another order gives the same numbers (the per-CTA scratch carries nothing over)
+    order = np.random.default_rng(0).permutation(len(states))
+    ll2, _, _ = eng.gt_replay([states[i] for i in order], hdr["heights"], hdr["thetas"], cons_to_mis=states[0]["cons_to_mis"],
+                              ncons_to_mis=states[0]["ncons_to_mis"])
+    assert np.array_equal(ll2, ll[order])
+    eng.close()
+    case.close()
