@@ -198,13 +198,13 @@ int pa_engine_phase_cycles(pa_engine* e, uint64_t* out10);
  * register-resident DFMA micro-benchmark run for about `millis` ms. Not part of the reference's interface. */
 int pa_device_fp64_peak(int device, int millis, double* tflops_out);
 
-/* PhyloAcc-ST-GBGC groundwork (not yet a chain): the per-branch GC-biased matrices of BPP_C::getRate and
+/* PhyloAcc-ST-GBGC building block (the chain itself is pa_engine_gbgc_run below): the per-branch GC-biased matrices of BPP_C::getRate and
  * BPP_C::getTransition (src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:13-30,1405-1427) for n (selection, bias, branch length) triples on `device`:
  * rate_out (may be NULL) and P_out are [n][16] row-major, rate i -> j and P(i -> j | t).  The reference returns log P transposed. */
 int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const double* sel, const double* bias, const double* t, double* rate_out,
                        double* P_out);
 
-/* PhyloAcc-ST-GBGC groundwork: replayed log-likelihoods under the GC-biased model.  For each state i: element elem[i], latent class Z
+/* PhyloAcc-ST-GBGC building block: replayed log-likelihoods under the GC-biased model.  For each state i: element elem[i], latent class Z
  * ([n_states][N], original node numbering) and gBGC indicator B ([n_states][N], 0 / 1) per branch, selection coefficients of the
  * accelerated / conserved classes, the element's gBGC bias.  Every branch gets exp(t * Q o f(s + b B)) with s = 0 / sel_c / sel_n by class
  * and b = gbc on the branches with B = 1 -- the six rate matrices of BPP_C::initMCMC and init_cache_TM (GBGC/SRC/bpp_c.cpp:196-204,
@@ -212,7 +212,7 @@ int pa_gbgc_transition(int device, const pa_subst* subst, int32_t n, const doubl
 int pa_engine_gbgc_replay(pa_engine* e, int32_t n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const double* sel_n,
                           const double* sel_c, const double* gbc, double* loglik_out);
 
-/* PhyloAcc-ST-GBGC groundwork: the random-number-free half of one GBGC iteration at given states -- expected (child base, parent base)
+/* PhyloAcc-ST-GBGC building block: the random-number-free half of one GBGC iteration at given states -- expected (child base, parent base)
  * pairs per branch (Update_Tg(g,.,.,true), GBGC/SRC/bpp_c.cpp:530-583), the six (Z, B) emissions of every branch, the 6-state upward messages
  * and the ELBO term (initial_prob_back, GBGC/SRC/bpp_c2.cpp:354-407).  fixZ is the model's constraint per node (1: class 2 forbidden), as
  * BPP_C::initMCMC sets it (GBGC/SRC/bpp_c.cpp:145-180).  post_out [n_states][N][16] (row: child base, column: parent base), emis_out

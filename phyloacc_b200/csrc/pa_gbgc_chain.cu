@@ -30,7 +30,11 @@ namespace pa {
 
 namespace {
 
-constexpr int kCBD = 128;
+#ifndef PA_GBGC_BD
+#define PA_GBGC_BD 128
+#endif
+constexpr int kCBD = PA_GBGC_BD;  // threads per CTA (a multiple of 32, at least 96); A/B knob together with PA_GBGC_CTAS (CTAs per SM)
+constexpr int kNW = kCBD / 32;
 // phase clock (thread 0): adds the cycles since the previous mark to phase k
 #define PH(k) do { if (tid == 0) { const long long t__ = clock64(); s_ph[k] += t__ - s_t0; s_t0 = t__; } } while (0)
 enum { PH_SETUP = 0, PH_MONITOR, PH_DOWN, PH_INIT_EMIS, PH_INIT_MSG, PH_BUILD, PH_EMIS, PH_MSG, PH_DRAW, PH_UP, PH_ELBO, PH_COMMIT };
@@ -62,10 +66,10 @@ constexpr int kPwStride = (kPow + 1) * 16 + 2;  // doubles between the power tab
 __constant__ double c_inv[kPow + 1] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11, 1.0 / 12, 1.0 / 13,
                                        1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19};
 
-// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | transposition tiles of the downward pass [4][16][33] |
+// doubles of the phase-shared region: pruning stack [slots][4][BD] + its scale counts | transposition tiles of the downward pass [warps][16][33] |
 // power basis of the P(t) builds [6][20][16]
 __host__ __device__ inline size_t uni_doubles(int n_max, int slots_max) {
-  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = 4 * 16 * 33, c = 6 * ((kPow + 1) * 16 + 2);
+  const size_t a = (size_t)slots_max * 4 * kCBD + ((size_t)slots_max * kCBD + 1) / 2, b = kNW * 16 * 33, c = 6 * ((kPow + 1) * 16 + 2);
   return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
@@ -435,8 +439,8 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
   double* bufs = P0 + (size_t)n_max * 16;                         // [3][n_max][5][16]
   const size_t buf_d = (size_t)n_max * 80;
   double* postb = bufs + 3 * buf_d;                               // [2][n_max][16]
-  double* gacc = postb + (size_t)2 * n_max * 16;                  // [4 warps][n_max][16] pair sums of each warp's patterns
-  double* gpart = gacc + (size_t)4 * n_max * 16;                  // [n_max][P_max][4]
+  double* gacc = postb + (size_t)2 * n_max * 16;                  // [warps][n_max][16] pair sums of each warp's patterns
+  double* gpart = gacc + (size_t)kNW * n_max * 16;                  // [n_max][P_max][4]
   int16_t* gsc = reinterpret_cast<int16_t*>(gpart + (size_t)n_max * L.P_max * 4);
   const pa_gbgc_params& pr = L.prm;
   if (tid < 4) s_pi[tid] = L.pi[tid];
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
         }
         __syncthreads();
         double* pn = postb + (size_t)nxt * n_max * 16;
-        const int nw = min(4, (P + 31) >> 5);  // warps that own patterns, in fixed order
+        const int nw = min(kNW, (P + 31) >> 5);  // warps that own patterns, in fixed order
         for (int t = tid; t < (n - 1) * 16; t += kCBD) {
           double v = 0.0;
           if (!(s.flags[t >> 4] & PA_F_MISSING)) {
@@ -877,7 +881,7 @@ size_t chain_smem_bytes(int n_max, int slots_max, int codes_cap) {
 }  // namespace
 
 size_t gbgc_chain_scratch_stride(int n_max, int P_max) {
-  const size_t d = (size_t)n_max * 16 + 3 * (size_t)n_max * 80 + 2 * (size_t)n_max * 16 + 4 * (size_t)n_max * 16 + (size_t)n_max * P_max * 4;
+  const size_t d = (size_t)n_max * 16 + 3 * (size_t)n_max * 80 + 2 * (size_t)n_max * 16 + (size_t)kNW * n_max * 16 + (size_t)n_max * P_max * 4;
   return ((d * 8 + (size_t)n_max * P_max * 2) + 255) & ~size_t(255);
 }
 
