@@ -123,3 +123,35 @@ def test_drop_in_writes_the_reference_files(native_lib):
             assert v.shape == (80, 4 + 2 * N) and set(np.unique(v[:, 4:4 + N])) <= {0.0, 1.0} and set(np.unique(v[:, 4 + N:])) <= {-1.0, 0.0, 1.0, 2.0}
     case.close()
     shutil.rmtree(case.dir, ignore_errors=True)
+
+
+@pytest.mark.gpu
+def test_sharded_run_writes_byte_identical_files(native_lib):
+    """pa_gbgc_run_from_config cuts the id list into shards (one engine + host thread each, pa_gbgc_app.cpp); chains are keyed by the element
+    number, so every file -- VERBOSE traces included -- is byte-identical for one shard and for three shards on one GPU (and, on a box with
+    several GPUs, for one shard per GPU)."""
+    import phyloacc_b200 as pab
+    import torch
+
+    case = Case("gbgc_chain43")
+    ids = list(range(case.C))
+    runs = {"one": {"PA_DEVICES": "1"}, "three_on_gpu0": {"PA_DEVICE_LIST": "0,0,0", "PA_MIN_ELEMS_PER_DEVICE": "2"}}
+    if torch.cuda.device_count() > 1:
+        runs["per_gpu"] = {"PA_MIN_ELEMS_PER_DEVICE": "2"}
+    outs = {}
+    for tag, env in runs.items():
+        out = os.path.join(case.dir, "s_" + tag)
+        cfg = _gbgc_cfg(case, out, ids)
+        r = subprocess.run([pab.BIN_GBGC_PATH, cfg], capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+        assert r.returncode == 0, (tag, r.stdout[-1500:], r.stderr[-1500:])
+        if tag != "one":
+            assert "# element shards =" in r.stdout
+        outs[tag] = out
+    names = sorted(f for f in os.listdir(outs["one"]) if f not in ("ids.txt", "gbgc.cfg"))
+    assert len(names) > 3 * len(ids)
+    for tag, out in outs.items():
+        assert sorted(f for f in os.listdir(out) if f not in ("ids.txt", "gbgc.cfg")) == names
+        for fn in names:
+            with open(os.path.join(outs["one"], fn), "rb") as fa, open(os.path.join(out, fn), "rb") as fb:
+                assert fa.read() == fb.read(), (tag, fn)
+    case.close()

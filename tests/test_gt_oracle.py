@@ -83,3 +83,43 @@ def test_cuda_gt_replay_matches_reference(native_lib):
     assert np.array_equal(ll2, ll[order])
     eng.close()
     case.close()
+
+
+@pytest.mark.gpu
+def test_gt_replay_on_the_species_tree_equals_the_st_replay(native_lib, tmp_path):
+    """Two independent kernels, one property: a gene tree that IS the species tree (every coalescence exactly at its species node) has the
+    species branch lengths as effective lengths, so pa_engine_gt_replay must give what pa_engine_loglik_replay gives for the same Z and
+    rates -- 43 taxa, elements with gaps and ambiguity codes but no missing species (with missing species the ST path re-roots the tree,
+    which is the same likelihood only as far as pi is stationary for the printed Q: 1e-6)."""
+    import phyloacc_b200 as pab
+    from oracle import frontend as fe
+    from phyloacc_b200 import synth
+
+    stree = synth.make_tree()
+    batch = synth.simulate(stree, C=8, length=150, seed=3, gap_frac=0.03, missing_frac=0.0, ambig_frac=0.01)
+    cfg = synth.write_files(batch, str(tmp_path), prefix="sim", params=dict(BURNIN=5, MCMC=10, CHAIN=1, SEED=1))
+    eng = pab.Engine.from_config(cfg, device=0)
+    tree = fe.parse_mod(fe.load_params(cfg).PHYTREE_FILE)
+    N, S = tree.N, tree.S
+    heights = gt.species_heights(np.asarray(tree.parent), np.asarray(tree.dist), N)
+    children = np.asarray(tree.children).reshape(N, 2)
+    cross = {s: [(s, s)] for s in range(S)}
+    for s in range(S, N):
+        cross[s] = [(int(children[s, 0]), s), (int(children[s, 1]), s), (s, s if s < N - 1 else N)]
+    rng = np.random.default_rng(7)
+    info = eng.run(list(range(batch.C)))
+    states, elem, Zs, nr, cr = [], [], [], [], []
+    for c in range(batch.C):
+        if info.filtered[c]:
+            continue
+        for _ in range(3):
+            Z = rng.integers(0, 3, N).astype(np.int8)
+            n_rate, c_rate = 0.5 + 2 * rng.random(), 0.1 + 0.8 * rng.random()
+            states.append(dict(elem=c, gchild=children, root=N - 1, gmissing=np.zeros(N, bool), gheights=heights, Z=Z, n_rate=n_rate, c_rate=c_rate,
+                               cross=cross))
+            elem.append(c); Zs.append(Z); nr.append(n_rate); cr.append(c_rate)
+    assert len(states) >= 12
+    ll_gt, _, _ = eng.gt_replay(states, heights, np.full(N, 0.01))
+    ll_st = eng.loglik_replay(elem, np.asarray(Zs), nr, cr)
+    assert np.all(np.isfinite(ll_st)) and np.all(np.abs(ll_gt - ll_st) <= 1e-10 * np.abs(ll_st)), np.abs(ll_gt / ll_st - 1).max()
+    eng.close()
