@@ -885,11 +885,16 @@ size_t gbgc_chain_scratch_stride(int n_max, int P_max) {
   return ((d * 8 + (size_t)n_max * P_max * 2) + 255) & ~size_t(255);
 }
 
-// Runs n_chains chains to completion.  Host arrays in, host arrays out (traces [n_chains][5][T], states [n_chains][T][n_max] in the local
-// node order of each element, heads [n_chains][8]); kernel_ms (optional) = the kernel's duration from CUDA events on `stream`.
-int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max,
-                const double* pi, const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
-                const pa_gbgc_params* prm, double* tr_out, uint8_t* zb_out, double* head_out, float* kernel_ms, unsigned long long* counters_out) {
+// One launch of the chain kernel = one WAVE of chains, asynchronous: gbgc_chains_launch uploads the wave's inputs, launches the kernel on the
+// wave's own stream and returns; gbgc_chains_wait blocks until the wave is done and copies its results to the host (traces [n][5][T], states
+// [n][T][n_max] in the local node order of each element, heads [n][8]; counters are ADDED to counters_out).  The caller keeps two waves in
+// flight so that the host-side summaries of one wave run under the kernel of the next (Engine::gbgc_run).
+int gbgc_chains_launch(int device, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max, const double* pi,
+                       const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
+                       const pa_gbgc_params* prm, GbgcWave* w) {
+  // `w` may come back from an earlier wave of the same run: its stream, events and device buffers are reused when they are large enough
+  // (cudaMalloc / cudaFree synchronise the device and would serialise the waves)
+  w->n_chains = 0;
   if (n_chains <= 0) return PA_OK;
   cudaError_t err = cudaSetDevice(device);
   const size_t nc = (size_t)n_chains;
@@ -907,56 +912,85 @@ int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_b
   const int grid = (int)std::min<size_t>(nc, (size_t)std::max(1, num_sms) * std::max(1, per_sm));
   const size_t stride = gbgc_chain_scratch_stride(n_max, P_max);
   const size_t b_in = nc * 8 + 2 * nc * N + 64, b_tr = nc * 5 * T * 8, b_zb = nc * T * n_max, b_head = nc * 8 * 8, b_ctr = 18 * 8;
-  unsigned char *d_in = nullptr, *d_scr = nullptr, *d_out = nullptr;
-  if (err == cudaSuccess) err = cudaMalloc(&d_in, b_in);
-  if (err == cudaSuccess) err = cudaMalloc(&d_scr, stride * grid);
-  if (err == cudaSuccess) err = cudaMalloc(&d_out, b_tr + b_head + b_ctr + b_zb);
+  w->n_chains = n_chains; w->b_tr = b_tr; w->b_zb = b_zb; w->b_head = b_head;
+  if (err == cudaSuccess && !w->stream) err = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);
+  auto ensure = [&](unsigned char*& p, size_t& cap, size_t need) {
+    if (err != cudaSuccess || (p && cap >= need)) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    err = cudaMalloc(&p, need);
+    if (err == cudaSuccess) cap = need;
+  };
+  ensure(w->d_in, w->cap_in, b_in);
+  ensure(w->d_scr, w->cap_scr, stride * grid);
+  ensure(w->d_out, w->cap_out, b_tr + b_head + b_ctr + b_zb);
   GbgcChainLaunch L;
   L.blobs = d_blobs; L.blob_off = d_blob_off; L.n_chains = n_chains; L.N = N; L.n_max = n_max; L.slots_max = slots_max; L.P_max = P_max; L.T = T;
   L.codes_cap = codes_cap;
-  int32_t* di = reinterpret_cast<int32_t*>(d_in);
+  int32_t* di = reinterpret_cast<int32_t*>(w->d_in);
   L.chain_elem = di; L.chain_resz = di + nc;
   int8_t* d8 = reinterpret_cast<int8_t*>(di + 2 * nc);
   L.fixZ = d8; L.upper = d8 + nc * N;
   L.prm = *prm;
   for (int k = 0; k < 4; k++) L.pi[k] = pi[k];
   for (int k = 0; k < 16; k++) L.Q0[k] = Q0[k];
-  L.scratch = d_scr; L.stride = stride;
-  L.tr = reinterpret_cast<double*>(d_out);
+  L.scratch = w->d_scr; L.stride = stride;
+  L.tr = reinterpret_cast<double*>(w->d_out);
   L.head = L.tr + nc * 5 * T;
   L.counters = reinterpret_cast<unsigned long long*>(L.head + nc * 8);
   L.queue = reinterpret_cast<int*>(L.counters + 16);
   L.tr_zb = reinterpret_cast<uint8_t*>(L.counters + 18);
+  w->dev_tr = L.tr; w->dev_head = L.head; w->dev_ctr = L.counters; w->dev_zb = L.tr_zb;
   auto up = [&](const void* dst, const void* src, size_t bytes) {
-    if (err == cudaSuccess) err = cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, w->stream);
   };
   up(L.chain_elem, chain_elem, nc * 4); up(L.chain_resz, chain_resz, nc * 4); up(L.fixZ, fixZ, nc * N); up(L.upper, upper, nc * N);
-  if (err == cudaSuccess) err = cudaMemsetAsync(d_out, 0, b_tr + b_head + b_ctr, stream);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (err == cudaSuccess) err = cudaEventCreate(&e0);
-  if (err == cudaSuccess) err = cudaEventCreate(&e1);
+  if (err == cudaSuccess) err = cudaMemsetAsync(w->d_out, 0, b_tr + b_head + b_ctr, w->stream);
+  if (err == cudaSuccess && !w->e0) err = cudaEventCreate(&w->e0);
+  if (err == cudaSuccess && !w->e1) err = cudaEventCreate(&w->e1);
   if (err == cudaSuccess) {
-    cudaEventRecord(e0, stream);
-    gbgc_chain_kernel<<<grid, kCBD, smem, stream>>>(L);
+    cudaEventRecord(w->e0, w->stream);
+    gbgc_chain_kernel<<<grid, kCBD, smem, w->stream>>>(L);
     err = cudaGetLastError();
-    cudaEventRecord(e1, stream);
+    cudaEventRecord(w->e1, w->stream);
   }
-  if (err == cudaSuccess) err = cudaMemcpyAsync(tr_out, L.tr, b_tr, cudaMemcpyDeviceToHost, stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(head_out, L.head, b_head, cudaMemcpyDeviceToHost, stream);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(zb_out, L.tr_zb, b_zb, cudaMemcpyDeviceToHost, stream);
-  if (err == cudaSuccess && counters_out) err = cudaMemcpyAsync(counters_out, L.counters, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(stream);
-  if (err == cudaSuccess && kernel_ms) cudaEventElapsedTime(kernel_ms, e0, e1);
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  if (d_in) cudaFree(d_in);
-  if (d_scr) cudaFree(d_scr);
-  if (d_out) cudaFree(d_out);
+  if (err != cudaSuccess) {
+    gbgc_chains_release(w);
+    set_error(std::string("gbgc_chains: ") + cudaGetErrorString(err));
+    return PA_ERR_CUDA;
+  }
+  return PA_OK;
+}
+
+int gbgc_chains_wait(GbgcWave* w, double* tr_out, uint8_t* zb_out, double* head_out, unsigned long long* counters_out) {
+  if (w->n_chains <= 0) return PA_OK;
+  cudaError_t err = cudaStreamSynchronize(w->stream);
+  // plain copies into the caller's (pageable) arrays: they run on the copy engine while the next wave's kernel computes
+  if (err == cudaSuccess) err = cudaMemcpy(tr_out, w->dev_tr, w->b_tr, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess) err = cudaMemcpy(head_out, w->dev_head, w->b_head, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess) err = cudaMemcpy(zb_out, w->dev_zb, w->b_zb, cudaMemcpyDeviceToHost);
+  if (err == cudaSuccess && counters_out) {
+    unsigned long long c[16];
+    err = cudaMemcpy(c, w->dev_ctr, sizeof(c), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess)
+      for (int k = 0; k < 16; k++) counters_out[k] += c[k];
+  }
   if (err != cudaSuccess) {
     set_error(std::string("gbgc_chains: ") + cudaGetErrorString(err));
     return PA_ERR_CUDA;
   }
   return PA_OK;
+}
+
+void gbgc_chains_release(GbgcWave* w) {
+  if (w->e0) cudaEventDestroy(w->e0);
+  if (w->e1) cudaEventDestroy(w->e1);
+  if (w->d_in) cudaFree(w->d_in);
+  if (w->d_scr) cudaFree(w->d_scr);
+  if (w->d_out) cudaFree(w->d_out);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  *w = GbgcWave();
 }
 
 }  // namespace pa

@@ -239,36 +239,51 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
       for (size_t q = 0; q + 1 < pl.nodes.size(); q++) fz[pl.nodes[q]] = 1;
     }
   }
-  std::vector<double> tr((size_t)nc * 5 * T), head((size_t)nc * 8);
-  std::vector<uint8_t> zb((size_t)nc * T * n_max);
-  float ms = 0;
-  unsigned long long ctr[16] = {0};
-  {
-    PA_NVTX_RANGE("gbgc_chains");
-    const int rc = gbgc_chains(device, stream, num_sms, d_blobs, d_blob_off, N, n_max, slots_max, P_max, model.tree.pi, model.tree.Q, nc, l_elem.data(),
-                               l_resz.data(), fixZ.data(), upper.data(), prm, tr.data(), zb.data(), head.data(), &ms, ctr);
-    if (rc != PA_OK) return rc;
-  }
-  out->kernel_ms = ms;
-  out->node_pattern_updates = ctr[0];
-  out->chain_iterations = ctr[2];
-  out->pt_builds = ctr[1];
-  out->branch_pattern_updates = ctr[3];
-  out->d2h_bytes = (uint64_t)(tr.size() * 8 + head.size() * 8 + zb.size());
-  for (int k = 0; k < 12; k++) out->phase_cycles[k] = ctr[4 + k];
-  PA_NVTX_RANGE("gbgc_summaries");
+  // ---- waves: the chains go through the device in W launches (every W-th chain of the longest-first order, so the waves are alike), two
+  // in flight; the host-side summaries of wave w (arg-max, medians, frequencies, the variant's Eval2) run under the kernel of wave w + 1
+  const int slots = std::max(1, num_sms) * 3;
+  const int W = nc < 4 * slots ? 1 : std::min(8, nc / (2 * slots));
   const int burn = prm->num_burn, mcmc = prm->num_mcmc;
-  auto summarise = [&](int k) {
-    const int c = order[k];
+  out->kernel_ms = 0;
+  out->d2h_bytes = 0;
+  unsigned long long ctr[16] = {0};
+  struct WaveHost {
+    std::vector<int> ks;  // positions in the launch order
+    std::vector<int32_t> elem, resz;
+    std::vector<int8_t> fixZ, upper;
+    std::vector<double> tr, head;
+    std::vector<uint8_t> zb;
+  };
+  std::vector<WaveHost> wh(W);
+  std::vector<GbgcWave> wd(std::min(W, 3));  // device slots, reused round-robin: wave w runs in slot w % 3
+  for (int k = 0; k < nc; k++) wh[k % W].ks.push_back(k);
+  auto launch = [&](int w) {
+    WaveHost& h = wh[w];
+    const size_t n = h.ks.size();
+    h.elem.resize(n); h.resz.resize(n); h.fixZ.resize(n * N); h.upper.resize(n * N);
+    for (size_t q = 0; q < n; q++) {
+      const int k = h.ks[q];
+      h.elem[q] = l_elem[k];
+      h.resz[q] = l_resz[k];
+      memcpy(h.fixZ.data() + q * N, fixZ.data() + (size_t)k * N, N);
+      memcpy(h.upper.data() + q * N, upper.data() + (size_t)k * N, N);
+    }
+    PA_NVTX_RANGE("gbgc_launch");
+    return gbgc_chains_launch(device, num_sms, d_blobs, d_blob_off, N, n_max, slots_max, P_max, model.tree.pi, model.tree.Q, (int)n, h.elem.data(), h.resz.data(),
+                              h.fixZ.data(), h.upper.data(), prm, &wd[w % 3]);
+  };
+  auto release_all = [&]() {
+    for (GbgcWave& g : wd) gbgc_chains_release(&g);
+  };
+  auto summarise = [&](int c, const double* d, const uint8_t* zbk, const double* hd) {
     const int i = chain_pos[c], mdl = chain_mdl[c];
     const ElemPlan& pl = plans[chain_elem[c]];
     const size_t im = (size_t)i * 3 + mdl;
-    const double* d = tr.data() + (size_t)k * 5 * T;
     std::vector<int8_t> Z((size_t)T * N, -1), B((size_t)T * N, 0);
     const int n = (int)pl.nodes.size();
     for (int m = 0; m < T; m++)
       for (int q = 0; q < n; q++) {
-        const uint8_t b = zb[((size_t)k * T + m) * n_max + q];
+        const uint8_t b = zbk[(size_t)m * n_max + q];
         Z[(size_t)m * N + pl.nodes[q]] = (int8_t)(b & 3);
         B[(size_t)m * N + pl.nodes[q]] = (int8_t)(b >> 2);
       }
@@ -305,24 +320,56 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
     }
     GbgcChainView v{T, N, burn, mcmc, chain_resz[c], d, d + T, d + 2 * (size_t)T, d + 3 * (size_t)T, d + 4 * (size_t)T, Z.data(), B.data(), &pl};
     out->loglik[im] = gbgc_eval2(v, mz, best);
-    out->accept[im * 2] = (int32_t)head[(size_t)k * 8 + 1];
-    out->accept[im * 2 + 1] = (int32_t)head[(size_t)k * 8 + 2];
+    out->accept[im * 2] = (int32_t)hd[1];
+    out->accept[im * 2 + 1] = (int32_t)hd[2];
     if (out->trace) memcpy(out->trace + im * 5 * T, d, sizeof(double) * 5 * T);
     if (out->trace_z) memcpy(out->trace_z + im * (size_t)T * N, Z.data(), (size_t)T * N);
     if (out->trace_b) memcpy(out->trace_b + im * (size_t)T * N, B.data(), (size_t)T * N);
   };
+  int rc = launch(0);
+  if (rc == PA_OK && W > 1) rc = launch(1);
+  if (rc != PA_OK) { release_all(); return rc; }
+  cudaEvent_t e_first = wd[0].e0;  // start of the first kernel: the reported kernel time is the span to the end of the last one
+  wd[0].e0 = nullptr;            // (slot 0 gets a new start event when it is launched again)
   const int nthr = std::max(1, std::min<int>(16, (int)std::thread::hardware_concurrency()));
-  std::vector<std::thread> pool;
-  std::atomic<int> next{0};
-  for (int t = 0; t < nthr; t++)
-    pool.emplace_back([&]() {
-      for (;;) {
-        const int k = next.fetch_add(1);
-        if (k >= nc) break;
-        summarise(k);
-      }
-    });
-  for (auto& th : pool) th.join();
+  for (int w = 0; w < W; w++) {
+    WaveHost& h = wh[w];
+    const size_t n = h.ks.size();
+    h.tr.resize(n * 5 * T); h.head.resize(n * 8); h.zb.resize(n * (size_t)T * n_max);
+    {
+      PA_NVTX_RANGE("gbgc_wait");
+      rc = gbgc_chains_wait(&wd[w % 3], h.tr.data(), h.zb.data(), h.head.data(), ctr);
+    }
+    if (rc == PA_OK && e_first && wd[w % 3].e1) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, e_first, wd[w % 3].e1) == cudaSuccess) out->kernel_ms = std::max(out->kernel_ms, (double)ms);
+    }
+    if (rc == PA_OK && w + 2 < W) rc = launch(w + 2);
+    if (rc != PA_OK) break;
+    out->d2h_bytes += (uint64_t)(h.tr.size() * 8 + h.head.size() * 8 + h.zb.size());
+    PA_NVTX_RANGE("gbgc_summaries");
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next{0};
+    for (int t = 0; t < nthr; t++)
+      pool.emplace_back([&]() {
+        for (;;) {
+          const size_t q = next.fetch_add(1);
+          if (q >= n) break;
+          summarise(order[h.ks[q]], h.tr.data() + q * 5 * T, h.zb.data() + q * (size_t)T * n_max, h.head.data() + q * 8);
+        }
+      });
+    for (auto& th : pool) th.join();
+    std::vector<double>().swap(h.tr);
+    std::vector<uint8_t>().swap(h.zb);
+  }
+  if (e_first) cudaEventDestroy(e_first);
+  release_all();
+  if (rc != PA_OK) return rc;
+  out->node_pattern_updates = ctr[0];
+  out->chain_iterations = ctr[2];
+  out->pt_builds = ctr[1];
+  out->branch_pattern_updates = ctr[3];
+  for (int k = 0; k < 12; k++) out->phase_cycles[k] = ctr[4 + k];
   return PA_OK;
 }
 

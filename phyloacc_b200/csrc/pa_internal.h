@@ -157,9 +157,20 @@ int gbgc_integrate(int device, cudaStream_t stream, const uint8_t* d_blobs, cons
                    const double* Q0, int n_states, const int32_t* elem, const int8_t* Z, const int8_t* B, const int8_t* fixZ, const int8_t* upper,
                    const double* sel_n, const double* sel_c, const double* gbc, double grate, double lrate, double prior_gb, double cons_to_mis,
                    double ncons_to_mis, double* post_out, double* emis_out, double* root_out);  // pa_gbgc.cu
-int gbgc_chains(int device, cudaStream_t stream, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max,
-                const double* pi, const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
-                const pa_gbgc_params* prm, double* tr_out, uint8_t* zb_out, double* head_out, float* kernel_ms, unsigned long long* counters_out);  // pa_gbgc_chain.cu
+struct GbgcWave {  // one asynchronous launch of the GBGC chain kernel (pa_gbgc_chain.cu)
+  unsigned char *d_in = nullptr, *d_scr = nullptr, *d_out = nullptr;
+  void *dev_tr = nullptr, *dev_head = nullptr, *dev_ctr = nullptr, *dev_zb = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;  // around the kernel
+  int n_chains = 0;
+  size_t b_tr = 0, b_zb = 0, b_head = 0;
+  size_t cap_in = 0, cap_scr = 0, cap_out = 0;
+};
+int gbgc_chains_launch(int device, int num_sms, const uint8_t* d_blobs, const int64_t* d_blob_off, int N, int n_max, int slots_max, int P_max, const double* pi,
+                       const double* Q0, int n_chains, const int32_t* chain_elem, const int32_t* chain_resz, const int8_t* fixZ, const int8_t* upper,
+                       const pa_gbgc_params* prm, GbgcWave* w);
+int gbgc_chains_wait(GbgcWave* w, double* tr_out, uint8_t* zb_out, double* head_out, unsigned long long* counters_out);
+void gbgc_chains_release(GbgcWave* w);
 void plan_element(const Model& m, const uint8_t* X, int64_t G, int64_t start, int32_t len, int elem_id, ElemPlan& out);
 
 }  // namespace pa

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out/gbgc10
+timeout 900 python -m pytest tests/test_gbgc_chain.py tests/test_gbgc_oracle.py tests/test_gbgc_dropin.py -m gpu -x -q -W ignore 2>&1 | tail -5 | tee gpurun_out/gbgc10/pytest.txt
+timeout 900 python bench.py --workload cfg4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/gbgc10/bench_cfg4.json 2> gpurun_out/gbgc10/bench_cfg4.err
+python - <<'PY'
+import json
+l=json.loads(open("gpurun_out/gbgc10/bench_cfg4.json").read().strip().split("\n")[-1])
+print("value", l["value"], "e2e", l["e2e"]["value"], "ms", l["ms_per_step"], "frac", l["roofline"]["frac"])
+PY
+tail -3 gpurun_out/gbgc10/bench_cfg4.err
