@@ -909,8 +909,14 @@ int gbgc_chains_launch(int device, int num_sms, const uint8_t* d_blobs, const in
     set_error("gbgc_chains: the tree does not fit the chain kernel's shared memory");
     return PA_ERR_ARG;
   }
-  const int grid = (int)std::min<size_t>(nc, (size_t)std::max(1, num_sms) * std::max(1, per_sm));
+  int grid = (int)std::min<size_t>(nc, (size_t)std::max(1, num_sms) * std::max(1, per_sm));
   const size_t stride = gbgc_chain_scratch_stride(n_max, P_max);
+  {  // one very long element inflates every CTA's scratch: fewer resident CTAs rather than an out-of-memory failure (three wave slots share the device)
+    size_t free_b = 0, total_b = 0;
+    if (err == cudaSuccess && !w->d_scr && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && stride * (size_t)grid > free_b / 5)
+      grid = (int)std::max<size_t>(1, (free_b / 5) / stride);
+    if (w->d_scr && w->cap_scr < stride * (size_t)grid) grid = (int)std::max<size_t>(1, w->cap_scr / stride);
+  }
   const size_t b_in = nc * 8 + 2 * nc * N + 64, b_tr = nc * 5 * T * 8, b_zb = nc * T * n_max, b_head = nc * 8 * 8, b_ctr = 18 * 8;
   w->n_chains = n_chains; w->b_tr = b_tr; w->b_zb = b_zb; w->b_head = b_head;
   if (err == cudaSuccess && !w->stream) err = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking);

@@ -87,6 +87,40 @@ def test_cuda_chain_matches_the_oracle_draw_for_draw(native_lib):
 
 
 @pytest.mark.gpu
+def test_cuda_chain_on_long_elements_matches_the_oracle(native_lib, tmp_path):
+    """1500-bp elements: ~1000 site patterns, i.e. eight pattern tiles per pass (the per-warp pair sums accumulate across tiles) and tip codes
+    too large for the shared-memory staging buffer (read from the element image instead) -- paths the 200-bp fixtures never take."""
+    import phyloacc_b200 as pab
+    from oracle import frontend as fe
+    from phyloacc_b200 import synth
+
+    stree = synth.make_tree()
+    batch = synth.simulate(stree, C=2, length=1500, seed=8, gap_frac=0.01, missing_frac=0.03, ambig_frac=0.002)
+    cfg = synth.write_files(batch, str(tmp_path), prefix="sim", params=dict(BURNIN=3, MCMC=6, CHAIN=1, SEED=1, GAPCHAR="-"))
+    P = fe.load_params(cfg)
+    otree = fe.parse_mod(P.PHYTREE_FILE)
+    names, X = fe.load_fasta(P.ALIGN_FILE)
+    _, pos = fe.load_bed(P.SEG_FILE)
+    starts, lens = fe.element_layout(pos)
+    model = fe.build_model(otree, P)
+    X = fe.reorder_alignment(otree, names, X)
+    eng = pab.Engine.from_config(cfg, device=0)
+    burn, mcmc, seed = 3, 6, 31
+    out = eng.gbgc_run([0, 1], stree.targets, traces=True, num_burn=burn, num_mcmc=mcmc, seed=seed)
+    Q0 = np.asarray(otree.Q, float).reshape(4, 4)
+    for c in range(2):
+        el = fe.element_frontend(model, X, int(starts[c]), int(lens[c]))
+        assert fe.compress_patterns(el.masks).weights.shape[0] > 600
+        for mdl in (0, 2):
+            par = gbgc.GbgcParams(num_burn=burn, num_mcmc=mcmc)
+            tr = gbgc.GbgcChain(Q0, otree.pi, el, otree.N, otree.S, MODELS[mdl], stree.targets, model.upper, par, seed, c * 4 + MODELS[mdl]).run()
+            assert np.array_equal(out["trace_z"][c, mdl], tr["Z"]) and np.array_equal(out["trace_b"][c, mdl], tr["B"]), (c, mdl)
+            for row, key in ((0, "loglik"), (1, "full"), (2, "c"), (3, "n"), (4, "gb")):
+                assert np.allclose(out["trace"][c, mdl][row], tr[key], rtol=1e-9, atol=1e-9), (c, mdl, key)
+    eng.close()
+
+
+@pytest.mark.gpu
 def test_cuda_chain_states_replay_to_their_recorded_likelihoods(native_lib):
     """Every recorded state of a chain, replayed from scratch by pa_engine_gbgc_replay (an independent kernel), gives the recorded
     log P(X | Z, B, r) to 1e-10 (north_star's replay criterion)."""
