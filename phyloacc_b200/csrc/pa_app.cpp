@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "pa_app.h"
+#include "pa_fmt.h"
 #include "pa_engine.h"
 #include "pa_nvtx.h"
 #include "pa_internal.h"
@@ -317,11 +318,20 @@ static int run_from_config(const char* cfg_path) {
                 ot << std::endl;
               } else ot.open(path.c_str(), std::ios::app);
               const int T = (int)tr.loglik.size();
+              std::string buf;
+              buf.reserve((size_t)T * (6 * 16 + 3 * N + 2));
               for (int t = 0; t < T; t++) {
-                ot << tr.loglik[t] << "\t" << tr.n_rate[t] << "\t" << tr.c_rate[t] << "\t" << tr.g_rate[t] << "\t" << tr.l_rate[t] << "\t" << tr.l2_rate[t] << "\t";
-                for (int s = 0; s < N; s++) ot << (int)tr.Z[(size_t)t * N + s] << "\t";
-                ot << std::endl;
+                for (const double v : {tr.loglik[t], tr.n_rate[t], tr.c_rate[t], tr.g_rate[t], tr.l_rate[t], tr.l2_rate[t]}) {
+                  fmt_g(buf, v, 8);
+                  buf.push_back('\t');
+                }
+                for (int s = 0; s < N; s++) {
+                  fmt_i(buf, tr.Z[(size_t)t * N + s]);
+                  buf.push_back('\t');
+                }
+                buf.push_back('\n');
               }
+              ot.write(buf.data(), (std::streamsize)buf.size());
             }
           }
         }
@@ -333,16 +343,29 @@ static int run_from_config(const char* cfg_path) {
       return 1;
     }
     // rows of _rate_postZ_Mk.txt (Output_init, bpp_c2.cpp:776-783; default ofstream precision = 6 significant digits)
-    for (int i = 0; i < n; i++) {
-      if (filtered[i]) continue;
+    {
+      PA_NVTX_RANGE("write rate_postZ");
+      const int n_chunks = std::max(1, std::min(n, 4 * std::max(1, P.num.num_thread)));
       for (int m = 0; m < 3; m++) {
         if (P.sample_hyper && m != PA_M2) continue;
-        const double* md = &med[((size_t)i * 3 + m) * 5];
-        out_Z[m] << ids[i] << "\t" << md[0] << "\t" << md[1] << "\t" << md[2] << "\t" << md[3] << "\t" << md[4];
-        const double* pz = &postZ[(((size_t)i * 3 + m) * N) * 4];
-        for (int s = 0; s < N; s++)
-          for (int k = 0; k < 4; k++) out_Z[m] << "\t" << pz[s * 4 + k];
-        out_Z[m] << std::endl;
+        std::vector<std::string> chunk(n_chunks);  // rows of contiguous element ranges, formatted by all host threads
+#pragma omp parallel for schedule(dynamic) num_threads(std::max(1, P.num.num_thread))
+        for (int ch = 0; ch < n_chunks; ch++) {
+          std::string& b = chunk[ch];
+          const int lo = (int)((long long)n * ch / n_chunks), hi = (int)((long long)n * (ch + 1) / n_chunks);
+          b.reserve((size_t)(hi - lo) * (64 + (size_t)N * 4 * 6));
+          for (int i = lo; i < hi; i++) {
+            if (filtered[i]) continue;
+            const double* md = &med[((size_t)i * 3 + m) * 5];
+            fmt_i(b, ids[i]);
+            for (int k = 0; k < 5; k++) { b.push_back('\t'); fmt_g(b, md[k]); }
+            const double* pz = &postZ[(((size_t)i * 3 + m) * N) * 4];
+            for (int k = 0; k < 4 * N; k++) { b.push_back('\t'); fmt_g(b, pz[k]); }
+            b.push_back('\n');
+          }
+        }
+        for (const std::string& b : chunk) out_Z[m].write(b.data(), (std::streamsize)b.size());
+        out_Z[m].flush();
       }
     }
     if (P.sample_hyper) {
@@ -387,11 +410,14 @@ static int run_from_config(const char* cfg_path) {
         oz << "No.";
         for (int s = 0; s < N; s++) oz << "\t" << tree.names[s];
         oz << std::endl;
+        std::string b;
+        b.reserve((size_t)n * (12 + 3 * (size_t)N));
         for (int i = 0; i < n; i++) {
-          oz << ids[i];
-          for (int s = 0; s < N; s++) oz << "\t" << (int)maxZ[((size_t)i * 3 + m) * N + s];
-          oz << std::endl;
+          fmt_i(b, ids[i]);
+          for (int s = 0; s < N; s++) { b.push_back('\t'); fmt_i(b, maxZ[((size_t)i * 3 + m) * N + s]); }
+          b.push_back('\n');
         }
+        oz.write(b.data(), (std::streamsize)b.size());
       }
     }
   }

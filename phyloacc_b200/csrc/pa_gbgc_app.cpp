@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "pa_app.h"
+#include "pa_fmt.h"
 #include "pa_nvtx.h"
 
 namespace pa {
@@ -298,14 +299,14 @@ int run_gbgc_from_config(const char* cfg_path) {
           for (int s = 0; s < N; s++) maxZ_full[(size_t)c * N + s] = mz[((size_t)i * 3 + 2) * N + s];
           for (int m = 0; m < 3; m++) {
             // Output_init (GBGC/SRC/bpp_c2.cpp:603-650): default stream formatting (6 significant digits)
-            std::ostringstream row;
+            std::string& row = rows[gi * 3 + m];
+            row.clear();
             const double* md = &med[((size_t)i * 3 + m) * 3];
-            row << c << "\t" << md[0] << "\t" << md[1] << "\t" << md[2];
-            for (int s = 0; s < N; s++) row << "\t" << pb[((size_t)i * 3 + m) * N + s];
-            for (int s = 0; s < N; s++)
-              for (int k = 0; k < 4; k++) row << "\t" << pz[(((size_t)i * 3 + m) * N + s) * 4 + k];
-            row << "\n";
-            rows[gi * 3 + m] = row.str();
+            fmt_i(row, c);
+            for (int k = 0; k < 3; k++) { row.push_back('\t'); fmt_g(row, md[k]); }
+            for (int s = 0; s < N; s++) { row.push_back('\t'); fmt_g(row, pb[((size_t)i * 3 + m) * N + s]); }
+            for (int k = 0; k < 4 * N; k++) { row.push_back('\t'); fmt_g(row, pz[((size_t)i * 3 + m) * N * 4 + k]); }
+            row.push_back('\n');
             if (!P.verbose) continue;
             // Output_sampling (bpp_c2.cpp:567-600): log P(X, Z, B, r), n_rate, c_rate, gBC, B per node, Z per node; 8 significant digits
             const std::string path = prefix + "_mcmc_trace_" + std::to_string(kFileOfModel[m]) + "_" + std::to_string(c) + ".txt";
@@ -321,12 +322,18 @@ int run_gbgc_from_config(const char* cfg_path) {
             const double* t5 = &tr[((size_t)i * 3 + m) * 5 * T];
             const int8_t* z = &tz[((size_t)i * 3 + m) * T * N];
             const int8_t* b = &tb[((size_t)i * 3 + m) * T * N];
+            std::string buf;
+            buf.reserve((size_t)T * (4 * 16 + 5 * (size_t)N + 2));
             for (int t = 0; t < T; t++) {
-              ot << t5[(size_t)T + t] << "\t" << t5[(size_t)3 * T + t] << "\t" << t5[(size_t)2 * T + t] << "\t" << t5[(size_t)4 * T + t] << "\t";
-              for (int s = 0; s < N; s++) ot << (int)b[(size_t)t * N + s] << "\t";
-              for (int s = 0; s < N; s++) ot << (int)z[(size_t)t * N + s] << "\t";
-              ot << "\n";
+              for (const double v : {t5[(size_t)T + t], t5[(size_t)3 * T + t], t5[(size_t)2 * T + t], t5[(size_t)4 * T + t]}) {
+                fmt_g(buf, v, 8);
+                buf.push_back('\t');
+              }
+              for (int s = 0; s < N; s++) { fmt_i(buf, b[(size_t)t * N + s]); buf.push_back('\t'); }
+              for (int s = 0; s < N; s++) { fmt_i(buf, z[(size_t)t * N + s]); buf.push_back('\t'); }
+              buf.push_back('\n');
             }
+            ot.write(buf.data(), (std::streamsize)buf.size());
           }
         }
       }
