@@ -39,16 +39,36 @@ static int load_config_inputs(const char* cfg_path, ConfigInputs& in) {
 }
 
 // LoadPhyloProfiles + LoadPhyloTree + id selection for parameters already in in.P (shared by the ST and GBGC front doors)
+// PA_TIMING=1: wall time of the host stages on stderr (where the time of a genome-scale batch goes outside the kernels)
+struct StageTimer {
+  const bool on = getenv("PA_TIMING") != nullptr;
+  double t0 = now();
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now();
+    std::cerr << "[pa timing] " << what << ": " << (t - t0) << " s" << std::endl;
+    t0 = t;
+  }
+};
+
 int load_inputs(ConfigInputs& in) {
   Params& P = in.P;
   Alignment aln;
+  StageTimer tm;
   if (!load_alignment_files(P.align_path, P.segment_path, aln)) return PA_ERR_IO;
+  tm.mark("FASTA + BED");
   std::cout << "Loading phylogenetic tree from " << P.phytree_path << "......" << std::endl;
   if (!load_tree(P.phytree_path, in.tree)) return PA_ERR_IO;
   if (!match_alignment_to_tree(in.tree, aln)) {
     set_error("alignment has fewer species than the tree");
     return PA_ERR_ARG;
   }
+  tm.mark("tree + row matching");
   const Tree& tree = in.tree;
   in.og = species_ids(tree, P.outgroup);
   in.cg = species_ids(tree, P.conservegroup);
@@ -74,6 +94,7 @@ int load_inputs(ConfigInputs& in) {
   }
   in.elem_start = aln.elem_start;
   in.elem_len = aln.elem_len;
+  tm.mark("alignment matrix");
   return PA_OK;
 }
 
@@ -109,9 +130,12 @@ static int create_from_config(const char* cfg_path, int device, pa_engine** out)
   int rc = load_config_inputs(cfg_path, in);
   if (rc != PA_OK) return rc;
   pa_engine* e = nullptr;
+  StageTimer tm;
   rc = make_engine(in, device, 0, &e);
   if (rc != PA_OK) return rc;
+  tm.mark("engine");
   rc = e->eng.load_alignment(in.X.data(), in.G, in.C, in.elem_start.data(), in.elem_len.data());
+  tm.mark("integer front-end + upload");
   if (rc != PA_OK) {
     delete e;
     return rc;

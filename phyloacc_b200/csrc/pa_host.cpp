@@ -257,30 +257,60 @@ bool load_tree(const std::string& path, Tree& t) {  // LoadPhyloTree (newick.cpp
 
 // ------------------------------------------------------------------------------------------ FASTA / BED / ids
 bool load_alignment_files(const std::string& fasta, const std::string& bed, Alignment& a) {  // profile.cpp:17-126
-  std::ifstream in(fasta.c_str());
-  if (!in) {
-    set_error("Cannot open the phylogenetic profile input file: " + fasta);
-    return false;
+  // The whole file in one read, one pass over its lines without per-line string objects (the getline / trim / append loop of the reference
+  // took 1.6 s for the 146 MB of a 16384-element batch): same rules -- every line trimmed of " \t\n" at both ends, a trimmed line that
+  // starts with '>' opens a record (name = the rest, trimmed), any other line is appended to the current record, lower-cased.
+  std::string buf;
+  {
+    FILE* f = fopen(fasta.c_str(), "rb");
+    if (!f) {
+      set_error("Cannot open the phylogenetic profile input file: " + fasta);
+      return false;
+    }
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = buf.empty() ? 0 : fread(&buf[0], 1, buf.size(), f);
+    fclose(f);
+    buf.resize(got);
   }
-  std::string line, whole;
+  unsigned char lower[256];
+  for (int c = 0; c < 256; c++) lower[c] = (unsigned char)((c >= 'A' && c <= 'Z') ? c - 'A' + 'a' : c);
+  auto is_ws = [](char c) { return c == ' ' || c == '\t' || c == '\n'; };
+  std::string whole;
   bool first = true;
-  auto lower = [](std::string& s) { for (auto& c : s) c = (char)tolower((unsigned char)c); };
-  while (std::getline(in, line)) {
-    line = trim(line);
-    if (!line.empty() && line[0] == '>') {
-      a.species_names.push_back(trim(line.substr(1)));
+  const char* base = buf.data();
+  const size_t size = buf.size();
+  size_t p = 0;
+  while (p < size) {
+    const char* nl = (const char*)memchr(base + p, '\n', size - p);
+    size_t e = nl ? (size_t)(nl - base) : size;
+    const size_t next = e + 1;
+    size_t b0 = p;
+    while (b0 < e && is_ws(base[b0])) b0++;
+    while (e > b0 && is_ws(base[e - 1])) e--;
+    if (e > b0 && base[b0] == '>') {
+      a.species_names.push_back(trim(std::string(base + b0 + 1, e - b0 - 1)));
       if (!first) {
-        lower(whole);
-        a.X.push_back(whole);
+        const size_t len = whole.size();
+        a.X.push_back(std::move(whole));
+        whole.clear();
+        whole.reserve(len);
       }
       first = false;
-      whole.clear();
-    } else {
-      whole += line;
+    } else if (e > b0) {
+      const size_t old = whole.size();
+      whole.resize(old + (e - b0));
+      unsigned char* dst = reinterpret_cast<unsigned char*>(&whole[old]);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(base + b0);
+      for (size_t k = 0; k < e - b0; k++) dst[k] = lower[src[k]];
     }
+    p = next;
   }
-  lower(whole);
-  a.X.push_back(whole);
+  a.X.push_back(std::move(whole));
+  std::string().swap(buf);
+  std::string line;
   a.S = (int)a.species_names.size();
   a.G = a.X.empty() ? 0 : (int64_t)a.X[0].size();
   for (auto& row : a.X)
