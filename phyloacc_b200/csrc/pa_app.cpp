@@ -190,6 +190,7 @@ static int run_from_config(const char* cfg_path) {
     std::cerr << "(Error. " << get_error() << ")" << std::endl;
     return 1;
   }
+  StageTimer tm;
   const Params& P = in.P;
   const Tree& tree = in.tree;
   const int N = tree.N;
@@ -296,6 +297,7 @@ static int run_from_config(const char* cfg_path) {
     destroy_all();
     return 1;
   }
+  tm.mark("file headers, engines (CUDA contexts), integer front-end + upload of every shard");
   for (int iter = 0; iter < P.num_chain; iter++) {
     std::cout << "Running MCMC chain " << iter + 1 << " ..." << std::endl;
     const bool ok = for_each_device([&](int d) {
@@ -366,6 +368,7 @@ static int run_from_config(const char* cfg_path) {
       destroy_all();
       return 1;
     }
+    tm.mark("chains + summaries + collect of every wave");
     // rows of _rate_postZ_Mk.txt (Output_init, bpp_c2.cpp:776-783; default ofstream precision = 6 significant digits)
     {
       PA_NVTX_RANGE("write rate_postZ");
@@ -446,7 +449,9 @@ static int run_from_config(const char* cfg_path) {
     }
   }
   for (int m = 0; m < 3; m++) out_Z[m].close();
+  tm.mark("result files");
   destroy_all();
+  tm.mark("engines released");
   std::cout << std::endl << std::endl << "time used:  " << (time(NULL) - start) / 60 << " min." << std::endl << std::endl;
   return 0;
 }
