@@ -52,6 +52,37 @@ def test_binary_probe_and_output_folder_check(native_lib):
     case.close()
 
 
+def test_program_fails_loudly_without_a_gpu_and_on_bad_input(native_lib, tmp_path):
+    """No CPU fallback in the GBGC program either: with a valid parameter file and no CUDA device it parses everything, then stops with exit
+    code 1 and says why.  A parameter file that does not exist, SAMPLE_HYPER 1 and a chain too short for the estimator are refused before
+    any data is read."""
+    import phyloacc_b200 as pab
+    import torch
+
+    case = Case("gbgc_chain43")
+    out = str(tmp_path / "o")
+    cfg = _gbgc_cfg(case, out, [0, 1])
+    r = subprocess.run([pab.BIN_GBGC_PATH, str(tmp_path / "missing.cfg")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Cannot open the parameters file" in r.stderr
+    if os.path.exists(REF):
+        ref = subprocess.run([REF, str(tmp_path / "missing.cfg")], capture_output=True, text=True)
+        assert ref.returncode == 1 and "Cannot open the parameters file" in ref.stderr
+    for extra, msg in (("SAMPLE_HYPER 1\n", "SAMPLE_HYPER 1 is not supported"), ("MCMC 1\n", "MCMC >= 2")):
+        with open(cfg) as f:
+            body = f.read()
+        bad = str(tmp_path / "bad.cfg")
+        with open(bad, "w") as f:
+            f.write(body + extra)
+        r = subprocess.run([pab.BIN_GBGC_PATH, bad], capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (extra, r.stderr)
+    if not torch.cuda.is_available():
+        r = subprocess.run([pab.BIN_GBGC_PATH, cfg], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1
+        assert "no usable CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+        assert not any(f.endswith("_elem_lik.txt") for f in os.listdir(out))
+    case.close()
+
+
 def _table(path):
     with open(path) as f:
         lines = f.read().split("\n")
