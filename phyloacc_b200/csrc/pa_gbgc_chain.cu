@@ -182,9 +182,12 @@ __device__ bool messages_lin(const Sh& s, const double* src, int n, int n_up, in
         }
         int ex = 0;
         if (mx > 0.0) {
-          ex = ilogb(mx);
+          if (mx < 0x1p-200) {  // renormalise by an exact power of two, and only when the weights have drifted far down
+            ex = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+            const double up2 = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
 #pragma unroll
-          for (int k = 0; k < 6; k++) w[k] = scalbn(w[k], -ex);
+            for (int k = 0; k < 6; k++) w[k] *= up2;
+          }
         } else {
           bad_w = 1;
         }
@@ -658,7 +661,16 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
             if (k + 1 < nd) fetch(k + 1);
             // 16 weighted pairs of this pattern into the warp's transposition tile [16][33], then lane (e, h) adds up element e of the patterns
             // 16 h .. 16 h + 15 in order and the two halves meet in one shuffle: 16 STS + 16 LDS + 16 DADD instead of a 31-shuffle butterfly
-            if (act) {
+            // an unambiguous tip (one base a*): ratio[b] PL[b][a*] = qp[b], so its pairs are w qp[b] in row a*, nothing else to compute
+            const bool tip1 = act && src < 0 && ((Lv[0] + Lv[1]) + (Lv[2] + Lv[3])) == 1.0;
+            if (tip1) {
+#pragma unroll
+              for (int b = 0; b < 4; b++) {
+                const double v = qp[b] * w;
+#pragma unroll
+                for (int a = 0; a < 4; a++) rt[(a * 4 + b) * 33 + lane] = Lv[a] * v;
+              }
+            } else if (act) {
               const double* Pi = s.Pm + i * 16;
               double PL[16], ratio[4];
 #pragma unroll
