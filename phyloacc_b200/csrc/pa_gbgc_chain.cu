@@ -76,6 +76,9 @@ __host__ __device__ inline size_t uni_doubles(int n_max, int slots_max) {
 struct Sh {  // shared-memory views of one chain
   double *Pm, *uni, *red, *emis, *emis_t, *back, *Qc, *scal, *msg, *lsum, *pw, *mu;
   int *stack_sc, *msc;
+  uint4* up_ch;   // upward program: per internal node (Sethi-Ullman order) both children resolved: {node | kind << 16, tip row or stack slot} x 2
+  uint2* up_self; // ... and the node itself: {node | stack slot << 16, arena index}
+  int n_upprog;
   int16_t *child, *tiprow, *su, *intidx, *parent, *up_nodes, *up_off, *down_nodes, *down_off, *dn_node, *dn_src, *dn_par;
   uint8_t *flags, *fix, *upr, *codes_s;
   int8_t *slot, *Z, *B, *Zn, *Bn;
@@ -213,14 +216,79 @@ __device__ bool messages_lin(const Sh& s, const double* src, int n, int n_up, in
 }
 
 // log P(X | Z, B, r): the upward pass at the matrices in s.Pm over the element's site patterns (thread = pattern, partials on a shared-memory
-// stack, every internal node's partial also written to the arena for the downward pass)
+// stack, every internal node's partial also written to the arena for the downward pass).  Same arithmetic, in the same order, as
+// prune_pattern<false, true> (pa_device.cuh), but driven by a per-chain RESOLVED program (s.up_ch / s.up_self, built once per chain): one
+// broadcast 16-byte load tells a step what both children are and where their data lies, instead of a chain of dependent look-ups
+// (order -> children -> flags -> tip row / slot).
 __device__ double upward_pass(const Sh& s, const ElemHeader* h, const uint8_t* codes, const uint16_t* weights, double* gpart, int16_t* gsc,
-                                           const double* pi, int tid) {
-  const TreeSmem ts{s.child, s.flags, s.tiprow, s.su, s.slot, s.intidx};
-  const int P = h->P, Ppad = h->Ppad;
+                              const double* pi, int tid) {
+  const int P = h->P, Ppad = h->Ppad, half = Ppad >> 1, root = h->n - 1, np = s.n_upprog;
+  double* stack = s.uni;
   double acc = 0.0;
-  for (int p = tid; p < Ppad; p += kCBD)
-    if (p < P) acc += (double)weights[p] * prune_pattern<false, true, false>(h, ts, codes, s.Pm, nullptr, s.uni, s.stack_sc, gpart, gsc, pi, p, kCBD, tid);
+  for (int p = tid; p < Ppad; p += kCBD) {
+    if (p >= P) continue;
+    double root_l[4] = {1.0, 1.0, 1.0, 1.0};
+    int root_sc = 0;
+    for (int k = 0; k < np; k++) {
+      const uint4 d = s.up_ch[k];
+      const uint2 me = s.up_self[k];
+      double out[4] = {1.0, 1.0, 1.0, 1.0};
+      int sc = 0;
+#pragma unroll
+      for (int cc = 0; cc < 2; cc++) {
+        const uint32_t cx = cc ? d.z : d.x, cy = cc ? d.w : d.y;
+        const uint32_t kind = cx >> 16;
+        if (kind == 0) continue;  // missing child
+        const double* Pc = s.Pm + (cx & 0xffffu) * 16;
+        if (kind == 1) {
+          const uint32_t byte = codes[(size_t)cy * half + (p >> 1)];
+          const uint32_t code = (byte >> ((p & 1) * 4)) & 15u;
+          if (code == 15u) continue;  // gap / N
+          if ((code & (code - 1)) == 0) {
+            const int bb = __ffs(code) - 1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) out[j] *= Pc[j * 4 + bb];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              double m = 0;
+#pragma unroll
+              for (int bb = 0; bb < 4; bb++) m += ((code >> bb) & 1u) ? Pc[j * 4 + bb] : 0.0;
+              out[j] *= m;
+            }
+          }
+        } else {
+          double Lc[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) Lc[i] = stack[(cy * 4 + i) * kCBD + tid];
+          sc += s.stack_sc[cy * kCBD + tid];
+#pragma unroll
+          for (int j = 0; j < 4; j++) out[j] *= ((Pc[j * 4 + 0] * Lc[0] + Pc[j * 4 + 1] * Lc[1]) + Pc[j * 4 + 2] * Lc[2]) + Pc[j * 4 + 3] * Lc[3];
+        }
+      }
+      const double mx = fmax(fmax(out[0], out[1]), fmax(out[2], out[3]));
+      if (mx < PA_SCALE_THRESH && mx > 0.0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] *= PA_SCALE_UP;
+        sc += 1;
+      }
+      const uint32_t sl = me.x >> 16;
+#pragma unroll
+      for (int j = 0; j < 4; j++) stack[(sl * 4 + j) * kCBD + tid] = out[j];
+      s.stack_sc[sl * kCBD + tid] = sc;
+      double2* g2 = reinterpret_cast<double2*>(gpart + ((size_t)me.y * Ppad + p) * 4);
+      g2[0] = make_double2(out[0], out[1]);
+      g2[1] = make_double2(out[2], out[3]);
+      gsc[(size_t)me.y * Ppad + p] = (int16_t)sc;
+      if ((int)(me.x & 0xffffu) == root) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) root_l[j] = out[j];
+        root_sc = sc;
+      }
+    }
+    const double lik = ((pi[0] * root_l[0] + pi[1] * root_l[1]) + pi[2] * root_l[2]) + pi[3] * root_l[3];
+    acc += (double)weights[p] * (log(lik) - root_sc * PA_LOG_SCALE);
+  }
   const double v = block_sum(acc, s.red, tid, kCBD);
   __syncthreads();
   return v;
@@ -389,7 +457,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_chain, s_flag, s_bufA, s_bufW;
   __shared__ long long s_ph[12], s_t0;
-  __shared__ int s_ntask, s_nbranch, s_ndown;
+  __shared__ int s_ntask, s_nbranch, s_ndown, s_nup;
   __shared__ double s_pi[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_max = L.n_max, slots_max = L.slots_max, N = L.N, T = L.T;
@@ -397,6 +465,8 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
   {
     double* d = reinterpret_cast<double*>(smem_raw);
     s.Pm = d; d += (size_t)n_max * 16;
+    s.up_ch = reinterpret_cast<uint4*>(d); d += (size_t)(n_max / 2 + 1) * 2;
+    s.up_self = reinterpret_cast<uint2*>(d); d += (size_t)(n_max / 2 + 1);
     s.uni = d;  // pruning stack [slots][4][BD] + scale counts | power basis of the P(t) builds
     const size_t uni_d = uni_doubles(n_max, slots_max);
     s.stack_sc = reinterpret_cast<int*>(d + (size_t)slots_max * 4 * kCBD);
@@ -525,6 +595,24 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
         k++;
       }
       s_ndown = k;
+      // program of the upward pass (see upward_pass)
+      int q = 0;
+      for (int kk = 0; kk < ni; kk++) {
+        const int x = s.su[kk];
+        if (x < 0) break;
+        uint32_t w4[4];
+        for (int cc = 0; cc < 2; cc++) {
+          const int chd = s.child[2 * x + cc];
+          const uint8_t f = s.flags[chd];
+          const uint32_t kind = (f & PA_F_MISSING) ? 0u : ((f & PA_F_TIP) ? 1u : 2u);
+          w4[2 * cc] = (uint32_t)chd | (kind << 16);
+          w4[2 * cc + 1] = kind == 1u ? (uint32_t)s.tiprow[chd] : (uint32_t)s.slot[chd];
+        }
+        s.up_ch[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        s.up_self[q] = make_uint2((uint32_t)x | ((uint32_t)s.slot[x] << 16), (uint32_t)s.intidx[x]);
+        q++;
+      }
+      s_nup = q;
     }
     // log P(constraints): the 6-state pass of initMCMC with "- log 2" per message (GBGC/SRC/bpp_c.cpp:232-254)
     for (int t = tid; t < n * 6; t += kCBD) s.emis_t[t] = (s.fix[t / 6] == 1 && (t % 3) == 2) ? -CUDART_INF : 0.0;
@@ -553,6 +641,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
       return lin;
     };
     load_Pm(s.Z, s.B, bufs);
+    s.n_upprog = s_nup;  // written by thread 0 above, several barriers ago
     {
       const double ll0 = upward();
       if (tid == 0) {
@@ -885,7 +974,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
 
 size_t chain_smem_bytes(int n_max, int slots_max, int codes_cap) {
   const size_t uni_d = uni_doubles(n_max, slots_max);
-  size_t b = ((size_t)n_max * 16 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N + (size_t)n_max * 4 + 6 + (n_max + 1) / 2 + (codes_cap + 7) / 8) * 8;
+  size_t b = ((size_t)n_max * 16 + (size_t)(n_max / 2 + 1) * 3 + uni_d + 34 + (size_t)n_max * 18 + 96 + SC_N + (size_t)n_max * 4 + 6 + (n_max + 1) / 2 + (codes_cap + 7) / 8) * 8;
   b += ((size_t)n_max * 13 + 4) * 2 + (size_t)n_max * 8;  // thirteen int16 arrays (two with 2 spare entries), eight byte arrays
   return (b + 63) & ~size_t(63);
 }
