@@ -171,6 +171,11 @@ int Engine::gt_replay(const pa_gt_states* gs, double* loglik_out, double* prior_
       return PA_ERR_ARG;
     }
     const int32_t* gc = gs->gchild + (size_t)st * N * 2;
+    for (int k = 0; k < 2 * N; k++)
+      if (gc[k] < -1 || gc[k] >= N) {
+        set_error("pa_engine_gt_replay: gene-tree child out of range");
+        return PA_ERR_ARG;
+      }
     const double* gh = gs->gheights + (size_t)st * N;
     const uint8_t* mis = gs->gmissing + (size_t)st * N;
     const int8_t* Z = gs->Z + (size_t)st * N;

@@ -59,6 +59,27 @@ def test_coalescent_draws_differ_from_the_species_topology():
     assert differ >= 4
 
 
+def test_gt_replay_has_no_cpu_fallback_and_checks_its_arguments(native_lib):
+    """Front-end-only engine (device = -1): the entry point refuses to compute (PA_ERR_CUDA, "no CPU fallback"); null arrays are PA_ERR_ARG."""
+    import ctypes as C
+
+    import phyloacc_b200 as pab
+
+    hdr, els = _golden()
+    case = Case("gt12")
+    eng = pab.Engine.from_config(case.cfg, device=-1)
+    st = dict(els[0]["states"][0], elem=0)
+    with pytest.raises(pab.PhyloAccError) as ei:
+        eng.gt_replay([st], hdr["heights"], hdr["thetas"])
+    assert "no CPU fallback" in str(ei.value)
+    gs = pab.PaGtStates()
+    gs.n_states, gs.N = 1, hdr["N"]
+    out = (C.c_double * 1)()
+    assert pab.load_library().pa_engine_gt_replay(eng._h, C.byref(gs), out, None, None) == -1  # PA_ERR_ARG: null arrays
+    eng.close()
+    case.close()
+
+
 @pytest.mark.gpu
 def test_cuda_gt_replay_matches_reference(native_lib):
     import phyloacc_b200 as pab
