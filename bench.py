@@ -379,7 +379,7 @@ def main_gbgc(args, wl, rank, local_rank, world):
                              "peak_theoretical": 148 * 64 * 2 * sm_clock / 1e12, "algorithmic_fma_per_step": fma, "kernel": "gbgc_chain_kernel",
                              "phase_kcycles_per_chain_iteration": {n: round(c / its / 1e3, 1) for n, c in zip(names, out["phase_cycles"])}},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(batch.X.nbytes), "d2h_bytes_per_step": int(out["d2h_bytes"]), "steps": args.steps},
-                "gpu_launches": args.steps, "clocks": _clock_summary(clocks),
+                "gpu_launches": args.steps * int(out["kernel_launches"]), "clocks": _clock_summary(clocks),
                 "work": {k: int(out[k]) for k in ("node_pattern_updates", "branch_pattern_updates", "pt_builds", "chain_iterations")},
                 "accelerated_calls_rank0": int(np.sum((lr[:, 1] - lr[:, 0] > 5) & (lr[:, 1] - lr[:, 2] > 5) & (out["filtered"] == 0)))}
         if not args.no_cpu_baseline:

@@ -265,6 +265,7 @@ typedef struct pa_gbgc_results {
   uint64_t d2h_bytes;                              /* bytes copied device -> host by this call */
   uint64_t phase_cycles[12]; /* SM cycles per kernel phase, thread 0 of every CTA summed (setup, monitor, downward pass, emissions, messages,
                                 P(t) builds, proposal emissions, proposal messages, (Z, B) draws, upward pass, ELBO + MH, commit) */
+  uint64_t kernel_launches;  /* launches of the chain kernel: the chains go through the device in waves */
 } pa_gbgc_results;
 /* targets: node ids of TARGETSPECIES (the only tips free to accelerate under M1).  model_mask: bit m set = run model m. */
 int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,

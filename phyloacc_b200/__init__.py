@@ -97,7 +97,7 @@ class PaGbgcResults(C.Structure):
                 ("med", _f64p), ("post_b", _f64p), ("post_z", _f64p), ("max_z", _i8p), ("max_b", _i8p), ("accept", _i32p),
                 ("trace", _f64p), ("trace_z", _i8p), ("trace_b", _i8p), ("kernel_ms", C.c_double),
                 ("node_pattern_updates", C.c_uint64), ("chain_iterations", C.c_uint64), ("pt_builds", C.c_uint64),
-                ("branch_pattern_updates", C.c_uint64), ("d2h_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 12)]
+                ("branch_pattern_updates", C.c_uint64), ("d2h_bytes", C.c_uint64), ("phase_cycles", C.c_uint64 * 12), ("kernel_launches", C.c_uint64)]
 
 
 class PaCounters(C.Structure):
@@ -524,7 +524,7 @@ class Engine:
                                             model_mask, C.byref(r)))
         out.update(kernel_ms=float(r.kernel_ms), node_pattern_updates=int(r.node_pattern_updates), chain_iterations=int(r.chain_iterations), pt_builds=int(r.pt_builds),
                    branch_pattern_updates=int(r.branch_pattern_updates), d2h_bytes=int(r.d2h_bytes),
-                   phase_cycles=[int(x) for x in r.phase_cycles])
+                   phase_cycles=[int(x) for x in r.phase_cycles], kernel_launches=int(r.kernel_launches))
         return out
 
     def trace(self, i: int, model: int):

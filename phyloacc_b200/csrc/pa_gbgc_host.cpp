@@ -365,6 +365,7 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
   if (e_first) cudaEventDestroy(e_first);
   release_all();
   if (rc != PA_OK) return rc;
+  out->kernel_launches = (uint64_t)(nc > 0 ? W : 0);
   out->node_pattern_updates = ctr[0];
   out->chain_iterations = ctr[2];
   out->pt_builds = ctr[1];
