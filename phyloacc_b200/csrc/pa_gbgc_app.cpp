@@ -135,7 +135,7 @@ int run_gbgc_from_config(const char* cfg_path) {
     return 1;
   }
   if (cfg.P.sample_hyper) {
-    std::cerr << "(Error. SAMPLE_HYPER 1 is not supported by the GPU build of PhyloAcc-ST-GBGC: the variant's hyper-parameter sweep is outside its scope)"
+    std::cerr << "(Error. SAMPLE_HYPER 1 is not supported by the GPU build of PhyloAcc-ST-GBGC: the variant's sweep (bpp.cpp:324-383) takes logs of the negative selection coefficients and is NaN in the reference itself)"
               << std::endl;
     return 1;
   }
