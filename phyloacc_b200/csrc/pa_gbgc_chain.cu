@@ -1,6 +1,6 @@
 // pa_gbgc_chain.cu -- the PhyloAcc-ST-GBGC chain on the device: BPP_C::Gibbs of src/PhyloAcc-ST-GBGC/SRC/bpp_c.cpp:259-345.
 //
-// One CTA (128 threads) per (element, model) chain, persistent grid pulling chains from an atomic queue.  Unlike PhyloAcc-ST the GC-biased
+// One CTA (160 threads) per (element, model) chain, persistent grid pulling chains from an atomic queue.  Unlike PhyloAcc-ST the GC-biased
 // sampler draws no substitution histories: an iteration works on the EXPECTED (child base, parent base) pairs of every branch
 //   1. MonitorChain                                                                      bpp_c.cpp:598-652
 //   2. expected pairs at the current state (downward pass over compressed site patterns)  Update_Tg(g,.,.,true)   :530-583
@@ -31,9 +31,12 @@ namespace pa {
 namespace {
 
 #ifndef PA_GBGC_BD
-#define PA_GBGC_BD 128
+#define PA_GBGC_BD 160
 #endif
-constexpr int kCBD = PA_GBGC_BD;  // threads per CTA (a multiple of 32, at least 96); A/B knob together with PA_GBGC_CTAS (CTAs per SM)
+// threads per CTA (a multiple of 32, at least 96); A/B knob together with PA_GBGC_CTAS (CTAs per SM).  160 x 3 at 128 registers: elements of
+// up to 160 site patterns (most 200-bp elements) take one pattern tile per pass; measured 128 x 3: 422.6 k, 160 x 3: 432.3 k, 192 x 3 and
+// 256 x 2 (before the last instruction cuts): +1 % / -3 % against 128 x 3
+constexpr int kCBD = PA_GBGC_BD;
 constexpr int kNW = kCBD / 32;
 // phase clock (thread 0): adds the cycles since the previous mark to phase k
 #define PH(k) do { if (tid == 0) { const long long t__ = clock64(); s_ph[k] += t__ - s_t0; s_t0 = t__; } } while (0)

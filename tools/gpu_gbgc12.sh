@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out/gbgc12
+for lib in libphyloacc_b200.so libpa_g160.so; do
+echo "== $lib" | tee -a gpurun_out/gbgc12/smoke.txt
+PA_LIB=$PWD/phyloacc_b200/$lib timeout 600 python tools/gbgc_smoke.py 1184 50 150 2>&1 | grep "chains\|cycles\|rror" | tee -a gpurun_out/gbgc12/smoke.txt
+done
