@@ -282,8 +282,10 @@ static int run_from_config(const char* cfg_path) {
   if (n_dev > 1) std::cout << "# element shards = " << n_dev << " (one engine and host thread per shard)." << std::endl;
   if (!for_each_device([&](int d) {
         PA_NVTX_RANGE("load shard");
+        StageTimer stt;
         int r = make_engine(in, devices[d], threads_per_dev, &engines[d]);
         if (r != PA_OK) return r;
+        stt.mark(("shard " + std::to_string(d) + ": engine + CUDA context").c_str());
         const int lo = shard_lo[d], cnt = shard_lo[d + 1] - lo;
         std::vector<int64_t> st(cnt);
         std::vector<int32_t> ln(cnt), gid(cnt);
@@ -292,7 +294,9 @@ static int run_from_config(const char* cfg_path) {
           ln[k] = in.elem_len[ids[lo + k]];
           gid[k] = ids[lo + k];
         }
-        return engines[d]->eng.load_alignment(in.X.data(), in.G, cnt, st.data(), ln.data(), gid.data());
+        r = engines[d]->eng.load_alignment(in.X.data(), in.G, cnt, st.data(), ln.data(), gid.data());
+        stt.mark(("shard " + std::to_string(d) + ": integer front-end + upload").c_str());
+        return r;
       })) {
     destroy_all();
     return 1;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# eight GPUs: the drop-in binary on 8192 cfg2 elements (one shard per GPU) with the stage times
+# several GPUs: the drop-in binary on 8192 cfg2 elements (one shard per GPU) with the stage times
 mkdir -p gpurun_out/r2q
 nvidia-smi -L | wc -l
 python - <<'PY'
@@ -21,6 +21,6 @@ for rep in range(2):
     res.append(dt)
     print("run", rep, "rc", r.returncode, "wall %.1f s" % dt, [l for l in r.stdout.split("\n") if "shards" in l])
     print("\n".join(l for l in r.stderr.split("\n") if "timing" in l and "collect" not in l))
-open("gpurun_out/r2q/product_8gpu.txt", "w").write(f"PhyloAcc-ST-b200 on 8192 cfg2 elements, 1500 iterations x 3 models, 8 GPUs (one shard each), NUM_THREAD 32: {res[0]:.1f} s and {res[1]:.1f} s wall (one GPU: 10.3 s, two: 8.2 s)\n")
+open("gpurun_out/r2q/product_8gpu.txt", "w").write(f"PhyloAcc-ST-b200 on 8192 cfg2 elements, 1500 iterations x 3 models, N GPUs (one shard each), NUM_THREAD 32: {res[0]:.1f} s and {res[1]:.1f} s wall (one GPU: 10.3 s, two: 8.2 s)\n")
 PY
 cat gpurun_out/r2q/product_8gpu.txt
