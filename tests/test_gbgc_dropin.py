@@ -186,3 +186,41 @@ def test_sharded_run_writes_byte_identical_files(native_lib):
             with open(os.path.join(outs["one"], fn), "rb") as fa, open(os.path.join(out, fn), "rb") as fb:
                 assert fa.read() == fb.read(), (tag, fn)
     case.close()
+
+
+@pytest.mark.gpu
+def test_batch_selection_and_outer_chain_iterations_follow_the_reference(native_lib):
+    """No ID_FILE: BATCH k takes the k-th third of the BED file (main.cpp:331-347).  CHAIN 2: two outer iterations -- the _rate_postZ files
+    get the rows of both, the VERBOSE traces are appended to, _hyper.txt gets one line per iteration, _elem_lik.txt is rewritten."""
+    import phyloacc_b200 as pab
+
+    if not os.path.exists(REF):
+        pytest.skip("reference GBGC binary not built (make -C oracle ref-gbgc)")
+    case = Case("gbgc_chain43")
+    outs = {}
+    for tag, exe in (("ref", REF), ("ours", pab.BIN_GBGC_PATH)):
+        out = os.path.join(case.dir, "b_" + tag)
+        cfg = _gbgc_cfg(case, out, [0])
+        with open(cfg) as f:
+            lines = [l for l in f.read().split("\n") if l and l.split()[0] not in ("ID_FILE", "CHAIN")]
+        with open(cfg, "w") as f:
+            f.write("\n".join(lines) + "\nBATCH 1\nCHAIN 2\n")
+        r = subprocess.run([exe, cfg], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (tag, r.stdout[-1500:], r.stderr[-1500:])
+        assert "Running MCMC chain 2 ..." in r.stdout
+        outs[tag] = out
+    skip = {"ids.txt", "gbgc.cfg"}
+    files = {t: sorted(f for f in os.listdir(o) if f not in skip) for t, o in outs.items()}
+    assert files["ours"] == files["ref"]
+    third = case.C // 3
+    want_ids = [str(c) for c in range(third, 2 * third)]
+    for fn in files["ref"]:
+        a, b = _table(os.path.join(outs["ref"], fn)), _table(os.path.join(outs["ours"], fn))
+        assert a[0] == b[0] and [len(r) for r in a] == [len(r) for r in b], fn
+        if "_rate_postZ_" in fn:
+            assert [r[0] for r in a[1:]] == [r[0] for r in b[1:]] == want_ids + want_ids
+        elif "_mcmc_trace_" in fn:
+            assert len(b) == 1 + 2 * 80
+        elif fn.endswith("_hyper.txt"):
+            assert [r[0] for r in b[1:]] == ["0", "1"]
+    case.close()
