@@ -190,3 +190,33 @@ def test_cuda_chain_matches_the_reference_across_seeds(native_lib):
     assert abs(lz.mean()) < 1.0 and np.abs(lz).max() < 6, (lz.mean(), np.abs(lz).max())
     eng.close()
     case.close()
+
+
+@pytest.mark.gpu
+def test_cuda_chain_on_a_240_taxon_tree_replays_to_its_recorded_likelihoods(native_lib, tmp_path):
+    """Zoonomia-scale tree (479 nodes: one CTA per SM, 212 KB of shared memory): the chain runs and every sampled state, replayed from
+    scratch by pa_engine_gbgc_replay (an independent kernel), gives the recorded log P(X | Z, B, r) to 1e-10."""
+    import phyloacc_b200 as pab
+    from phyloacc_b200 import synth
+
+    S = 240
+    stree = synth.make_tree(S=S, seed=9, n_out=S // 6, n_target=S // 5)
+    batch = synth.simulate(stree, C=4, length=200, seed=5, gap_frac=0.01, missing_frac=0.03, ambig_frac=0.002)
+    cfg = synth.write_files(batch, str(tmp_path), prefix="sim", params=dict(BURNIN=5, MCMC=10, CHAIN=1, GAPCHAR="-"))
+    eng = pab.Engine.from_config(cfg, device=0)
+    out = eng.gbgc_run(list(range(4)), stree.targets, traces=True, num_burn=10, num_mcmc=20, seed=3)
+    assert np.isfinite(out["loglik_max"][out["filtered"] == 0]).all()
+    el, Z, B, sn, sc, gb, want = [], [], [], [], [], [], []
+    for i in range(4):
+        if out["filtered"][i]:
+            continue
+        for mdl in range(3):
+            assert out["accept"][i, mdl, 1] > 0  # some (Z, B) updates were accepted
+            for m in (0, 7, 19, 29):
+                el.append(i); Z.append(np.maximum(out["trace_z"][i, mdl, m], 0)); B.append(out["trace_b"][i, mdl, m])
+                sc.append(out["trace"][i, mdl, 2, m]); sn.append(out["trace"][i, mdl, 3, m]); gb.append(out["trace"][i, mdl, 4, m])
+                want.append(out["trace"][i, mdl, 0, m])
+    got = eng.gbgc_replay(el, np.asarray(Z), np.asarray(B), sn, sc, gb)
+    want = np.asarray(want)
+    assert len(want) >= 24 and np.all(np.abs(got - want) <= 1e-10 * np.abs(want)), np.abs(got / want - 1).max()
+    eng.close()
