@@ -88,7 +88,7 @@ struct Sh {  // shared-memory views of one chain
 };
 
 enum { SC_LG0 = 0, SC_LG1, SC_LL0, SC_LL1, SC_SELC, SC_SELN, SC_GBC, SC_PSELC, SC_PSELN, SC_PGBC, SC_LOGLIK, SC_LOGLIK_OLD, SC_ELBO_OLD, SC_LOGPZ,
-       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_G, SC_L, SC_KC, SC_KN, SC_KG, SC_N };
+       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_G, SC_L, SC_KC, SC_KN, SC_KG, SC_LB0, SC_LB1, SC_LC, SC_LN, SC_N };
 
 // log TM_Int (child class a, parent class j) of a branch (GBGC/SRC/bpp.hpp:284-316): (0,0) = 1-g, (1,0) = g, (1,1) = 1-l, (2,1) = l, (2,2) = 1;
 // on the outgroup lineage (1,1) = 1 and (2,1) = 0
@@ -316,7 +316,7 @@ __device__ __forceinline__ double pair_dot(const double* __restrict__ lp, const 
 // emissions of classes k_lo..5 of every branch into dst; class 0 (and missing branches) are copied from `base` when k_lo == 1
 __device__ void emissions(const Sh& s, const GbgcChainLaunch& L, double* dst, const double* base, const double* P0, const double* buf,
                           const double* post, int n, int k_lo, int tid) {
-  const double l_b0 = log(1.0 - L.prm.gbprior_c), l_b1 = log(L.prm.gbprior_c), l_c = log(1.0 - L.prm.cons_to_mis), l_n = log(1.0 - L.prm.ncons_to_mis);
+  const double l_b0 = s.scal[SC_LB0], l_b1 = s.scal[SC_LB1], l_c = s.scal[SC_LC], l_n = s.scal[SC_LN];  // logs of the chain's constants
   for (int t = tid; t < 6 * (n - 1); t += kCBD) {
     const int i = t / 6, k = t - 6 * i;
     const bool fix1 = s.fix[i] == 1;
@@ -340,6 +340,20 @@ __device__ void emissions(const Sh& s, const GbgcChainLaunch& L, double* dst, co
 }
 
 // sum over the non-missing branches of <log P of the branch's class, expected pairs>  (BPP_C::ELBO, GBGC/SRC/bpp_c.cpp:840-878)
+// The same sum taken from emissions already in shared memory: emis[i][k] = <log P_k, pairs> + log prior(B) + log(1 - loss), so the branch's term
+// is the emission of its class minus the two constants -- no second pass over the log tables in global memory.  `emis` must belong to the
+// same rates and the same expected pairs as the tables the term is defined on (s.emis after initial_prob_back / after the rate moves).
+__device__ double elbo_from_emissions(const Sh& s, const GbgcChainLaunch& L, const double* emis, const int8_t* Z, const int8_t* B, int n, int tid) {
+  const double l_b0 = s.scal[SC_LB0], l_b1 = s.scal[SC_LB1], l_c = s.scal[SC_LC], l_n = s.scal[SC_LN];  // logs of the chain's constants
+  double acc = 0.0;
+  for (int i = tid; i < n - 1; i += kCBD)
+    if (!(s.flags[i] & PA_F_MISSING)) {
+      const int k = Z[i] + 3 * B[i];
+      acc += (emis[i * 6 + k] - (k < 3 ? l_b0 : l_b1)) - (k % 3 == 1 ? l_c : l_n);
+    }
+  return block_sum(acc, s.red, tid, kCBD);
+}
+
 __device__ double elbo_term(const Sh& s, const int8_t* Z, const int8_t* B, const double* P0, const double* buf, const double* post, int n, int tid) {
   double acc = 0.0;
   for (int i = tid; i < n - 1; i += kCBD)
@@ -363,7 +377,7 @@ __device__ void build_logs(const Sh& s, const GbgcChainLaunch& L, const ElemView
       if ((s.flags[i] & PA_F_MISSING) || k < k_lo) emis_dst[t] = emis_base[t];
       else if (s.fix[i] == 1 && k % 3 == 2) emis_dst[t] = -CUDART_INF;
     }
-  const double l_b0 = log(1.0 - L.prm.gbprior_c), l_b1 = log(L.prm.gbprior_c), l_c = log(1.0 - L.prm.cons_to_mis), l_n = log(1.0 - L.prm.ncons_to_mis);
+  const double l_b0 = s.scal[SC_LB0], l_b1 = s.scal[SC_LB1], l_c = s.scal[SC_LC], l_n = s.scal[SC_LN];  // logs of the chain's constants
   if (tid >= k_lo && tid < 6) {
     double Q[16];
     gbgc_rate(L.Q0, tid % 3 == 0 ? 0.0 : (tid % 3 == 1 ? sel_c : sel_n), tid >= 3 ? gbc : 0.0, Q);
@@ -564,6 +578,9 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
       // constants of the three log Gamma densities: lgamma(a) + log(b)
       s.scal[SC_KC] = lgamma(pr.cprior_a) + log(pr.cprior_b); s.scal[SC_KN] = lgamma(pr.nprior_a) + log(pr.nprior_b);
       s.scal[SC_KG] = lgamma(pr.gbprior_a) + log(pr.gbprior_b);
+      // log prior of the gBGC indicator (absent / present) and log(1 - loss) of a conserved / non-conserved branch
+      s.scal[SC_LB0] = log(1.0 - pr.gbprior_c); s.scal[SC_LB1] = log(pr.gbprior_c);
+      s.scal[SC_LC] = log(1.0 - pr.cons_to_mis); s.scal[SC_LN] = log(1.0 - pr.ncons_to_mis);
       s_bufA = 0; s_bufW = 0;
     }
     __syncthreads();
@@ -824,7 +841,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
       PH(PH_INIT_EMIS);
       integrate(s.emis);
       PH(PH_INIT_MSG);
-      const double elbo_old = elbo_term(s, s.Z, s.B, P0, bufA, post, n, tid);
+      const double elbo_old = elbo_from_emissions(s, L, s.emis, s.Z, s.B, n, tid);
       if (tid == 0) {
         s.scal[SC_LOGLIK_OLD] = s.scal[SC_LL_PROP];
         s.scal[SC_ELBO_OLD] = elbo_old;
@@ -926,7 +943,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
       load_Pm(s.Zn, s.Bn, bufW);
       const double ll_new = upward();
       PH(PH_UP);
-      const double elbo_new = elbo_term(s, s.Zn, s.Bn, P0, bufW, post, n, tid);
+      const double elbo_new = elbo_from_emissions(s, L, s.emis, s.Zn, s.Bn, n, tid);
       if (tid == 0) {
         const double ratio = ll_new - s.scal[SC_LOGLIK] + s.scal[SC_ELBO_OLD] - elbo_new;
         const bool acc = log(u01(philox4(pr.seed, key, 0u, 2u, (uint32_t)m, PA_ST_GBGC).x)) < ratio;
