@@ -88,7 +88,7 @@ struct Sh {  // shared-memory views of one chain
 };
 
 enum { SC_LG0 = 0, SC_LG1, SC_LL0, SC_LL1, SC_SELC, SC_SELN, SC_GBC, SC_PSELC, SC_PSELN, SC_PGBC, SC_LOGLIK, SC_LOGLIK_OLD, SC_ELBO_OLD, SC_LOGPZ,
-       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_G, SC_L, SC_KC, SC_KN, SC_KG, SC_LB0, SC_LB1, SC_LC, SC_LN, SC_N };
+       SC_LOGPZC, SC_FULL, SC_LL_PROP, SC_G, SC_L, SC_KC, SC_KN, SC_KG, SC_LB0, SC_LB1, SC_LC, SC_LN, SC_LCM, SC_LNM, SC_N };
 
 // log TM_Int (child class a, parent class j) of a branch (GBGC/SRC/bpp.hpp:284-316): (0,0) = 1-g, (1,0) = g, (1,1) = 1-l, (2,1) = l, (2,2) = 1;
 // on the outgroup lineage (1,1) = 1 and (2,1) = 0
@@ -325,7 +325,7 @@ __device__ void emissions(const Sh& s, const GbgcChainLaunch& L, double* dst, co
       if (base) e = base[t];
       else {
         e = 0.0;
-        if (!(s.flags[s.parent[i]] & PA_F_MISSING)) e = (k % 3 == 1) ? log(L.prm.cons_to_mis) : log(L.prm.ncons_to_mis);
+        if (!(s.flags[s.parent[i]] & PA_F_MISSING)) e = (k % 3 == 1) ? s.scal[SC_LCM] : s.scal[SC_LNM];
         if (fix1 && k % 3 == 2) e = -CUDART_INF;
       }
     } else if (fix1 && k % 3 == 2) {
@@ -581,6 +581,7 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
       // log prior of the gBGC indicator (absent / present) and log(1 - loss) of a conserved / non-conserved branch
       s.scal[SC_LB0] = log(1.0 - pr.gbprior_c); s.scal[SC_LB1] = log(pr.gbprior_c);
       s.scal[SC_LC] = log(1.0 - pr.cons_to_mis); s.scal[SC_LN] = log(1.0 - pr.ncons_to_mis);
+      s.scal[SC_LCM] = log(pr.cons_to_mis); s.scal[SC_LNM] = log(pr.ncons_to_mis);
       s_bufA = 0; s_bufW = 0;
     }
     __syncthreads();
@@ -695,8 +696,8 @@ __global__ void __launch_bounds__(kCBD, PA_GBGC_CTAS) gbgc_chain_kernel(GbgcChai
             double v = s.scal[SC_LOGLIK] + s.scal[SC_LOGPZ];
             v += lgp(-s.scal[SC_SELC], pr.cprior_a, pr.cprior_b, s.scal[SC_KC]);
             if (resz != 0) v += lgp(s.scal[SC_SELN] + pr.nprior_c, pr.nprior_a, pr.nprior_b, s.scal[SC_KN]);
-            v += log(1.0 - pr.ncons_to_mis) * c0 + log(1.0 - pr.cons_to_mis) * c1 + log(pr.ncons_to_mis) * c2 + log(pr.cons_to_mis) * c3;
-            v += log(1.0 - pr.gbprior_c) * ungb + lgp(s.scal[SC_GBC], pr.gbprior_a, pr.gbprior_b, s.scal[SC_KG]) + log(pr.gbprior_c) * gb;
+            v += s.scal[SC_LN] * c0 + s.scal[SC_LC] * c1 + s.scal[SC_LNM] * c2 + s.scal[SC_LCM] * c3;
+            v += s.scal[SC_LB0] * ungb + lgp(s.scal[SC_GBC], pr.gbprior_a, pr.gbprior_b, s.scal[SC_KG]) + s.scal[SC_LB1] * gb;
             s.scal[SC_FULL] = v;
           }
         }

@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <string>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
@@ -68,22 +70,28 @@ struct GbgcChainView {
 double gbgc_eval2(const GbgcChainView& v, const int8_t* maxZ, double max_loglik) {
   const int T = v.T, N = v.N, burn = v.burn, mcmc = v.mcmc;
   std::vector<int> uncertain;
-  for (int s = 0; s < N; s++) {
-    int cnt = 0;
-    for (int i = burn; i < T; i++) cnt += v.Z[(size_t)i * N + s] == maxZ[s];
-    if (cnt < mcmc) uncertain.push_back(s);
+  {
+    std::vector<int> same_as_max(N, 0);  // row by row: the trace is [T][N]
+    for (int i = burn; i < T; i++) {
+      const int8_t* zi = v.Z + (size_t)i * N;
+      for (int s = 0; s < N; s++) same_as_max[s] += zi[s] == maxZ[s];
+    }
+    for (int s = 0; s < N; s++)
+      if (same_as_max[s] < mcmc) uncertain.push_back(s);
   }
   const int d = 2 + (v.resz != 0 ? 1 : 0);
   struct Conf {
     const int8_t* z;
     int cnt = 0;
     double mean[3] = {0, 0, 0}, var[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, sum_full = 0;
-    std::vector<std::vector<int>> bsets;
+    // the distinct sets of gBGC branches seen with this configuration (getShifts, bpp_c2.cpp:14-27), as bit masks over the nodes, and how
+    // often each was seen, in order of first appearance (a linear search over vectors of node ids made a chain's Eval2 quadratic in MCMC)
+    std::unordered_map<std::string, int> bindex;
     std::vector<int> bcnt;
   };
   std::vector<Conf> conf(1);
   conf[0].z = maxZ;
-  std::vector<int> shifts;
+  std::string shifts((size_t)(N + 7) / 8, '\0');
   for (int i = T - 1; i >= burn; i--) {
     const int8_t* zi = v.Z + (size_t)i * N;
     size_t j = 0;
@@ -99,18 +107,12 @@ double gbgc_eval2(const GbgcChainView& v, const int8_t* maxZ, double max_loglik)
     }
     Conf& c = conf[j];
     c.cnt++;
-    shifts.clear();  // getShifts (bpp_c2.cpp:14-27): the non-missing nodes of the pruned tree with B = 1, as an ordered set
+    std::fill(shifts.begin(), shifts.end(), '\0');  // the non-missing nodes of the pruned tree with B = 1, as a set
     for (int s : v.plan->nodes)
-      if (!v.plan->missing[s] && v.B[(size_t)i * N + s]) shifts.push_back(s);
-    std::sort(shifts.begin(), shifts.end());
-    size_t k = 0;
-    for (; k < c.bsets.size(); k++)
-      if (c.bsets[k] == shifts) break;
-    if (k == c.bsets.size()) {
-      c.bsets.push_back(shifts);
-      c.bcnt.push_back(0);
-    }
-    c.bcnt[k]++;
+      if (!v.plan->missing[s] && v.B[(size_t)i * N + s]) shifts[s >> 3] |= (char)(1 << (s & 7));
+    auto ins = c.bindex.emplace(shifts, (int)c.bcnt.size());
+    if (ins.second) c.bcnt.push_back(0);
+    c.bcnt[ins.first->second]++;
     const double cr = v.c[i], gb = v.gb[i], nr = v.n[i];
     c.var[1 * 3 + 1] += cr * cr; c.mean[1] += cr;
     c.var[0] += gb * gb; c.mean[0] += gb;
@@ -308,15 +310,21 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
     out->med[im * 3 + 0] = med(d + 3 * (size_t)T);
     out->med[im * 3 + 1] = med(d + 2 * (size_t)T);
     out->med[im * 3 + 2] = med(d + 4 * (size_t)T);
-    for (int s = 0; s < N; s++) {
-      int cz[4] = {0, 0, 0, 0}, cb = 0;
+    {
+      std::vector<int> cz((size_t)N * 4, 0), cb(N, 0);  // row by row: the traces are [T][N]
       for (int m = burn; m < T; m++) {
-        cz[Z[(size_t)m * N + s] + 1]++;
-        cb += B[(size_t)m * N + s];
+        const int8_t* zr = Z.data() + (size_t)m * N;
+        const int8_t* br = B.data() + (size_t)m * N;
+        for (int s = 0; s < N; s++) {
+          cz[(size_t)s * 4 + zr[s] + 1]++;
+          cb[s] += br[s];
+        }
       }
-      if (pl.missing[s]) cz[0] = mcmc;
-      for (int q = 0; q < 4; q++) out->post_z[(im * N + s) * 4 + q] = (double)cz[q] / mcmc;
-      out->post_b[im * N + s] = (double)cb / mcmc;
+      for (int s = 0; s < N; s++) {
+        if (pl.missing[s]) cz[(size_t)s * 4] = mcmc;
+        for (int q = 0; q < 4; q++) out->post_z[(im * N + s) * 4 + q] = (double)cz[(size_t)s * 4 + q] / mcmc;
+        out->post_b[im * N + s] = (double)cb[s] / mcmc;
+      }
     }
     GbgcChainView v{T, N, burn, mcmc, chain_resz[c], d, d + T, d + 2 * (size_t)T, d + 3 * (size_t)T, d + 4 * (size_t)T, Z.data(), B.data(), &pl};
     out->loglik[im] = gbgc_eval2(v, mz, best);
