@@ -271,6 +271,16 @@ typedef struct pa_gbgc_results {
 int pa_engine_gbgc_run(pa_engine* e, const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm,
                        int model_mask, pa_gbgc_results* out);
 
+/* BPP_C::Eval2 of the GBGC variant (src/PhyloAcc-ST-GBGC/SRC/bpp_c2.cpp:29-285) on a GIVEN chain: the variational estimate of log P(X | model)
+ * from the post-burn-in samples -- configurations of Z over the uncertain nodes, within each the sets of gBGC branches, a Gaussian over
+ * (gBC, c_rate[, n_rate]).  Host-only (no device needed): it is what pa_engine_gbgc_run applies to every finished chain, exposed so that it
+ * can be pinned against the reference's own Eval2 on the same trace.  full / c_rate / n_rate / gbc: [burn + mcmc]; Z, B: [burn + mcmc][N];
+ * nodes: the element's pruned tree (post-order, original ids), missing: [N]; resz: the reference's resZ (0 null, 2 restricted, 1 full).
+ * max_loglik_out (may be NULL): MonitorChain's MaxLoglik. */
+int pa_gbgc_eval2(int32_t N, int32_t burn, int32_t mcmc, int32_t resz, const double* full, const double* c_rate, const double* n_rate,
+                  const double* gbc, const int8_t* Z, const int8_t* B, const int32_t* nodes, int32_t n_nodes, const uint8_t* missing,
+                  double* loglik_out, double* max_loglik_out);
+
 /* PhyloAcc-GT groundwork (no GT sampler yet): what the gene-tree variant evaluates for an element at a given GENE tree
  * embedded in the species tree, for n_states states at once --
  *   loglik_out: log P(X | gene tree, Z, rates), the upward half of GTree::Update_Tg (src/PhyloAcc-GT/genetree.cpp:1330-1418) summed over the

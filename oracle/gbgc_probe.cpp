@@ -118,6 +118,33 @@ int main(int argc, char** argv) {
         ll += BPP::log_exp_sum(el.lambda[g][el.root]);
       }
       printf("loglik %a\n", ll);
+    } else if (cmd == "eval2") {
+      // eval2 <resZ> <burn> <mcmc> <trace file>: BPP_C::Eval2 (GBGC/SRC/bpp_c2.cpp:29-285) on a GIVEN chain.  The file holds one row per
+      // iteration: log P(X, Z, B, r), c_rate, n_rate, gBC, Z[N], B[N].  MaxLoglik / Max_Z are taken as MonitorChain takes them
+      // (bpp_c.cpp:655-664: first maximum of the post-burn-in log P(X, Z, B, r)).
+      if (filter) { printf("eval2 skipped\n"); continue; }
+      int resZ, burn, mcmc; string path;
+      ss >> resZ >> burn >> mcmc >> path;
+      const int N = bpp.N, T = burn + mcmc;
+      el.num_burn = burn; el.num_mcmc = mcmc;
+      el.trace_full_loglik.assign(T, 0.0); el.trace_loglik.assign(T, 0.0);
+      el.trace_c_rate.assign(T, 0.0); el.trace_n_rate.assign(T, 0.0); el.trace_n_GB.assign(T, 0.0);
+      el.trace_Z.assign(T, vector<int>(N, 1));
+      el.trace_GB.assign(T, vector<bool>(N, false));
+      ifstream tf(path.c_str());
+      for (int m = 0; m < T; m++) {
+        tf >> el.trace_full_loglik[m] >> el.trace_c_rate[m] >> el.trace_n_rate[m] >> el.trace_n_GB[m];
+        for (int s2 = 0; s2 < N; s2++) { int z; tf >> z; el.trace_Z[m][s2] = z; }
+        for (int s2 = 0; s2 < N; s2++) { int b; tf >> b; el.trace_GB[m][s2] = (b != 0); }
+      }
+      el.MaxLoglik = -INFINITY;
+      for (int m = burn; m < T; m++)
+        if (el.MaxLoglik < el.trace_full_loglik[m]) { el.MaxLoglik = el.trace_full_loglik[m]; el.Max_Z = el.trace_Z[m]; }
+      el.verbose = false;
+      bpp.log_liks_null[el.CC] = bpp.log_liks_resZ[el.CC] = bpp.log_liks_sgl[el.CC] = 0;
+      el.Eval2(bpp, resZ);
+      const double v = resZ == 0 ? bpp.log_liks_null[el.CC] : (resZ == 2 ? bpp.log_liks_resZ[el.CC] : bpp.log_liks_sgl[el.CC]);
+      printf("eval2 %d %a\n", resZ, v);
     } else if (cmd == "integ") {
       // integ <resZ> <sel_c> <sel_n> <gbc> Z[N] B[N]: the evaluations of one Gibbs iteration that do not involve random numbers, at a given
       // state -- expected parent / child base pairs per branch (Update_Tg(g, ., ., true), GBGC/SRC/bpp_c.cpp:530-583), the six

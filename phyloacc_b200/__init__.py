@@ -123,7 +123,7 @@ EXPORTS = [
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_gbgc_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
     "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
-    "pa_gbgc_params_default", "pa_engine_gbgc_run", "pa_engine_gt_replay",
+    "pa_gbgc_params_default", "pa_engine_gbgc_run", "pa_engine_gt_replay", "pa_gbgc_eval2",
 ]
 
 _lib = None
@@ -194,6 +194,23 @@ def load_library(build_if_missing: bool = True):
 def _check(rc: int):
     if rc != PA_OK:
         raise PhyloAccError(rc, load_library().pa_last_error().decode(errors="replace"))
+
+
+def gbgc_eval2(full, c_rate, n_rate, gbc, Z, B, nodes, missing, burn: int, resz: int):
+    """The GBGC variant's Eval2 on a given chain (pa_gbgc_eval2, host-only): returns (estimate of log P(X | model), MaxLoglik)."""
+    lib = load_library()
+    full, c_rate, n_rate, gbc = (np.ascontiguousarray(x, dtype=np.float64) for x in (full, c_rate, n_rate, gbc))
+    T = len(full)
+    Z = np.ascontiguousarray(Z, dtype=np.int8).reshape(T, -1)
+    N = Z.shape[1]
+    B = np.ascontiguousarray(B, dtype=np.int8).reshape(T, N)
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+    missing = np.ascontiguousarray(missing, dtype=np.uint8)
+    out, mx = C.c_double(), C.c_double()
+    _check(lib.pa_gbgc_eval2(N, burn, T - burn, resz, full.ctypes.data_as(_f64p), c_rate.ctypes.data_as(_f64p), n_rate.ctypes.data_as(_f64p),
+                             gbc.ctypes.data_as(_f64p), Z.ctypes.data_as(_i8p), B.ctypes.data_as(_i8p), nodes.ctypes.data_as(_i32p), len(nodes),
+                             missing.ctypes.data_as(_u8p), C.byref(out), C.byref(mx)))
+    return out.value, mx.value
 
 
 def gbgc_transition(Q, sel, bias, t, device: int = 0):

@@ -178,6 +178,32 @@ double gbgc_eval2(const GbgcChainView& v, const int8_t* maxZ, double max_loglik)
 
 }  // namespace
 
+}  // namespace pa
+
+// The variant's Eval2 on a given chain (host-only; what pa_engine_gbgc_run applies to every finished chain): exposed for parity tests against
+// the reference's own Eval2 (tests/test_gbgc_eval2.py)
+extern "C" int pa_gbgc_eval2(int32_t N, int32_t burn, int32_t mcmc, int32_t resz, const double* full, const double* c_rate, const double* n_rate,
+                             const double* gbc, const int8_t* Z, const int8_t* B, const int32_t* nodes, int32_t n_nodes, const uint8_t* missing,
+                             double* loglik_out, double* max_loglik_out) {
+  if (N <= 0 || burn < 0 || mcmc < 2 || !full || !c_rate || !n_rate || !gbc || !Z || !B || !nodes || !missing || !loglik_out) return PA_ERR_ARG;
+  const int T = burn + mcmc;
+  pa::ElemPlan pl;
+  pl.nodes.assign(nodes, nodes + n_nodes);
+  pl.missing.assign(missing, missing + N);
+  double best = -INFINITY;
+  int best_m = -1;
+  for (int m = burn; m < T; m++)
+    if (full[m] > best) { best = full[m]; best_m = m; }
+  std::vector<int8_t> mz(N, -1);
+  if (best_m >= 0) mz.assign(Z + (size_t)best_m * N, Z + (size_t)(best_m + 1) * N);
+  pa::GbgcChainView v{T, N, burn, mcmc, resz, nullptr, full, c_rate, n_rate, gbc, Z, B, &pl};
+  *loglik_out = pa::gbgc_eval2(v, mz.data(), best);
+  if (max_loglik_out) *max_loglik_out = best;
+  return PA_OK;
+}
+
+namespace pa {
+
 int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm, int model_mask,
                      pa_gbgc_results* out) {
   if (!loaded) {
