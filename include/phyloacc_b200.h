@@ -281,6 +281,13 @@ int pa_gbgc_eval2(int32_t N, int32_t burn, int32_t mcmc, int32_t resz, const dou
                   const double* gbc, const int8_t* Z, const int8_t* B, const int32_t* nodes, int32_t n_nodes, const uint8_t* missing,
                   double* loglik_out, double* max_loglik_out);
 
+/* BPP_C::Output_init of the GBGC variant (bpp_c2.cpp:603-650) on a GIVEN chain, host-only: med3_out = {n_rate, c_rate, gBC} as the reference takes
+ * them (element T/2 of the trace whose post-burn-in tail is sorted), post_b_out [N] = P(B = 1), post_z_out [N][4] = P(Z = -1, 0, 1, 2) with the
+ * reference's rule for missing nodes.  What pa_engine_gbgc_run applies to every finished chain; exposed for parity tests against the reference's
+ * own writer. */
+int pa_gbgc_output_init(int32_t N, int32_t burn, int32_t mcmc, const double* n_rate, const double* c_rate, const double* gbc, const int8_t* Z,
+                        const int8_t* B, const uint8_t* missing, double* med3_out, double* post_b_out, double* post_z_out);
+
 /* PhyloAcc-GT groundwork (no GT sampler yet): what the gene-tree variant evaluates for an element at a given GENE tree
  * embedded in the species tree, for n_states states at once --
  *   loglik_out: log P(X | gene tree, Z, rates), the upward half of GTree::Update_Tg (src/PhyloAcc-GT/genetree.cpp:1330-1418) summed over the

@@ -145,6 +145,33 @@ int main(int argc, char** argv) {
       el.Eval2(bpp, resZ);
       const double v = resZ == 0 ? bpp.log_liks_null[el.CC] : (resZ == 2 ? bpp.log_liks_resZ[el.CC] : bpp.log_liks_sgl[el.CC]);
       printf("eval2 %d %a\n", resZ, v);
+    } else if (cmd == "output_init") {
+      // output_init <resZ> <burn> <mcmc> <trace file>: the reference's own row of _rate_postZ_<resZ>.txt (BPP_C::Output_init,
+      // GBGC/SRC/bpp_c2.cpp:603-650) for a GIVEN chain (file format as for eval2), echoed as it was written
+      if (filter) { printf("output_init skipped\n"); continue; }
+      int resZ, burn, mcmc; string path;
+      ss >> resZ >> burn >> mcmc >> path;
+      const int N = bpp.N, T = burn + mcmc;
+      el.num_burn = burn; el.num_mcmc = mcmc;
+      el.trace_full_loglik.assign(T, 0.0); el.trace_loglik.assign(T, 0.0);
+      el.trace_c_rate.assign(T, 0.0); el.trace_n_rate.assign(T, 0.0); el.trace_n_GB.assign(T, 0.0);
+      el.trace_Z.assign(T, vector<int>(N, 1));
+      el.trace_GB.assign(T, vector<bool>(N, false));
+      ifstream tf(path.c_str());
+      for (int m = 0; m < T; m++) {
+        tf >> el.trace_full_loglik[m] >> el.trace_c_rate[m] >> el.trace_n_rate[m] >> el.trace_n_GB[m];
+        for (int s2 = 0; s2 < N; s2++) { int z; tf >> z; el.trace_Z[m][s2] = z; }
+        for (int s2 = 0; s2 < N; s2++) { int b; tf >> b; el.trace_GB[m][s2] = (b != 0); }
+      }
+      const string rowfile = path + ".row";
+      {
+        ofstream oz(rowfile.c_str());
+        el.Output_init(string("."), string("."), bpp, oz, resZ);
+      }
+      ifstream rf(rowfile.c_str());
+      string row;
+      getline(rf, row);
+      printf("output_init %d\t%s\n", resZ, row.c_str());
     } else if (cmd == "integ") {
       // integ <resZ> <sel_c> <sel_n> <gbc> Z[N] B[N]: the evaluations of one Gibbs iteration that do not involve random numbers, at a given
       // state -- expected parent / child base pairs per branch (Update_Tg(g, ., ., true), GBGC/SRC/bpp_c.cpp:530-583), the six

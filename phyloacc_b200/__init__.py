@@ -123,7 +123,7 @@ EXPORTS = [
     "pa_engine_get_ids", "pa_engine_get_params", "pa_run_from_config", "pa_gbgc_run_from_config", "pa_device_fp64_peak",
     "pa_engine_sample_ex", "pa_engine_get_hyper", "pa_engine_set_hyper", "pa_engine_sample_hyper", "pa_engine_hyper_sums",
     "pa_engine_sample_hyper_sums", "pa_engine_element_blob", "pa_gbgc_transition", "pa_engine_gbgc_replay", "pa_engine_gbgc_integrate",
-    "pa_gbgc_params_default", "pa_engine_gbgc_run", "pa_engine_gt_replay", "pa_gbgc_eval2",
+    "pa_gbgc_params_default", "pa_engine_gbgc_run", "pa_engine_gt_replay", "pa_gbgc_eval2", "pa_gbgc_output_init",
 ]
 
 _lib = None
@@ -211,6 +211,22 @@ def gbgc_eval2(full, c_rate, n_rate, gbc, Z, B, nodes, missing, burn: int, resz:
                              gbc.ctypes.data_as(_f64p), Z.ctypes.data_as(_i8p), B.ctypes.data_as(_i8p), nodes.ctypes.data_as(_i32p), len(nodes),
                              missing.ctypes.data_as(_u8p), C.byref(out), C.byref(mx)))
     return out.value, mx.value
+
+
+def gbgc_output_init(n_rate, c_rate, gbc, Z, B, missing, burn: int):
+    """The GBGC variant's Output_init summaries on a given chain (pa_gbgc_output_init, host-only): (med [3], P(B) [N], P(Z) [N, 4])."""
+    lib = load_library()
+    n_rate, c_rate, gbc = (np.ascontiguousarray(x, dtype=np.float64) for x in (n_rate, c_rate, gbc))
+    T = len(n_rate)
+    Z = np.ascontiguousarray(Z, dtype=np.int8).reshape(T, -1)
+    N = Z.shape[1]
+    B = np.ascontiguousarray(B, dtype=np.int8).reshape(T, N)
+    missing = np.ascontiguousarray(missing, dtype=np.uint8)
+    med, pb, pz = np.zeros(3), np.zeros(N), np.zeros((N, 4))
+    _check(lib.pa_gbgc_output_init(N, burn, T - burn, n_rate.ctypes.data_as(_f64p), c_rate.ctypes.data_as(_f64p), gbc.ctypes.data_as(_f64p),
+                                   Z.ctypes.data_as(_i8p), B.ctypes.data_as(_i8p), missing.ctypes.data_as(_u8p), med.ctypes.data_as(_f64p),
+                                   pb.ctypes.data_as(_f64p), pz.ctypes.data_as(_f64p)))
+    return med, pb, pz
 
 
 def gbgc_transition(Q, sel, bias, t, device: int = 0):

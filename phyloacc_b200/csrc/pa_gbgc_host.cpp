@@ -66,6 +66,36 @@ struct GbgcChainView {
   const ElemPlan* plan;
 };
 
+// BPP_C::Output_init of the GBGC variant (bpp_c2.cpp:603-650): the tail of each rate trace is sorted and element T / 2 of the WHOLE trace is
+// reported as the "median"; P(B = 1) and P(Z = -1, 0, 1, 2) per node from the post-burn-in samples, with P(Z = -1) set to 1 for a missing node
+// on top of whatever its samples counted.  med = {n_rate, c_rate, gBC}.
+void gbgc_output_init(int T, int N, int burn, const double* n_rate, const double* c_rate, const double* gbc, const int8_t* Z, const int8_t* B,
+                      const uint8_t* missing, double* med3, double* post_b, double* post_z) {
+  const int mcmc = T - burn;
+  auto med = [&](const double* x) {
+    std::vector<double> v(x, x + T);
+    std::sort(v.begin() + burn, v.end());
+    return v[T / 2];
+  };
+  med3[0] = med(n_rate);
+  med3[1] = med(c_rate);
+  med3[2] = med(gbc);
+  std::vector<int> cz((size_t)N * 4, 0), cb(N, 0);  // row by row: the traces are [T][N]
+  for (int m = burn; m < T; m++) {
+    const int8_t* zr = Z + (size_t)m * N;
+    const int8_t* br = B + (size_t)m * N;
+    for (int s = 0; s < N; s++) {
+      cz[(size_t)s * 4 + zr[s] + 1]++;
+      cb[s] += br[s];
+    }
+  }
+  for (int s = 0; s < N; s++) {
+    if (missing[s]) cz[(size_t)s * 4] = mcmc;
+    for (int q = 0; q < 4; q++) post_z[(size_t)s * 4 + q] = (double)cz[(size_t)s * 4 + q] / mcmc;
+    post_b[s] = (double)cb[s] / mcmc;
+  }
+}
+
 // BPP_C::Eval2 of the GBGC variant (bpp_c2.cpp:29-285)
 double gbgc_eval2(const GbgcChainView& v, const int8_t* maxZ, double max_loglik) {
   const int T = v.T, N = v.N, burn = v.burn, mcmc = v.mcmc;
@@ -202,6 +232,14 @@ extern "C" int pa_gbgc_eval2(int32_t N, int32_t burn, int32_t mcmc, int32_t resz
   return PA_OK;
 }
 
+// The variant's Output_init summaries on a given chain (host-only; parity tests against the reference's own writer)
+extern "C" int pa_gbgc_output_init(int32_t N, int32_t burn, int32_t mcmc, const double* n_rate, const double* c_rate, const double* gbc, const int8_t* Z,
+                                   const int8_t* B, const uint8_t* missing, double* med3_out, double* post_b_out, double* post_z_out) {
+  if (N <= 0 || burn < 0 || mcmc < 1 || !n_rate || !c_rate || !gbc || !Z || !B || !missing || !med3_out || !post_b_out || !post_z_out) return PA_ERR_ARG;
+  pa::gbgc_output_init(burn + mcmc, N, burn, n_rate, c_rate, gbc, Z, B, missing, med3_out, post_b_out, post_z_out);
+  return PA_OK;
+}
+
 namespace pa {
 
 int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, int32_t n_targets, const pa_gbgc_params* prm, int model_mask,
@@ -327,31 +365,8 @@ int Engine::gbgc_run(const int32_t* ids, int32_t n_ids, const int32_t* targets, 
       mz[s] = best_m >= 0 ? Z[(size_t)best_m * N + s] : (int8_t)-1;
       mb[s] = best_m >= 0 ? B[(size_t)best_m * N + s] : (int8_t)0;
     }
-    // Output_init: the tail of each rate trace is sorted and element T / 2 of the WHOLE trace is reported (bpp_c2.cpp:606-613)
-    auto med = [&](const double* x) {
-      std::vector<double> v(x, x + T);
-      std::sort(v.begin() + burn, v.end());
-      return v[T / 2];
-    };
-    out->med[im * 3 + 0] = med(d + 3 * (size_t)T);
-    out->med[im * 3 + 1] = med(d + 2 * (size_t)T);
-    out->med[im * 3 + 2] = med(d + 4 * (size_t)T);
-    {
-      std::vector<int> cz((size_t)N * 4, 0), cb(N, 0);  // row by row: the traces are [T][N]
-      for (int m = burn; m < T; m++) {
-        const int8_t* zr = Z.data() + (size_t)m * N;
-        const int8_t* br = B.data() + (size_t)m * N;
-        for (int s = 0; s < N; s++) {
-          cz[(size_t)s * 4 + zr[s] + 1]++;
-          cb[s] += br[s];
-        }
-      }
-      for (int s = 0; s < N; s++) {
-        if (pl.missing[s]) cz[(size_t)s * 4] = mcmc;
-        for (int q = 0; q < 4; q++) out->post_z[(im * N + s) * 4 + q] = (double)cz[(size_t)s * 4 + q] / mcmc;
-        out->post_b[im * N + s] = (double)cb[s] / mcmc;
-      }
-    }
+    gbgc_output_init(T, N, burn, d + 3 * (size_t)T, d + 2 * (size_t)T, d + 4 * (size_t)T, Z.data(), B.data(), pl.missing.data(), out->med + im * 3,
+                     out->post_b + im * N, out->post_z + im * N * 4);
     GbgcChainView v{T, N, burn, mcmc, chain_resz[c], d, d + T, d + 2 * (size_t)T, d + 3 * (size_t)T, d + 4 * (size_t)T, Z.data(), B.data(), &pl};
     out->loglik[im] = gbgc_eval2(v, mz, best);
     out->accept[im * 2] = (int32_t)hd[1];

@@ -1,7 +1,9 @@
 """The GBGC variant's Eval2 (host code of pa_engine_gbgc_run, exposed as pa_gbgc_eval2) against the REFERENCE'S OWN Eval2
 (src/PhyloAcc-ST-GBGC/SRC/bpp_c2.cpp:29-285, driven through oracle/_ref/gbgc_probe `eval2`) on the same chains: numpy-oracle chains of
 two elements under the three models, plus edited traces that force the estimator's other branches (a single Z configuration; no
-configuration above the 5 % weight: the q(r) q(Z) fallback; configurations seen fewer than 11 times: diagonal covariance).  CPU only."""
+configuration above the 5 % weight: the q(r) q(Z) fallback; configurations seen fewer than 11 times: diagonal covariance).  The same chains
+go through the reference's own Output_init (the row of _rate_postZ_<resZ>.txt: "medians" of the three rates, P(B), P(Z) per node with its
+rule for missing nodes) and through pa_gbgc_output_init: equal at the file's 6 significant digits.  CPU only."""
 import os
 import subprocess
 
@@ -18,7 +20,7 @@ MODELS = (0, 2, 1)
 
 
 def _reference_eval2(case, c, requests, tmp):
-    """requests: [(resZ, burn, trace dict)] -> [estimate]"""
+    """requests: [(resZ, burn, trace dict)] -> ([Eval2 estimate], [the row Output_init writes, split at tabs])"""
     lines = [f"element {c}"]
     for k, (resZ, burn, tr) in enumerate(requests):
         path = os.path.join(tmp, f"trace_{c}_{k}.txt")
@@ -28,11 +30,13 @@ def _reference_eval2(case, c, requests, tmp):
                 f.write(" ".join([repr(float(tr[k][m])) for k in ("full", "c", "n", "gb")] +  # repr round-trips a double exactly (operator>> reads no hex floats)
                                  [str(int(z)) for z in tr["Z"][m]] + [str(int(b)) for b in tr["B"][m]]) + "\n")
         lines.append(f"eval2 {resZ} {burn} {T - burn} {path}")
+        lines.append(f"output_init {resZ} {burn} {T - burn} {path}")
     script = os.path.join(tmp, f"script_{c}.txt")
     with open(script, "w") as f:
         f.write("\n".join(lines) + "\n")
     r = subprocess.run([PROBE, case.cfg, script], capture_output=True, text=True, check=True)
-    return [float.fromhex(l.split()[2]) for l in r.stdout.split("\n") if l.startswith("eval2 ")]
+    rows = [l.split("\t")[1:] for l in r.stdout.split("\n") if l.startswith("output_init ")]
+    return [float.fromhex(l.split()[2]) for l in r.stdout.split("\n") if l.startswith("eval2 ")], rows
 
 
 @pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/gbgc_probe not built (make -C oracle ref-gbgc)")
@@ -70,8 +74,13 @@ def test_host_eval2_matches_the_reference(native_lib, tmp_path):
                 for m in range(len(few["full"])):
                     few["Z"][m, el.nodes[:4]] = [((m // 8) >> b) & 1 for b in range(4)]
                 reqs.append((1, burn, few))
-        want = _reference_eval2(case, c, reqs, str(tmp_path))
-        assert len(want) == len(reqs)
+        want, rows = _reference_eval2(case, c, reqs, str(tmp_path))
+        assert len(want) == len(reqs) == len(rows)
+        for (resZ, b0, tr), row in zip(reqs, rows):
+            # the reference's own _rate_postZ row for this chain (Output_init) against pa_gbgc_output_init, at the file's 6 significant digits
+            med, pb, pz = pab.gbgc_output_init(tr["n"], tr["c"], tr["gb"], tr["Z"], tr["B"], el.missing, b0)
+            mine = [f"{x:.6g}" for x in np.concatenate([med, pb, pz.ravel()])]
+            assert row[0] == str(c) and [f"{float(x):.6g}" for x in row[1:]] == mine, (c, resZ)
         for (resZ, b0, tr), w in zip(reqs, want):
             got, _ = pab.gbgc_eval2(tr["full"], tr["c"], tr["n"], tr["gb"], tr["Z"], tr["B"], el.nodes, el.missing, b0, resZ)
             assert np.isfinite(w) == np.isfinite(got)
