@@ -172,6 +172,26 @@ int main(int argc, char** argv) {
       string row;
       getline(rf, row);
       printf("output_init %d\t%s\n", resZ, row.c_str());
+    } else if (cmd == "monitor") {
+      // monitor <resZ> <loglik> <sel_c> <sel_n> <gbc> Z[N] B[N]: what Gibbs records for a state -- log P(constraints) of initMCMC
+      // (GBGC/SRC/bpp_c.cpp:232-254), logp_Z = prior_Z(Z) - logpZC (:273, bpp_c2.cpp:484-498) and MonitorChain's log P(X, Z, B, r)
+      // (bpp_c.cpp:598-652) given the state's log P(X | Z, B, r)
+      if (filter) { printf("monitor skipped\n"); continue; }
+      int resZ; double ll, sc, sn, gb;
+      ss >> resZ >> ll >> sc >> sn >> gb;
+      const int N = bpp.N;
+      fflush(stdout);
+      freopen("/dev/null", "w", stdout);
+      el.initMCMC(0, bpp, resZ);
+      for (int s2 = 0; s2 < N; s2++) { int z; ss >> z; el.Z[s2] = z; }
+      for (int s2 = 0; s2 < N; s2++) { int b; ss >> b; el.isGB[s2] = (b != 0); }
+      const double lpz = el.prior_Z(el.Z) - el.logpZC;
+      el.trace_loglik[1] = ll; el.trace_c_rate[1] = sc; el.trace_n_rate[1] = sn; el.trace_n_GB[1] = gb;
+      int a1 = 0, a2 = 0;
+      el.MonitorChain(1, true, a1, a2, bpp, lpz, resZ);
+      fflush(stdout);
+      dup2(fileno(real_stdout), fileno(stdout));
+      printf("monitor %d %a %a %a\n", resZ, el.trace_full_loglik[1], lpz, el.logpZC);
     } else if (cmd == "integ") {
       // integ <resZ> <sel_c> <sel_n> <gbc> Z[N] B[N]: the evaluations of one Gibbs iteration that do not involve random numbers, at a given
       // state -- expected parent / child base pairs per branch (Update_Tg(g, ., ., true), GBGC/SRC/bpp_c.cpp:530-583), the six

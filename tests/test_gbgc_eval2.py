@@ -89,3 +89,39 @@ def test_host_eval2_matches_the_reference(native_lib, tmp_path):
             n_checked += 1
     assert n_checked == 12
     case.close()
+
+
+@pytest.mark.skipif(not os.path.exists(PROBE), reason="oracle/_ref/gbgc_probe not built (make -C oracle ref-gbgc)")
+def test_recorded_full_loglik_and_prior_of_z_match_the_reference(tmp_path):
+    """What a chain RECORDS for a state: log P(constraints) of initMCMC, logp_Z = prior_Z(Z) - log P(constraints) and MonitorChain's
+    log P(X, Z, B, r).  The CUDA chain is compared draw for draw with oracle/gbgc.py; here the numpy formulas are pinned against the
+    reference's own initMCMC / prior_Z / MonitorChain (gbgc_probe `monitor`) at the states a short chain visits, under the three models."""
+    case = Case("gbgc_chain43")
+    tree = case.tree
+    targets = [tree.names.index(x) for x in case.P.TARGETSPECIES.split(";") if x]
+    Q0 = np.asarray(tree.Q, float).reshape(4, 4)
+    n = 0
+    for c in (0, 7):
+        el = case.element(c)
+        lines, want = [f"element {c}"], []
+        for mdl in range(3):
+            par = gbgc.GbgcParams(num_burn=4, num_mcmc=14)
+            ch = gbgc.GbgcChain(Q0, tree.pi, el, tree.N, tree.S, MODELS[mdl], targets, case.model.upper, par, 77, c * 4 + MODELS[mdl])
+            tr = ch.run()
+            for m in (0, 5, 11, 17):
+                Z, B = tr["Z"][m], tr["B"][m]
+                lines.append(f"monitor {MODELS[mdl]} {float(tr['loglik'][m])!r} {float(tr['c'][m])!r} {float(tr['n'][m])!r} {float(tr['gb'][m])!r} " +
+                             " ".join(str(int(z)) for z in Z) + " " + " ".join(str(int(b)) for b in B))
+                want.append((float(tr["full"][m]), float(ch.prior_z(Z) - tr["logp_zc"]), float(tr["logp_zc"])))
+        script = os.path.join(str(tmp_path), f"mon_{c}.txt")
+        with open(script, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        r = subprocess.run([PROBE, case.cfg, script], capture_output=True, text=True, check=True)
+        got = [[float.fromhex(x) for x in l.split()[2:5]] for l in r.stdout.split("\n") if l.startswith("monitor ")]
+        assert len(got) == len(want) == 12
+        for g, w in zip(got, want):
+            assert abs(g[2] - w[2]) <= 1e-12 * abs(w[2]) and abs(g[1] - w[1]) <= 1e-12 * max(1.0, abs(w[1])), (g, w)
+            assert abs(g[0] - w[0]) <= 1e-12 * abs(w[0]), (g, w)
+            n += 1
+    assert n == 24
+    case.close()
