@@ -115,6 +115,15 @@ def test_expected_pairs_and_zb_integration_match_reference():
     for r, d in zip(reqs, dumps):
         assert d["resZ"] == r["integ"]
         el = case.element(r["c"])
+        # the model's constraints as BPP_C::initMCMC sets them (GBGC/SRC/bpp_c.cpp:143-180) and the 3 x 3 tables of Z
+        targets = [case.tree.names.index(x) for x in case.P.TARGETSPECIES.split(";") if x]
+        fz = gbgc.gbgc_fixz(el, case.tree.N, case.tree.S, d["resZ"], targets)
+        assert all(int(fz[s]) == int(d["fixZ"][s]) for s in el.nodes), (r["c"], d["resZ"])
+        mine = gbgc._tm_int(el, case.tree.N, case.model.upper, 0.8, 0.1)  # PREP_GRATE / PREP_LRATE defaults of the probe's BPP
+        for s in el.nodes[:-1]:
+            w, g = np.asarray(d["tmint"][s]), np.asarray(mine[s])
+            fin = np.isfinite(w)
+            assert w.shape == g.shape and np.array_equal(fin, np.isfinite(g)) and np.allclose(g[fin], w[fin], rtol=1e-14, atol=0), (r["c"], s)
         post = gbgc.expected_pairs(Q0, pi, el, d["Z"], r["B"], r["sel_c"], r["sel_n"], r["gbc"])
         for s, want in d["post"].items():
             assert np.allclose(post[s], want, rtol=1e-9, atol=1e-12), (r["c"], d["resZ"], s)
