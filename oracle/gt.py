@@ -50,6 +50,12 @@ def parse_probe(text: str):
                 st["cross"][int(f[1])] = list(zip(v[0::2], v[1::2]))
             elif k == "coal":
                 st["coalesce"][int(f[1])] = [int(x) for x in f[2:]]
+            elif k == "tg":  # sampled history: species -> {gene lineage: base at the bottom of its piece in that species, per column}
+                st.setdefault("tg", {}).setdefault(int(f[1]), {})[int(f[2])] = np.array([int(x) for x in f[3:]], dtype=np.int8)
+            elif k == "amb":  # an ambiguity-coded tip column: the allowed bases
+                st.setdefault("amb", {})[(int(f[1]), int(f[2]))] = np.array([int(x) for x in f[3:7]])
+            elif k == "emission":
+                st.setdefault("emission", {})[int(f[1])] = np.array([float.fromhex(x) for x in f[2:5]])
             elif k in ("loglik", "logpz", "prior"):
                 st[k] = float.fromhex(f[1])
             elif k == "end":
@@ -156,3 +162,95 @@ def replay_loglik(st, hdr, masks):
 
     root = up(st["root"])
     return float(np.sum(np.log(root @ pi)))
+
+
+def _lse(v):
+    m = np.max(v)
+    return -np.inf if m == -np.inf else float(np.log(np.sum(np.exp(v - m))) + m)
+
+
+def emission(st, hdr, GG):
+    """BPP_C::getEmission of PhyloAcc-GT (bpp_c.cpp:1043-1216): log P(what happened inside species branch ss | Z[ss] = k) for k = background,
+    conserved, accelerated, GIVEN one sampled history (st["tg"]): the loss / no-loss terms of the lineages that start in the branch, and for
+    every column the probability of the sampled states at the top of the branch given the states at its bottom, with the coalescence nodes
+    INSIDE the branch summed out by a small pruning pass.  GG = number of columns.  Returns {species: [3]}."""
+    N, S, h, par = hdr["N"], hdr["S"], hdr["heights"], hdr["parent"]
+    Q = hdr["Q"].reshape(4, 4)
+    gh, mis, gc, tg = st["gheights"], st["gmissing"], st["gchild"], st["tg"]
+    rates = (1.0, st["c_rate"], st["n_rate"])
+    lc, ln = st["cons_to_mis"], st["ncons_to_mis"]
+    amb = st.get("amb", {})  # (tip, column) -> allowed bases, in the history's own column order
+    out = {}
+
+    def log_tm(length, rate):  # [child base i, parent base j] = log P(j -> i), as BPP::getlogTMc lays it out
+        if length < 0:
+            length = 1e-9
+        with np.errstate(divide="ignore"):
+            return np.log(transition(Q, rate * length)).T
+
+    for ss in sorted(st["cross"]):
+        lin = st["cross"][ss]
+        sp = int(par[ss])
+        em = np.zeros(3)
+        for first, _ in lin:  # bpp_c.cpp:1083-1117
+            if first < S or gh[first] >= h[ss]:
+                if mis[first]:
+                    em += np.log([ln, lc, ln])
+                else:
+                    em += np.log([1 - ln, 1 - lc, 1 - ln])
+        base = {}
+        for gs, _ in lin:  # lineages that enter the branch from below: indicator of their sampled state (or the tip's own vector)
+            if gh[gs] <= h[ss]:
+                tl = np.zeros((GG, 4))
+                if not mis[gs]:
+                    t = tg[ss][gs]
+                    for g in range(GG):
+                        if t[g] >= 4:
+                            continue
+                        tl[g] = -np.inf
+                        if t[g] == -1:
+                            with np.errstate(divide="ignore"):
+                                tl[g] = np.log(amb[(gs, g)].astype(float))
+                        elif ss >= S:
+                            tl[g, t[g]] = 0.0
+                base[gs] = tl
+        for rr in range(3):
+            e = em[rr]
+            templ = dict(base)
+            for gs in st["coalesce"].get(ss, []):
+                acc = np.zeros((GG, 4))
+                for chi in gc[gs]:
+                    if mis[chi]:
+                        continue
+                    tm = log_tm(gh[gs] - max(gh[chi], h[ss]), rates[rr])
+                    t = tg[ss][chi]
+                    for g in range(GG):
+                        if t[g] >= 4:
+                            continue
+                        x = tm + templ[chi][g][:, None]
+                        m = x.max()
+                        acc[g] += np.full(4, -np.inf) if m == -np.inf else np.log(np.exp(x - m).sum(axis=0)) + m
+                templ[gs] = acc
+            if sp < N:
+                for first, second in lin:
+                    if first != second or mis[first]:
+                        continue
+                    tm = log_tm(h[sp] - max(gh[first], h[ss]), rates[rr])
+                    tb, tt = tg[ss][first], tg[sp][first]
+                    for g in range(GG):
+                        if tb[g] >= 4:
+                            continue
+                        if ss >= S or tb[g] == -1:
+                            e += _lse(tm[:, tt[g]] + templ[first][g])
+                        else:
+                            e += tm[tb[g], tt[g]]
+            else:
+                root = st["root"]
+                if not mis[ss]:
+                    t = tg[ss][root]
+                    for g in range(GG):
+                        if t[g] < 4:
+                            e += templ[root][g][t[g]]
+            em[rr] = e
+        out[ss] = em
+    return out

@@ -12,7 +12,10 @@
 //     (bpp_c.cpp:385-440), and the log-likelihood  sum_g log_exp_sum(lambda[N-1][root][g].col(2) + log_pi)
 // It pins oracle/gt.py and the CUDA kernel behind pa_engine_gt_replay.
 //
-// usage: gt_probe <cfg> <script>    script lines: "element <c>", "state <resZ> <coal 0|1> <n_rate> <c_rate> Z[N]"
+//   * with "hist 1": one draw of the substitution history on the embedded tree (Update_Tg(.., true, ..), genetree.cpp:1419-1533, the shim's
+//     random stream) and, GIVEN that history, the Z emissions of every species branch under the three classes
+//     (BPP_C::getEmission, bpp_c.cpp:1043-1216) -- a deterministic function of the dumped history
+// usage: gt_probe <cfg> <script>    script lines: "element <c>", "state <resZ> <coal 0|1> <n_rate> <c_rate> Z[N] [hist]"
 #include <dirent.h>
 #include <math.h>
 #include <stdio.h>
@@ -142,6 +145,9 @@ int main(int argc, char** argv) {
       ss >> resZ >> coal >> nr >> cr;
       vector<int> Zin(N);
       for (int s = 0; s < N; s++) ss >> Zin[s];
+      string hist_flag;
+      ss >> hist_flag;
+      const bool hist = hist_flag == "hist";
       freopen("/dev/null", "w", stdout);
       bpp.cur_Z[resZ][el->CC] = Zin;
       bpp.cur_nrate[el->CC] = nr;
@@ -172,6 +178,11 @@ int main(int argc, char** argv) {
       for (int g = 0; g < GG; g++) ll += BPP::log_exp_sum(gt->lambda[N - 1][gt->root][g].col(2) + el->log_pi);
       const double lpz = gt->get_logpZ1(bpp, el->Z, el->consToMis, el->nconsToMis);
       const double prior = gt->priorTree(bpp);
+      if (hist) {
+        gt->Update_Tg(GG, visited, bpp, true, el->nodes, el->Z, el->trace_n_rate[0], el->trace_c_rate[0], el->log_pi, el->eigenvec, el->eigenval, el->eigeninv);
+        el->m = 0;
+        el->getEmission(GG, bpp);
+      }
       fflush(stdout);
       dup2(fileno(real_stdout), fileno(stdout));
       printf("state resZ %d coal %d root %d\n", resZ, coal, gt->root);
@@ -199,6 +210,29 @@ int main(int argc, char** argv) {
         printf("coal %d", s);
         for (size_t k = 0; k < gt->temp_coal[s].size(); k++) printf(" %d", gt->temp_coal[s][k]);
         printf("\n");
+      }
+      if (hist) {
+        for (int s = 0; s < N; s++)
+          for (map<int, vector<int> >::iterator it = gt->Tg[s].begin(); it != gt->Tg[s].end(); it++) {
+            printf("tg %d %d", s, it->first);
+            for (int g = 0; g < GG; g++) printf(" %d", it->second[g]);
+            printf("\n");
+          }
+        // tips with an ambiguity code (Tg = -1): the bases the code allows, in the probe's own column order (the GT front-end moves
+        // columns: blocks of identical sites first)
+        for (int s = 0; s < S; s++) {
+          if (gt->Tg[s].find(s) == gt->Tg[s].end()) continue;
+          for (int g = 0; g < GG; g++)
+            if (gt->Tg[s][s][g] == -1) {
+              printf("amb %d %d", s, g);
+              for (int b = 0; b < 4; b++) printf(" %d", gt->lambda[s][s][g](b, 2) == 0 ? 1 : 0);
+              printf("\n");
+            }
+        }
+        for (size_t k = 0; k < el->nodes.size(); k++) {
+          const int s = el->nodes[k];
+          printf("emission %d %a %a %a\n", s, el->log_emission[s][0], el->log_emission[s][1], el->log_emission[s][2]);
+        }
       }
       printf("loglik %a\nlogpz %a\nprior %a\nend\n", ll, lpz, prior);
     }

@@ -59,6 +59,23 @@ def main():
         f.write("\n".join(lines) + "\n")
     with open(os.path.join(OUT, "probe.txt"), "w") as f:
         f.write(r.stdout)
+    # a second, separate run: two states per element (species topology, coalescent draw) with one sampled substitution history each and the
+    # Z emissions BPP_C::getEmission derives from it ("hist")
+    rng = np.random.default_rng(2)
+    hlines = []
+    for c in range(batch.C):
+        hlines.append(f"element {c}")
+        for k in range(2):
+            Z = rng.integers(0, 3, N)
+            hlines.append(f"state 1 {k} {0.5 + rng.random() * 2:.6f} {0.1 + rng.random() * 0.8:.6f} " + " ".join(map(str, Z)) + " hist")
+    hscript = os.path.join(work, "script_hist.txt")
+    with open(hscript, "w") as f:
+        f.write("\n".join(hlines) + "\n")
+    rh = subprocess.run([PROBE, cfg, hscript], capture_output=True, text=True, check=True)
+    with open(os.path.join(OUT, "script_hist.txt"), "w") as f:
+        f.write("\n".join(hlines) + "\n")
+    with open(os.path.join(OUT, "probe_hist.txt"), "w") as f:
+        f.write(rh.stdout)
     print("wrote", OUT, len(r.stdout), "bytes of probe output")
 
 

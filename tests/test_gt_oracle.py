@@ -144,3 +144,24 @@ def test_gt_replay_on_the_species_tree_equals_the_st_replay(native_lib, tmp_path
     ll_st = eng.loglik_replay(elem, np.asarray(Zs), nr, cr)
     assert np.all(np.isfinite(ll_st)) and np.all(np.abs(ll_gt - ll_st) <= 1e-10 * np.abs(ll_st)), np.abs(ll_gt / ll_st - 1).max()
     eng.close()
+
+
+def test_emissions_given_a_sampled_history_match_reference():
+    """tests/golden/gt12/probe_hist.txt: per element one species-topology and one coalescent gene tree, each with ONE substitution history
+    drawn by the reference (GTree::Update_Tg(.., true, ..)) and the Z emissions BPP_C::getEmission (bpp_c.cpp:1043-1216) derives from it.  The
+    emissions are a deterministic function of the dumped history: oracle/gt.py:emission restates them (loss terms, entry / exit states of
+    every lineage of a species branch, the coalescences inside the branch summed out) -- 1e-12 on all three classes of every species."""
+    with open(os.path.join(GOLD, "probe_hist.txt")) as f:
+        hdr, els = gt.parse_probe(f.read())
+    case = Case("gt12")
+    n = 0
+    for e in els:
+        el = case.element(e["c"])
+        for st in e["states"]:
+            got = gt.emission(st, hdr, el.GG)
+            assert set(st["emission"]) <= set(got)
+            for s, want in st["emission"].items():
+                assert np.all(np.abs(got[s] - want) <= 1e-12 * np.maximum(1.0, np.abs(want))), (e["c"], st["coal"], s, got[s], want)
+                n += 1
+    assert n >= 8 * 20
+    case.close()
